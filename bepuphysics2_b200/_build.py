@@ -1,0 +1,71 @@
+"""Builds the native libraries in-tree (the .so files travel to the GPU box with the repo snapshot).
+
+    libbepucuda.so   hand-written sm_100a CUDA kernels + the C ABI of include/bepucuda.h
+    libbepuhost.so   C++ host-side mirror of the reference's Bodies/Solver/Timestepper slice (links libbepucuda)
+
+nvcc cross-compiles for sm_100a without a GPU. The solver kernels are compiled twice: once with FMA contraction
+(`bepu_fast`) and once with -fmad=false (`bepu_strict`, bit-exact against a non-contracting CPU evaluation).
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(CSRC, "build")
+LIB_CUDA = os.path.join(HERE, "libbepucuda.so")
+LIB_HOST = os.path.join(HERE, "libbepuhost.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+GXX = "/usr/bin/g++"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", GXX]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build(force=False, verbose=False):
+    os.makedirs(BUILD, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
+    headers.append(os.path.join(HERE, "..", "include", "bepucuda.h"))
+    units = [
+        ("solver_fast.o", "bepu_solver_kernels.cu", ["-DBEPU_NS=bepu_fast"]),
+        ("solver_strict.o", "bepu_solver_kernels.cu", ["-DBEPU_NS=bepu_strict", "-fmad=false"]),
+        ("layout.o", "bepu_layout_kernels.cu", []),
+        ("api.o", "bepucuda_api.cu", []),
+    ]
+    jobs = []
+    for obj, src, extra in units:
+        o = os.path.join(BUILD, obj)
+        s = os.path.join(CSRC, src)
+        if force or _newer(o, [s] + headers):
+            jobs.append([NVCC] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            for out in ex.map(_run, jobs):
+                if verbose and out.strip():
+                    print(out)
+    objs = [os.path.join(BUILD, u[0]) for u in units]
+    if force or _newer(LIB_CUDA, objs):
+        _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB_CUDA] + objs)
+    host_src = os.path.join(CSRC, "host", "bepu_host.cpp")
+    if force or _newer(LIB_HOST, [host_src, LIB_CUDA] + headers):
+        _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB_HOST, host_src, "-L" + HERE, "-lbepucuda", "-Wl,-rpath,$ORIGIN"])
+    return LIB_CUDA, LIB_HOST
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", LIB_CUDA, LIB_HOST)

@@ -1,0 +1,185 @@
+// Layout conversion and topology analysis kernels of libbepucuda (no constraint numerics here, compiled once):
+//   - BodyDynamics 128-B AOS (BepuPhysics/BodyProperties.cs:L318-338)  <->  four arrays of 32-B records
+//   - reference AOSOA-W type batch buffers (Constraints/TypeBatch.cs:L10-27)  <->  device AOSOA-32
+//   - integration ownership (Solver_Solve.cs:L951-1044,L1072-1388) and the batch invariant check
+#include "bepu_layout_kernels.h"
+
+namespace bepucuda {
+
+// One thread per float4 of the AOS record: fully coalesced 128-B-per-body reads.
+//   float4 0,1 -> pose | 2,3 -> velocity | 4,5 -> local inertia | 6,7 -> world inertia
+__global__ void split_bodies_kernel(const float4* __restrict__ raw, int body_count, BodyBuffers B) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)body_count * 8) return;
+    const size_t body = t >> 3;
+    const int part = (int)(t & 7);
+    float4 v = raw[t];
+    if (part == 1 || part == 2 || part == 3) v.w = 0.0f;  // padding floats carry no meaning
+    if (part == 5) v.w = 0.0f;
+    if (part == 7) v.w = 0.0f;
+    float4* dst = part < 2 ? B.pose : part < 4 ? B.velocity : part < 6 ? B.inertia_local : B.inertia_world;
+    dst[body * 2 + (part & 1)] = v;
+}
+
+// Writes pose, velocity and world inertia back into the retained raw AOS image; local inertia and padding stay as uploaded.
+__global__ void merge_bodies_kernel(float4* __restrict__ raw, int body_count, BodyBuffers B) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)body_count * 8) return;
+    const size_t body = t >> 3;
+    const int part = (int)(t & 7);
+    if (part == 4 || part == 5) return;
+    const float4* src = part < 2 ? B.pose : part < 4 ? B.velocity : B.inertia_world;
+    float4 v = src[body * 2 + (part & 1)];
+    float4 old = raw[t];
+    if (part == 1 || part == 2 || part == 3 || part == 7) v.w = old.w;  // keep the host's padding bits
+    raw[t] = v;
+}
+
+// AOSOA-W (reference layout: [bundleW][row][W]) <-> AOSOA-32 for every device type batch in one launch.
+// One warp per destination bundle; lane = destination constraint slot. `map` (fallback levels only) gives the source
+// constraint index of each destination slot, -1 = padding; without a map slot i is source constraint i.
+// For W = 8 a warp reads four 32-B sectors per row (sector-efficient) and writes one 128-B line per row.
+__global__ void transpose_in_all_kernel(const DeviceTypeBatch* __restrict__ tbs, const TransposeDesc* __restrict__ descs, const WorkItem* __restrict__ work, int work_count,
+                                        int W, int what) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const TransposeDesc d = descs[w.type_batch];
+    const int slot = w.bundle * 32 + lane;
+    int c = d.map ? d.map[slot] : slot;
+    if (c >= d.src_count) c = -1;
+    const size_t sb = c < 0 ? 0 : (size_t)(c / W), sl = c < 0 ? 0 : (size_t)(c % W);
+    if (what & kTransposeRefs) {
+        int32_t* dst = tb.refs + (size_t)w.bundle * d.bodies * 32 + lane;
+        for (int r = 0; r < d.bodies; ++r) {
+            int32_t v = kRefEmpty;
+            if (c >= 0) {
+                v = d.src_refs[(sb * d.bodies + r) * W + sl];
+                v = v < 0 ? kRefEmpty : (int32_t)(((uint32_t)v & kRefIndexMask) | ((uint32_t)v & kRefKinematicBit));
+            }
+            dst[r * 32] = v;
+        }
+    }
+    if (what & kTransposePrestep) {
+        float* dst = tb.prestep + (size_t)w.bundle * d.prestep_rows * 32 + lane;
+        for (int r = 0; r < d.prestep_rows; ++r) dst[r * 32] = c < 0 ? 0.0f : d.src_prestep[(sb * d.prestep_rows + r) * W + sl];
+    }
+    if (what & kTransposeImpulses) {
+        float* dst = tb.impulses + (size_t)w.bundle * d.impulse_rows * 32 + lane;
+        for (int r = 0; r < d.impulse_rows; ++r) dst[r * 32] = c < 0 ? 0.0f : d.src_impulses[(sb * d.impulse_rows + r) * W + sl];
+    }
+}
+__global__ void transpose_out_all_kernel(const DeviceTypeBatch* __restrict__ tbs, const TransposeDesc* __restrict__ descs, const WorkItem* __restrict__ work, int work_count,
+                                         int W, int what) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const TransposeDesc d = descs[w.type_batch];
+    const int slot = w.bundle * 32 + lane;
+    const int c = d.map ? d.map[slot] : slot;
+    if (c < 0 || c >= d.src_count) return;
+    const size_t sb = (size_t)(c / W), sl = (size_t)(c % W);
+    if (what & kTransposePrestep) {
+        const float* src = tb.prestep + (size_t)w.bundle * d.prestep_rows * 32 + lane;
+        for (int r = 0; r < d.prestep_rows; ++r) d.src_prestep[(sb * d.prestep_rows + r) * W + sl] = src[r * 32];
+    }
+    if (what & kTransposeImpulses) {
+        const float* src = tb.impulses + (size_t)w.bundle * d.impulse_rows * 32 + lane;
+        for (int r = 0; r < d.impulse_rows; ++r) d.src_impulses[(sb * d.impulse_rows + r) * W + sl] = src[r * 32];
+    }
+}
+
+// Pass 1 over every (constraint, body slot): first_batch[body] = min device batch referencing it as a dynamic body;
+// per-body reference count and bitmask of synchronized batches for the batch-invariant check.
+__global__ void ownership_pass1_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
+                                       int sync_batch_count, int body_count, int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, int32_t* error_flag) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int nb = bodies_per_type[tb.type_id];
+    for (int s = 0; s < nb; ++s) {
+        const int32_t enc = tb.refs[((size_t)w.bundle * nb + s) * 32 + lane];
+        if (enc < 0 || (enc & kRefKinematicBit)) continue;
+        const int idx = enc & kRefIndexMask;
+        if (idx >= body_count) { atomicExch(error_flag, 2); continue; }
+        atomicMin(first_batch + idx, tb.device_batch);
+        if (tb.device_batch < sync_batch_count && tb.device_batch < 64) {
+            atomicAdd(sync_refcount + idx, 1);
+            atomicOr(sync_mask + idx, 1ull << tb.device_batch);
+        }
+    }
+}
+// Pass 2: set the integrate bit on the owning lane, mark constrained bodies.
+__global__ void ownership_pass2_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
+                                       int body_count, const int32_t* __restrict__ first_batch, uint8_t* constrained) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int nb = bodies_per_type[tb.type_id];
+    for (int s = 0; s < nb; ++s) {
+        int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
+        const int32_t enc = *r;
+        if (enc < 0) continue;
+        const int idx = enc & kRefIndexMask;
+        if (idx >= body_count) continue;
+        constrained[idx] = 1;  // kinematics referenced by constraints count as constrained too (Solver_Solve.cs:L1372-1381)
+        if (enc & kRefKinematicBit) continue;
+        if (first_batch[idx] == tb.device_batch) *r = (int32_t)((uint32_t)enc | kRefIntegrateBit);
+    }
+}
+__global__ void check_invariant_kernel(int body_count, const int32_t* __restrict__ sync_refcount, const unsigned long long* __restrict__ sync_mask, int32_t* error_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= body_count) return;
+    if (__popcll(sync_mask[i]) != sync_refcount[i]) atomicExch(error_flag, 1);
+}
+__global__ void mark_kinematics_kernel(const int32_t* __restrict__ kinematics, int count, int body_count, uint8_t* constrained, int32_t* error_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int idx = kinematics[i];
+    if (idx < 0 || idx >= body_count) { atomicExch(error_flag, 2); return; }
+    constrained[idx] = 1;
+}
+__global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+void launch_split_bodies(const void* raw, int body_count, const BodyBuffers& B, cudaStream_t s) {
+    if (body_count <= 0) return;
+    split_bodies_kernel<<<blocks_for((size_t)body_count * 8, 256), 256, 0, s>>>((const float4*)raw, body_count, B);
+}
+void launch_merge_bodies(void* raw, int body_count, const BodyBuffers& B, cudaStream_t s) {
+    if (body_count <= 0) return;
+    merge_bodies_kernel<<<blocks_for((size_t)body_count * 8, 256), 256, 0, s>>>((float4*)raw, body_count, B);
+}
+void launch_transpose_in_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s) {
+    if (work_count <= 0) return;
+    transpose_in_all_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, what);
+}
+void launch_transpose_out_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s) {
+    if (work_count <= 0) return;
+    transpose_out_all_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, what);
+}
+void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
+    if (n == 0) return;
+    fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, v);
+}
+void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
+                      int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
+                      int32_t* error_flag, cudaStream_t s) {
+    if (work_count > 0) {
+        ownership_pass1_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, sync_batch_count, body_count, first_batch,
+                                                                                         sync_refcount, sync_mask, error_flag);
+        ownership_pass2_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, body_count, first_batch, constrained);
+    }
+    if (body_count > 0) check_invariant_kernel<<<blocks_for(body_count, 256), 256, 0, s>>>(body_count, sync_refcount, sync_mask, error_flag);
+    if (kinematic_count > 0) mark_kinematics_kernel<<<blocks_for(kinematic_count, 128), 128, 0, s>>>(kinematics, kinematic_count, body_count, constrained, error_flag);
+}
+
+}  // namespace bepucuda

@@ -1,0 +1,40 @@
+// Launchers of the layout / topology kernels (bepu_layout_kernels.cu).
+#pragma once
+#include "bepu_device_types.h"
+
+namespace bepucuda {
+
+void launch_split_bodies(const void* raw, int body_count, const BodyBuffers& B, cudaStream_t s);
+void launch_merge_bodies(void* raw, int body_count, const BodyBuffers& B, cudaStream_t s);
+// Per device type batch: where its data lives in the uploaded reference-layout (AOSOA-W) image.
+struct TransposeDesc {
+    int32_t* src_refs;
+    float* src_prestep;
+    float* src_impulses;
+    const int32_t* map;   // destination slot -> source constraint index (fallback levels), or nullptr for identity
+    int32_t src_count;    // TypeBatch.ConstraintCount of the source
+    int32_t bodies, prestep_rows, impulse_rows;
+};
+enum { kTransposeRefs = 1, kTransposePrestep = 2, kTransposeImpulses = 4 };
+void launch_transpose_in_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s);
+void launch_transpose_out_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s);
+void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s);
+void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
+                      int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
+                      int32_t* error_flag, cudaStream_t s);
+
+// Numerics flavours (bepu_solver_kernels.cu, compiled twice).
+struct SolverLaunchers {
+    // Launches one constraint stage (kStageWarmStartFirst / kStageWarmStart / kStageSolve / kStageIncremental) over `work_count` bundles.
+    void (*constraint_stage)(int stage, const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
+    void (*kinematic_stage)(int stage, const int32_t* kinematics, int count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
+    void (*final_pose)(const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
+    // Persistent cooperative kernel: runs a whole stage program with a grid barrier between ops. Returns a cudaError_t.
+    int (*persistent)(const StageOp* program, int op_count, const DeviceTypeBatch* tbs, const WorkItem* work, const int32_t* kinematics, const BodyBuffers& B,
+                      const FrameParams* fp, unsigned int* barrier_state, cudaStream_t s);
+    int (*persistent_grid_size)(void);
+};
+const SolverLaunchers* get_launchers_bepu_fast();
+const SolverLaunchers* get_launchers_bepu_strict();
+
+}  // namespace bepucuda

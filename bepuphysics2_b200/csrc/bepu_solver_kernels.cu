@@ -1,0 +1,38 @@
+// Compiled twice: -DBEPU_NS=bepu_fast (default FMA contraction) and -DBEPU_NS=bepu_strict -fmad=false.
+#include "bepu_solver_kernels.cuh"
+#include "bepu_persistent.cuh"
+#include "bepu_layout_kernels.h"
+
+namespace BEPU_NS {
+
+static void launch_constraint_stage(int stage, const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s) {
+    if (work_count <= 0) return;
+    const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
+    switch (stage) {
+        case kStageWarmStartFirst: constraint_stage_kernel<kStageWarmStartFirst><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
+        case kStageWarmStart: constraint_stage_kernel<kStageWarmStart><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
+        case kStageSolve: constraint_stage_kernel<kStageSolve><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
+        case kStageIncremental: constraint_stage_kernel<kStageIncremental><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
+        default: break;
+    }
+}
+static void launch_kinematic_stage(int stage, const int32_t* kinematics, int count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s) {
+    if (count <= 0) return;
+    const unsigned blocks = (unsigned)((count + 127) / 128);
+    if (stage == kStageKinematicFirst) kinematic_stage_kernel<kStageKinematicFirst><<<blocks, 128, 0, s>>>(kinematics, count, B, fp);
+    else kinematic_stage_kernel<kStageKinematic><<<blocks, 128, 0, s>>>(kinematics, count, B, fp);
+}
+static void launch_final_pose(const BodyBuffers& B, const FrameParams* fp, cudaStream_t s) {
+    if (B.count <= 0) return;
+    final_pose_kernel<<<(unsigned)((B.count + 255) / 256), 256, 0, s>>>(B, fp);
+}
+
+static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent, &persistent_grid_size};
+
+}  // namespace BEPU_NS
+
+namespace bepucuda {
+#define BEPU_CAT2(a, b) a##b
+#define BEPU_CAT(a, b) BEPU_CAT2(a, b)
+const SolverLaunchers* BEPU_CAT(get_launchers_, BEPU_NS)() { return &BEPU_NS::kLaunchers; }
+}  // namespace bepucuda

@@ -1,0 +1,881 @@
+// libbepucuda host side: context, device memory, uploads/downloads, topology analysis, stage program, CUDA graph.
+// C ABI declared in include/bepucuda.h. No CPU fallback lives here: without a usable CUDA device bepucuda_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bepucuda.h"
+#include "bepu_layout_kernels.h"
+
+using namespace bepucuda;
+
+namespace bepucuda {
+
+// ---- type registry -------------------------------------------------------------------------------------------------------
+// bodies / prestep floats / impulse floats per BatchTypeId, and SURVEY.md §8d algorithmic bytes:
+//   solve       = 4 * (P + 2D + n + sum(R_i + W_i))        R/W from the type's Solve access filters
+//   warm start  = 4 * (P + D + n + sum(R'_i + W'_i))       (non-integrating lane, WarmStart filters)
+//   incremental = 4 * (P_read + contacts_written + n + 6n)
+// Filters (IBodyAccessFilter.cs:L38-126): pos 3, orientation 4, lin 3, ang 3, inertia tensor 6, mass 1.
+static TypeInfo make_contact(int bodies, int prestep, int impulses, int contacts, const char* name) {
+    TypeInfo t{};
+    t.bodies = bodies; t.prestep_rows = prestep; t.impulse_rows = impulses; t.incremental = 1; t.name = name;
+    const int body_rw = 13 + 6;  // AccessNoPose: velocity 6 + inertia 7 read, velocity 6 written
+    t.solve_bytes = 4 * (prestep + 2 * impulses + bodies + bodies * body_rw);
+    t.warm_start_bytes = 4 * (prestep + impulses + bodies + bodies * body_rw);
+    t.incremental_bytes = 4 * (prestep + contacts + bodies + 6 * bodies);
+    return t;
+}
+static TypeInfo make_joint(int bodies, int prestep, int impulses, int solve_r, int solve_w, int ws_r, int ws_w, const char* name) {
+    TypeInfo t{};
+    t.bodies = bodies; t.prestep_rows = prestep; t.impulse_rows = impulses; t.incremental = 0; t.name = name;
+    t.solve_bytes = 4 * (prestep + 2 * impulses + bodies + solve_r + solve_w);
+    t.warm_start_bytes = 4 * (prestep + impulses + bodies + ws_r + ws_w);
+    t.incremental_bytes = 0;
+    return t;
+}
+struct Registry {
+    TypeInfo types[64];
+    bool present[64];
+    Registry() {
+        std::memset(present, 0, sizeof(present));
+        auto add = [&](int id, TypeInfo t) { types[id] = t; present[id] = true; };
+        add(0, make_contact(1, 11, 4, 1, "Contact1OneBody")); add(1, make_contact(1, 15, 5, 2, "Contact2OneBody"));
+        add(2, make_contact(1, 19, 6, 3, "Contact3OneBody")); add(3, make_contact(1, 23, 7, 4, "Contact4OneBody"));
+        add(4, make_contact(2, 14, 4, 1, "Contact1")); add(5, make_contact(2, 18, 5, 2, "Contact2"));
+        add(6, make_contact(2, 22, 6, 3, "Contact3")); add(7, make_contact(2, 26, 7, 4, "Contact4"));
+        add(8, make_contact(1, 18, 6, 2, "Contact2NonconvexOneBody")); add(9, make_contact(1, 25, 9, 3, "Contact3NonconvexOneBody"));
+        add(10, make_contact(1, 32, 12, 4, "Contact4NonconvexOneBody"));
+        add(15, make_contact(2, 21, 6, 2, "Contact2Nonconvex")); add(16, make_contact(2, 28, 9, 3, "Contact3Nonconvex"));
+        add(17, make_contact(2, 35, 12, 4, "Contact4Nonconvex"));
+#define BEPU_REGISTER_JOINTS
+#include "bepu_joint_registry.inc"
+#undef BEPU_REGISTER_JOINTS
+    }
+};
+static const Registry& registry() {
+    static Registry r;
+    return r;
+}
+const TypeInfo* get_type_info(int type_id) {
+    if (type_id < 0 || type_id >= 64 || !registry().present[type_id]) return nullptr;
+    return &registry().types[type_id];
+}
+
+// ---- small RAII helpers ------------------------------------------------------------------------------------------------------
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t capacity = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= capacity) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        capacity = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) capacity = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        capacity = 0;
+    }
+    template <class T> T* as() const { return (T*)ptr; }
+};
+
+// Bump allocator over chunks that are never reallocated (uploads are enqueued against their addresses).
+struct ChunkArena {
+    struct Chunk { char* base; size_t size, used; };
+    std::vector<Chunk> chunks;
+    bool pinned_host = false;
+    size_t min_chunk = (size_t)64 << 20;
+    void reset() { for (auto& c : chunks) c.used = 0; }
+    void* alloc(size_t bytes, cudaError_t* err) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (auto& c : chunks)
+            if (c.size - c.used >= bytes) {
+                void* p = c.base + c.used;
+                c.used += bytes;
+                return p;
+            }
+        Chunk c{};
+        c.size = std::max(bytes, min_chunk);
+        cudaError_t e = pinned_host ? cudaMallocHost((void**)&c.base, c.size) : cudaMalloc((void**)&c.base, c.size);
+        if (e != cudaSuccess) { if (err) *err = e; return nullptr; }
+        c.used = bytes;
+        chunks.push_back(c);
+        return chunks.back().base;
+    }
+    void release() {
+        for (auto& c : chunks) { if (pinned_host) cudaFreeHost(c.base); else cudaFree(c.base); }
+        chunks.clear();
+    }
+};
+
+struct SourceTypeBatch {
+    int batch_index, type_batch_index, type_id, count;
+    int live = 0;          // constraints actually present (fallback type batches may contain holes)
+    float* host_impulses;
+    int32_t* raw_refs;     // device, reference AOSOA-W layout
+    float* raw_prestep;
+    float* raw_impulses;
+    size_t refs_bytes, prestep_bytes, impulse_bytes;
+    std::vector<int32_t> host_refs;  // retained only for fallback batches (levelisation)
+    std::vector<int> device_tbs;
+};
+
+}  // namespace bepucuda
+
+struct bepucuda_ctx {
+    bepucuda_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_solve_begin = nullptr, ev_solve_end = nullptr, ev_up_begin = nullptr, ev_up_end = nullptr, ev_down_begin = nullptr, ev_down_end = nullptr;
+    bool up_open = false, have_solve = false, have_down = false, have_up = false;
+    std::string error;
+    const SolverLaunchers* launchers = nullptr;
+
+    // solve description / integrator
+    std::vector<int32_t> iterations{1};
+    int fallback_threshold = 64;
+    bepucuda_integrator_desc integ{};
+    bool integ_set = false;
+
+    // bodies
+    int body_count = 0;
+    DeviceBuffer raw_bodies, pose, velocity, inertia_local, inertia_world, constrained, first_batch, sync_refcount, sync_mask;
+    BodyBuffers B{};
+
+    // constraints
+    int W = 8;
+    int batch_count = 0;
+    bool constraints_open = false, constraints_ready = false, data_dirty = false;
+    std::vector<SourceTypeBatch> sources;
+    ChunkArena raw_arena, pinned_arena;
+    DeviceBuffer refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
+    std::vector<DeviceTypeBatch> tbs;
+    std::vector<TransposeDesc> tdescs;
+    std::vector<WorkItem> work;                 // grouped by device batch, then the incremental list
+    std::vector<std::pair<int, int>> batch_work; // per device batch: (begin, count) into work
+    int inc_work_begin = 0, inc_work_count = 0;
+    int all_work_count = 0;                     // work[0 .. all_work_count) covers every bundle once
+    int sync_batch_count = 0, fallback_levels = 0;
+    std::vector<int32_t> kinematics;
+    std::vector<StageOp> program;
+    FrameParams* frame_params_host = nullptr;   // pinned
+
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_valid = false;
+
+    bepucuda_timings timings{};
+    int64_t h2d_accum = 0;
+};
+
+namespace {
+
+int fail(bepucuda_ctx* c, int code, const std::string& msg) {
+    if (c) c->error = msg;
+    return code;
+}
+int cuda_fail(bepucuda_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, e == cudaErrorMemoryAllocation ? BEPUCUDA_ERR_OUT_OF_MEMORY : BEPUCUDA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);  \
+    } while (0)
+
+void open_upload_window(bepucuda_ctx* ctx) {
+    if (!ctx->up_open) {
+        cudaEventRecord(ctx->ev_up_begin, ctx->stream);
+        ctx->up_open = true;
+    }
+}
+
+// H2D copy of one host buffer into the raw arena. Small buffers are packed through pinned staging so that hundreds of
+// tiny type batches do not each pay a pageable-memory DMA setup; large ones go directly (fast when the host registered them).
+int copy_in(bepucuda_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return BEPUCUDA_OK;
+    if (bytes < ((size_t)256 << 10)) {
+        cudaError_t e = cudaSuccess;
+        void* stage = ctx->pinned_arena.alloc(bytes, &e);
+        if (!stage) return cuda_fail(ctx, e, "pinned staging");
+        std::memcpy(stage, src, bytes);
+        CK(cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->h2d_accum += (int64_t)bytes;
+    return BEPUCUDA_OK;
+}
+
+void invalidate_graph(bepucuda_ctx* ctx) {
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->graph) cudaGraphDestroy(ctx->graph);
+    ctx->graph_exec = nullptr;
+    ctx->graph = nullptr;
+    ctx->graph_valid = false;
+}
+
+// Issues the whole stage sequence of one frame as individual launches on `s` (used directly in STREAM mode and under
+// capture in GRAPH mode). Order: Solver_Solve.cs:L1419-1479, then PoseIntegrator.IntegrateAfterSubstepping.
+void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) {
+    const DeviceTypeBatch* tbs = ctx->tb_table.as<DeviceTypeBatch>();
+    const WorkItem* work = ctx->work_table.as<WorkItem>();
+    const FrameParams* fp = ctx->frame_params_dev.as<FrameParams>();
+    const int32_t* kin = ctx->kinematics_dev.as<int32_t>();
+    int64_t n = 0;
+    for (const StageOp& op : ctx->program) {
+        switch (op.stage) {
+            case kStageWarmStartFirst: case kStageWarmStart: case kStageSolve: case kStageIncremental:
+                if (op.work_count > 0) { ctx->launchers->constraint_stage(op.stage, tbs, work + op.work_begin, op.work_count, ctx->B, fp, s); ++n; }
+                break;
+            case kStageKinematicFirst: case kStageKinematic:
+                if (op.work_count > 0) { ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, s); ++n; }
+                break;
+            case kStageFinalPose:
+                if (ctx->B.count > 0) { ctx->launchers->final_pose(ctx->B, fp, s); ++n; }
+                break;
+        }
+    }
+    if (launches) *launches = n;
+}
+
+// Builds the flat stage program for the current topology + solve description.
+void build_program(bepucuda_ctx* ctx) {
+    ctx->program.clear();
+    const int substeps = (int)ctx->iterations.size();
+    const int kin = (int)ctx->kinematics.size();
+    for (int s = 0; s < substeps; ++s) {
+        if (s > 0) {
+            if (ctx->inc_work_count > 0) ctx->program.push_back({kStageIncremental, ctx->inc_work_begin, ctx->inc_work_count, 0});
+            if (kin > 0) ctx->program.push_back({kStageKinematic, 0, kin, 0});
+        } else if (ctx->integ.integrate_velocity_for_kinematics && kin > 0) {
+            ctx->program.push_back({kStageKinematicFirst, 0, kin, 0});
+        }
+        for (auto& bw : ctx->batch_work)
+            if (bw.second > 0) ctx->program.push_back({s == 0 ? kStageWarmStartFirst : kStageWarmStart, bw.first, bw.second, 0});
+        for (int it = 0; it < ctx->iterations[s]; ++it)
+            for (auto& bw : ctx->batch_work)
+                if (bw.second > 0) ctx->program.push_back({kStageSolve, bw.first, bw.second, 0});
+    }
+    ctx->program.push_back({kStageFinalPose, 0, ctx->body_count, 0});
+}
+
+int upload_program(bepucuda_ctx* ctx) {
+    build_program(ctx);
+    CK(ctx->program_dev.reserve(ctx->program.size() * sizeof(StageOp)));
+    CK(cudaMemcpyAsync(ctx->program_dev.ptr, ctx->program.data(), ctx->program.size() * sizeof(StageOp), cudaMemcpyHostToDevice, ctx->stream));
+    // The copy source is a std::vector: make sure the DMA read it before anyone mutates it.
+    CK(cudaStreamSynchronize(ctx->stream));
+    invalidate_graph(ctx);
+    // stage statistics
+    int64_t stages = 0;
+    for (auto& op : ctx->program) stages += (op.work_count > 0 || op.stage == kStageFinalPose) ? 1 : 0;
+    ctx->timings.stage_count = stages;
+    return BEPUCUDA_OK;
+}
+
+void compute_frame_params(bepucuda_ctx* ctx, float dt, FrameParams* fp) {
+    const int substeps = (int)ctx->iterations.size();
+    const float substepDt = dt / substeps;  // Solver_Solve.cs:L1417
+    auto clamp01 = [](float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); };
+    const bepucuda_integrator_desc& d = ctx->integ;
+    fp->dt = substepDt;
+    fp->inverse_dt = 1.0f / substepDt;
+    // PrepareForIntegration(substepDt): Demos/DemoCallbacks.cs:L79-86
+    fp->linear_damping_dt = powf(clamp01(1 - d.linear_damping), substepDt);
+    fp->angular_damping_dt = powf(clamp01(1 - d.angular_damping), substepDt);
+    for (int i = 0; i < 3; ++i) fp->gravity_dt[i] = d.gravity[i] * substepDt;
+    // IntegrateAfterSubstepping: PoseIntegrator.cs:L707-712
+    const float finalDt = d.allow_substeps_for_unconstrained ? substepDt : dt;
+    fp->final_dt = finalDt;
+    fp->final_linear_damping_dt = powf(clamp01(1 - d.linear_damping), finalDt);
+    fp->final_angular_damping_dt = powf(clamp01(1 - d.angular_damping), finalDt);
+    for (int i = 0; i < 3; ++i) fp->final_gravity_dt[i] = d.gravity[i] * finalDt;
+    fp->final_steps = d.allow_substeps_for_unconstrained ? substeps : 1;
+    fp->angular_mode = d.angular_integration_mode;
+    fp->integrate_velocity_for_kinematics = d.integrate_velocity_for_kinematics;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t bepucuda_type_info(int32_t type_id, int32_t* bodies_per_constraint, int32_t* prestep_floats, int32_t* impulse_floats) {
+    const TypeInfo* t = get_type_info(type_id);
+    if (!t) return BEPUCUDA_ERR_UNSUPPORTED_TYPE;
+    if (bodies_per_constraint) *bodies_per_constraint = t->bodies;
+    if (prestep_floats) *prestep_floats = t->prestep_rows;
+    if (impulse_floats) *impulse_floats = t->impulse_rows;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_create(const bepucuda_config* cfg, bepucuda_ctx** out) {
+    if (!cfg || !out) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return BEPUCUDA_ERR_NO_DEVICE;  // no CPU fallback, by design
+    if (cfg->device_ordinal < 0 || cfg->device_ordinal >= count) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    bepucuda_ctx* ctx = new bepucuda_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device_ordinal;
+    ctx->launchers = cfg->strict_fp ? get_launchers_bepu_strict() : get_launchers_bepu_fast();
+    ctx->pinned_arena.pinned_host = true;
+    ctx->pinned_arena.min_chunk = (size_t)16 << 20;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaEvent_t* evs[] = {&ctx->ev_solve_begin, &ctx->ev_solve_end, &ctx->ev_up_begin, &ctx->ev_up_end, &ctx->ev_down_begin, &ctx->ev_down_end};
+    for (auto ev : evs)
+        if (e == cudaSuccess) e = cudaEventCreate(ev);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->frame_params_host, sizeof(FrameParams));
+    if (e == cudaSuccess) e = ctx->frame_params_dev.reserve(sizeof(FrameParams));
+    if (e == cudaSuccess) e = ctx->barrier_dev.reserve(2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->barrier_dev.ptr, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = ctx->error_dev.reserve(sizeof(int32_t));
+    if (e != cudaSuccess) {
+        bepucuda_destroy(ctx);
+        return e == cudaErrorMemoryAllocation ? BEPUCUDA_ERR_OUT_OF_MEMORY : BEPUCUDA_ERR_CUDA;
+    }
+    // DemoPoseIntegratorCallbacks defaults (Demos/DemoCallbacks.cs:L60)
+    ctx->integ.gravity[0] = 0; ctx->integ.gravity[1] = -10; ctx->integ.gravity[2] = 0;
+    ctx->integ.linear_damping = 0.03f;
+    ctx->integ.angular_damping = 0.03f;
+    *out = ctx;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
+    if (!ctx) return BEPUCUDA_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    invalidate_graph(ctx);
+    DeviceBuffer* bufs[] = {&ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
+                            &ctx->sync_mask, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
+                            &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev};
+    for (auto b : bufs) b->release();
+    ctx->raw_arena.release();
+    ctx->pinned_arena.release();
+    if (ctx->frame_params_host) cudaFreeHost(ctx->frame_params_host);
+    cudaEvent_t evs[] = {ctx->ev_solve_begin, ctx->ev_solve_end, ctx->ev_up_begin, ctx->ev_up_end, ctx->ev_down_begin, ctx->ev_down_end};
+    for (auto ev : evs)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return BEPUCUDA_OK;
+}
+
+const char* bepucuda_last_error(bepucuda_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int32_t bepucuda_host_register(bepucuda_ctx* ctx, void* ptr, int64_t bytes) {
+    if (!ctx || !ptr || bytes <= 0) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "host_register: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return BEPUCUDA_OK;
+}
+int32_t bepucuda_host_unregister(bepucuda_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "host_unregister: bad arguments");
+    CK(cudaHostUnregister(ptr));
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_set_solve_description(bepucuda_ctx* ctx, int32_t substep_count, const int32_t* its, int32_t fallback_batch_threshold) {
+    if (!ctx || substep_count < 1 || !its || fallback_batch_threshold < 1) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_solve_description: bad arguments");
+    for (int i = 0; i < substep_count; ++i)
+        if (its[i] < 0) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_solve_description: negative iteration count");
+    std::vector<int32_t> v(its, its + substep_count);
+    const bool threshold_changed = fallback_batch_threshold != ctx->fallback_threshold;
+    const bool changed = v != ctx->iterations || threshold_changed;
+    ctx->iterations = v;
+    ctx->fallback_threshold = fallback_batch_threshold;
+    if (threshold_changed && ctx->constraints_ready) ctx->constraints_ready = false;  // fallback split must be redone
+    if (changed && ctx->constraints_ready) {
+        CK(cudaSetDevice(ctx->device));
+        return upload_program(ctx);
+    }
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_set_integrator(bepucuda_ctx* ctx, const bepucuda_integrator_desc* desc) {
+    if (!ctx || !desc) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_integrator: bad arguments");
+    if (desc->angular_integration_mode < 0 || desc->angular_integration_mode > 2) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_integrator: unknown AngularIntegrationMode");
+    const bool kin_changed = (desc->integrate_velocity_for_kinematics != 0) != (ctx->integ.integrate_velocity_for_kinematics != 0);
+    ctx->integ = *desc;
+    ctx->integ_set = true;
+    if (kin_changed && ctx->constraints_ready) {
+        CK(cudaSetDevice(ctx->device));
+        return upload_program(ctx);
+    }
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_upload_bodies(bepucuda_ctx* ctx, const void* body_dynamics, int32_t body_count) {
+    if (!ctx || body_count < 0 || (body_count > 0 && !body_dynamics)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "upload_bodies: bad arguments");
+    if ((uint32_t)body_count > kRefIndexMask) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "upload_bodies: too many bodies");
+    CK(cudaSetDevice(ctx->device));
+    open_upload_window(ctx);
+    const size_t n = (size_t)body_count;
+    if (body_count != ctx->body_count) {
+        // constrained flags / ownership depend on the body count; force a rebuild of topology products.
+        if (ctx->constraints_ready) ctx->constraints_ready = false;
+        invalidate_graph(ctx);
+    }
+    CK(ctx->raw_bodies.reserve(n * 128));
+    CK(ctx->pose.reserve(n * 32));
+    CK(ctx->velocity.reserve(n * 32));
+    CK(ctx->inertia_local.reserve(n * 32));
+    CK(ctx->inertia_world.reserve(n * 32));
+    const size_t old_constrained_cap = ctx->constrained.capacity;
+    CK(ctx->constrained.reserve(n + 1));
+    if (ctx->constrained.capacity != old_constrained_cap) CK(cudaMemsetAsync(ctx->constrained.ptr, 0, ctx->constrained.capacity, ctx->stream));
+    ctx->body_count = body_count;
+    BodyBuffers B{};
+    B.pose = ctx->pose.as<float4>();
+    B.velocity = ctx->velocity.as<float4>();
+    B.inertia_local = ctx->inertia_local.as<float4>();
+    B.inertia_world = ctx->inertia_world.as<float4>();
+    B.constrained = ctx->constrained.as<uint8_t>();
+    B.count = body_count;
+    if (B.pose != ctx->B.pose || B.velocity != ctx->B.velocity || B.inertia_local != ctx->B.inertia_local || B.inertia_world != ctx->B.inertia_world ||
+        B.constrained != ctx->B.constrained || B.count != ctx->B.count)
+        invalidate_graph(ctx);  // kernel arguments are baked into graph nodes
+    ctx->B = B;
+    if (body_count > 0) {
+        CK(cudaMemcpyAsync(ctx->raw_bodies.ptr, body_dynamics, n * 128, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_accum += (int64_t)n * 128;
+        launch_split_bodies(ctx->raw_bodies.ptr, body_count, ctx->B, ctx->stream);
+        CK(cudaGetLastError());
+    }
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_begin_constraints(bepucuda_ctx* ctx, int32_t source_bundle_width, int32_t batch_count) {
+    if (!ctx || source_bundle_width < 1 || source_bundle_width > 64 || batch_count < 0) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "begin_constraints: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));  // staging arenas are recycled below
+    open_upload_window(ctx);
+    ctx->W = source_bundle_width;
+    ctx->batch_count = batch_count;
+    ctx->sources.clear();
+    ctx->raw_arena.reset();
+    ctx->pinned_arena.reset();
+    ctx->constraints_open = true;
+    ctx->constraints_ready = false;
+    invalidate_graph(ctx);
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_upload_type_batch(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index, int32_t type_id, int32_t constraint_count,
+                                   const int32_t* body_references, const float* prestep, float* accumulated_impulses) {
+    if (!ctx) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    if (!ctx->constraints_open) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "upload_type_batch outside begin/end_constraints");
+    if (batch_index < 0 || batch_index >= ctx->batch_count || type_batch_index < 0 || constraint_count < 0)
+        return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "upload_type_batch: bad indices");
+    const TypeInfo* t = get_type_info(type_id);
+    if (!t) return fail(ctx, BEPUCUDA_ERR_UNSUPPORTED_TYPE, "upload_type_batch: unsupported constraint type id " + std::to_string(type_id));
+    if (constraint_count == 0) return BEPUCUDA_OK;
+    if (!body_references || !prestep || !accumulated_impulses) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "upload_type_batch: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->W;
+    const size_t bundles = ((size_t)constraint_count + W - 1) / W;
+    SourceTypeBatch s{};
+    s.batch_index = batch_index; s.type_batch_index = type_batch_index; s.type_id = type_id; s.count = constraint_count;
+    s.host_impulses = accumulated_impulses;
+    s.refs_bytes = bundles * t->bodies * W * 4;
+    s.prestep_bytes = bundles * t->prestep_rows * W * 4;
+    s.impulse_bytes = bundles * t->impulse_rows * W * 4;
+    cudaError_t e = cudaSuccess;
+    s.raw_refs = (int32_t*)ctx->raw_arena.alloc(s.refs_bytes, &e);
+    s.raw_prestep = (float*)ctx->raw_arena.alloc(s.prestep_bytes, &e);
+    s.raw_impulses = (float*)ctx->raw_arena.alloc(s.impulse_bytes, &e);
+    if (!s.raw_refs || !s.raw_prestep || !s.raw_impulses) return cuda_fail(ctx, e, "raw arena");
+    int rc;
+    if ((rc = copy_in(ctx, s.raw_refs, body_references, s.refs_bytes)) != BEPUCUDA_OK) return rc;
+    if ((rc = copy_in(ctx, s.raw_prestep, prestep, s.prestep_bytes)) != BEPUCUDA_OK) return rc;
+    if ((rc = copy_in(ctx, s.raw_impulses, accumulated_impulses, s.impulse_bytes)) != BEPUCUDA_OK) return rc;
+    if (batch_index >= ctx->fallback_threshold) s.host_refs.assign(body_references, body_references + s.refs_bytes / 4);
+    ctx->sources.push_back(std::move(s));
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_set_constrained_kinematics(bepucuda_ctx* ctx, const int32_t* body_indices, int32_t count) {
+    if (!ctx || count < 0 || (count > 0 && !body_indices)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_constrained_kinematics: bad arguments");
+    ctx->kinematics.assign(body_indices, body_indices + count);
+    if (ctx->constraints_ready) ctx->constraints_ready = false;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
+    if (!ctx) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    if (!ctx->constraints_open) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "end_constraints without begin_constraints");
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->W;
+    std::stable_sort(ctx->sources.begin(), ctx->sources.end(), [](const SourceTypeBatch& a, const SourceTypeBatch& b) {
+        return a.batch_index != b.batch_index ? a.batch_index < b.batch_index : a.type_batch_index < b.type_batch_index;
+    });
+
+    // ---- device batches: synchronized batches in order, then dependency levels of the sequential fallback batch ----
+    ctx->tbs.clear();
+    ctx->tdescs.clear();
+    std::vector<int32_t> maps;                       // concatenated slot->source maps for fallback-level type batches
+    std::vector<size_t> map_offset;                  // per device tb: offset into maps or SIZE_MAX
+    std::vector<std::vector<int>> batch_tbs;         // device batch -> device tb indices
+    int64_t constraint_count = 0;
+    ctx->sync_batch_count = 0;
+    ctx->fallback_levels = 0;
+    {
+        int current_batch = -1;
+        for (size_t si = 0; si < ctx->sources.size(); ++si) {
+            SourceTypeBatch& s = ctx->sources[si];
+            s.device_tbs.clear();
+            if (s.batch_index >= ctx->fallback_threshold) continue;
+            if (s.batch_index != current_batch) { batch_tbs.emplace_back(); current_batch = s.batch_index; }
+            const TypeInfo* t = get_type_info(s.type_id);
+            DeviceTypeBatch d{};
+            d.type_id = s.type_id;
+            d.bundle_count = (s.count + 31) / 32;
+            d.device_batch = (int)batch_tbs.size() - 1;
+            TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows};
+            s.device_tbs.push_back((int)ctx->tbs.size());
+            batch_tbs.back().push_back((int)ctx->tbs.size());
+            ctx->tbs.push_back(d);
+            ctx->tdescs.push_back(td);
+            map_offset.push_back(SIZE_MAX);
+            s.live = s.count;
+            constraint_count += s.count;
+        }
+        ctx->sync_batch_count = (int)batch_tbs.size();
+    }
+    {
+        // Fallback levelisation. The reference executes fallback bundles one after another on a single thread
+        // (Solver_Solve.cs:L546-583); within a bundle no dynamic body repeats (TypeProcessor.cs:L338-359). A constraint's
+        // level is 1 + the highest level of any earlier-bundle constraint sharing a dynamic body with it: executing levels in
+        // order with a barrier in between preserves every read-after-write of the sequential loop, so results are identical.
+        std::vector<int32_t> last_level;  // per body: highest level assigned so far (0 = none)
+        struct Slot { int level; int source; int constraint; };
+        std::vector<Slot> slots;
+        bool any = false;
+        for (size_t si = 0; si < ctx->sources.size(); ++si) {
+            SourceTypeBatch& s = ctx->sources[si];
+            if (s.batch_index < ctx->fallback_threshold) continue;
+            if (!any) { last_level.assign((size_t)ctx->body_count, 0); any = true; }
+            s.live = 0;
+            const TypeInfo* t = get_type_info(s.type_id);
+            const int nb = t->bodies;
+            const int bundles = (s.count + W - 1) / W;
+            std::vector<int> lane_level(W);
+            for (int k = 0; k < bundles; ++k) {
+                // all lanes of a bundle read the state left by earlier bundles
+                for (int l = 0; l < W; ++l) {
+                    lane_level[l] = 0;
+                    const int c = k * W + l;
+                    if (c >= s.count) continue;
+                    const int32_t first = s.host_refs[((size_t)k * nb) * W + l];
+                    if (first < 0) continue;  // hole
+                    int lvl = 0;
+                    for (int b = 0; b < nb; ++b) {
+                        const int32_t enc = s.host_refs[((size_t)k * nb + b) * W + l];
+                        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
+                        const uint32_t idx = (uint32_t)enc & kRefIndexMask;
+                        if ((int)idx >= ctx->body_count) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "end_constraints: body reference out of range");
+                        lvl = std::max(lvl, last_level[idx]);
+                    }
+                    lane_level[l] = lvl + 1;
+                }
+                for (int l = 0; l < W; ++l) {
+                    if (lane_level[l] == 0) continue;
+                    for (int b = 0; b < nb; ++b) {
+                        const int32_t enc = s.host_refs[((size_t)k * nb + b) * W + l];
+                        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
+                        last_level[(uint32_t)enc & kRefIndexMask] = lane_level[l];
+                    }
+                    slots.push_back({lane_level[l], (int)si, k * W + l});
+                    ++s.live;
+                    ++constraint_count;
+                }
+            }
+        }
+        if (any) {
+            std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.level != b.level ? a.level < b.level : a.source < b.source; });
+            size_t i = 0;
+            while (i < slots.size()) {
+                const int level = slots[i].level;
+                batch_tbs.emplace_back();
+                ++ctx->fallback_levels;
+                while (i < slots.size() && slots[i].level == level) {
+                    const int source = slots[i].source;
+                    size_t j = i;
+                    while (j < slots.size() && slots[j].level == level && slots[j].source == source) ++j;
+                    SourceTypeBatch& s = ctx->sources[source];
+                    const TypeInfo* t = get_type_info(s.type_id);
+                    const int n = (int)(j - i);
+                    DeviceTypeBatch d{};
+                    d.type_id = s.type_id;
+                    d.bundle_count = (n + 31) / 32;
+                    d.device_batch = (int)batch_tbs.size() - 1;
+                    map_offset.push_back(maps.size());
+                    for (size_t q = i; q < j; ++q) maps.push_back(slots[q].constraint);
+                    for (int q = n; q < d.bundle_count * 32; ++q) maps.push_back(-1);
+                    TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows};
+                    s.device_tbs.push_back((int)ctx->tbs.size());
+                    batch_tbs.back().push_back((int)ctx->tbs.size());
+                    ctx->tbs.push_back(d);
+                    ctx->tdescs.push_back(td);
+                    i = j;
+                }
+            }
+        }
+    }
+
+    // ---- device arenas for the AOSOA-32 image ----
+    size_t refs_floats = 0, prestep_floats = 0, impulse_floats = 0;
+    std::vector<size_t> ro(ctx->tbs.size()), po(ctx->tbs.size()), io(ctx->tbs.size());
+    for (size_t i = 0; i < ctx->tbs.size(); ++i) {
+        const TypeInfo* t = get_type_info(ctx->tbs[i].type_id);
+        ro[i] = refs_floats; po[i] = prestep_floats; io[i] = impulse_floats;
+        refs_floats += (size_t)ctx->tbs[i].bundle_count * t->bodies * 32;
+        prestep_floats += (size_t)ctx->tbs[i].bundle_count * t->prestep_rows * 32;
+        impulse_floats += (size_t)ctx->tbs[i].bundle_count * t->impulse_rows * 32;
+    }
+    CK(ctx->refs32.reserve(refs_floats * 4 + 4));
+    CK(ctx->prestep32.reserve(prestep_floats * 4 + 4));
+    CK(ctx->impulses32.reserve(impulse_floats * 4 + 4));
+    CK(ctx->map_table.reserve(maps.size() * 4 + 4));
+    for (size_t i = 0; i < ctx->tbs.size(); ++i) {
+        ctx->tbs[i].refs = ctx->refs32.as<int32_t>() + ro[i];
+        ctx->tbs[i].prestep = ctx->prestep32.as<float>() + po[i];
+        ctx->tbs[i].impulses = ctx->impulses32.as<float>() + io[i];
+        ctx->tdescs[i].map = map_offset[i] == SIZE_MAX ? nullptr : ctx->map_table.as<int32_t>() + map_offset[i];
+    }
+
+    // ---- work lists: per device batch (one warp per bundle), then the incremental-update list over all contact bundles ----
+    ctx->work.clear();
+    ctx->batch_work.clear();
+    for (auto& list : batch_tbs) {
+        const int begin = (int)ctx->work.size();
+        for (int tb : list)
+            for (int k = 0; k < ctx->tbs[tb].bundle_count; ++k) ctx->work.push_back({tb, k});
+        ctx->batch_work.push_back({begin, (int)ctx->work.size() - begin});
+    }
+    ctx->all_work_count = (int)ctx->work.size();
+    ctx->inc_work_begin = (int)ctx->work.size();
+    for (size_t tb = 0; tb < ctx->tbs.size(); ++tb)
+        if (get_type_info(ctx->tbs[tb].type_id)->incremental)
+            for (int k = 0; k < ctx->tbs[tb].bundle_count; ++k) ctx->work.push_back({(int)tb, k});
+    ctx->inc_work_count = (int)ctx->work.size() - ctx->inc_work_begin;
+
+    // ---- upload tables ----
+    int32_t bodies_per_type[64];
+    for (int i = 0; i < 64; ++i) bodies_per_type[i] = get_type_info(i) ? get_type_info(i)->bodies : 0;
+    CK(ctx->tb_table.reserve(ctx->tbs.size() * sizeof(DeviceTypeBatch) + 16));
+    CK(ctx->tdesc_table.reserve(ctx->tdescs.size() * sizeof(TransposeDesc) + 16));
+    CK(ctx->work_table.reserve(ctx->work.size() * sizeof(WorkItem) + 16));
+    CK(ctx->bodies_per_type.reserve(sizeof(bodies_per_type)));
+    CK(ctx->kinematics_dev.reserve(ctx->kinematics.size() * 4 + 4));
+    if (!ctx->tbs.empty()) CK(cudaMemcpyAsync(ctx->tb_table.ptr, ctx->tbs.data(), ctx->tbs.size() * sizeof(DeviceTypeBatch), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->tdescs.empty()) CK(cudaMemcpyAsync(ctx->tdesc_table.ptr, ctx->tdescs.data(), ctx->tdescs.size() * sizeof(TransposeDesc), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->work.empty()) CK(cudaMemcpyAsync(ctx->work_table.ptr, ctx->work.data(), ctx->work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
+    if (!maps.empty()) CK(cudaMemcpyAsync(ctx->map_table.ptr, maps.data(), maps.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->bodies_per_type.ptr, bodies_per_type, sizeof(bodies_per_type), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->kinematics.empty()) CK(cudaMemcpyAsync(ctx->kinematics_dev.ptr, ctx->kinematics.data(), ctx->kinematics.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    // ---- transposition into AOSOA-32 + ownership analysis ----
+    launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, W,
+                            kTransposeRefs | kTransposePrestep | kTransposeImpulses, ctx->stream);
+    const size_t nb = (size_t)std::max(ctx->body_count, 1);
+    CK(ctx->first_batch.reserve(nb * 4));
+    CK(ctx->sync_refcount.reserve(nb * 4));
+    CK(ctx->sync_mask.reserve(nb * 8));
+    launch_fill_i32(ctx->first_batch.as<int32_t>(), nb, 0x7fffffff, ctx->stream);
+    CK(cudaMemsetAsync(ctx->sync_refcount.ptr, 0, nb * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->sync_mask.ptr, 0, nb * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->constrained.ptr, 0, nb, ctx->stream));
+    CK(cudaMemsetAsync(ctx->error_dev.ptr, 0, 4, ctx->stream));
+    launch_ownership(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), ctx->sync_batch_count,
+                     ctx->body_count, ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (unsigned long long*)ctx->sync_mask.ptr, ctx->constrained.as<uint8_t>(),
+                     ctx->kinematics_dev.as<int32_t>(), (int)ctx->kinematics.size(), ctx->error_dev.as<int32_t>(), ctx->stream);
+    CK(cudaGetLastError());
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(&err, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // also guarantees the std::vector sources of the copies above were consumed
+    if (err == 1) return fail(ctx, BEPUCUDA_ERR_BATCH_INVARIANT, "end_constraints: a synchronized batch references the same dynamic body more than once");
+    if (err == 2) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "end_constraints: body reference out of range");
+
+    ctx->timings.constraint_count = constraint_count;
+    ctx->timings.device_batch_count = (int)batch_tbs.size();
+    ctx->timings.fallback_level_count = ctx->fallback_levels;
+    ctx->constraints_open = false;
+    ctx->constraints_ready = true;
+    ctx->data_dirty = false;
+    return upload_program(ctx);
+}
+
+int32_t bepucuda_update_type_batch(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index, const float* prestep, float* accumulated_impulses) {
+    if (!ctx || !prestep || !accumulated_impulses) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "update_type_batch: bad arguments");
+    if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "update_type_batch before end_constraints");
+    CK(cudaSetDevice(ctx->device));
+    open_upload_window(ctx);
+    for (auto& s : ctx->sources)
+        if (s.batch_index == batch_index && s.type_batch_index == type_batch_index) {
+            // Direct copies only: the pinned staging arena is recycled per begin_constraints, not per frame.
+            CK(cudaMemcpyAsync(s.raw_prestep, prestep, s.prestep_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(s.raw_impulses, accumulated_impulses, s.impulse_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_accum += (int64_t)(s.prestep_bytes + s.impulse_bytes);
+            s.host_impulses = accumulated_impulses;
+            ctx->data_dirty = true;
+            return BEPUCUDA_OK;
+        }
+    return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "update_type_batch: unknown type batch");
+}
+
+int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
+    if (!ctx || !(dt > 0)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "solve: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->constraints_ready) {
+        // No constraints were ever described (or the description was invalidated): only legal when nothing was uploaded.
+        if (ctx->constraints_open) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "solve inside begin/end_constraints");
+        if (!ctx->sources.empty()) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "solve: constraint description is stale; re-run begin/upload/end_constraints");
+        int rc = bepucuda_begin_constraints(ctx, ctx->W, 0);
+        if (rc == BEPUCUDA_OK) rc = bepucuda_end_constraints(ctx);
+        if (rc != BEPUCUDA_OK) return rc;
+    }
+    if (ctx->data_dirty) {
+        launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
+                                kTransposePrestep | kTransposeImpulses, ctx->stream);
+        ctx->data_dirty = false;
+    }
+    if (ctx->up_open) {
+        cudaEventRecord(ctx->ev_up_end, ctx->stream);
+        ctx->up_open = false;
+        ctx->have_up = true;
+    }
+    ctx->timings.h2d_bytes = ctx->h2d_accum;
+    ctx->h2d_accum = 0;
+    // frame parameters (previous frame's copy has completed by stream order only after its graph; wait for it before reusing the pinned struct)
+    CK(cudaEventSynchronize(ctx->ev_solve_end));
+    compute_frame_params(ctx, dt, ctx->frame_params_host);
+    CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
+
+    CK(cudaEventRecord(ctx->ev_solve_begin, ctx->stream));
+    int64_t launches = 0;
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_PERSISTENT) {
+        int rc = ctx->launchers->persistent(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(),
+                                            ctx->kinematics_dev.as<int32_t>(), ctx->B, ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->stream);
+        if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "persistent kernel launch");
+        launches = 1;
+    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_GRAPH) {
+        if (!ctx->graph_valid) {
+            CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int64_t n = 0;
+            issue_stage_sequence(ctx, ctx->stream, &n);
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->graph);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "graph capture");
+            CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
+            ctx->graph_valid = true;
+            ctx->timings.kernel_launches = n;
+        }
+        CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        launches = ctx->timings.kernel_launches;
+    } else {
+        issue_stage_sequence(ctx, ctx->stream, &launches);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev_solve_end, ctx->stream));
+    ctx->have_solve = true;
+    ctx->timings.kernel_launches = launches;
+
+    // metric bookkeeping
+    int64_t ci = 0, bytes = 0;
+    const int substeps = (int)ctx->iterations.size();
+    for (const SourceTypeBatch& s : ctx->sources) {
+        const TypeInfo* t = get_type_info(s.type_id);
+        const int64_t n = s.live;
+        for (int sub = 0; sub < substeps; ++sub) {
+            ci += n * ctx->iterations[sub];
+            bytes += n * ((int64_t)t->warm_start_bytes + (int64_t)ctx->iterations[sub] * t->solve_bytes + (sub > 0 ? t->incremental_bytes : 0));
+        }
+    }
+    bytes += (int64_t)ctx->body_count * 108;
+    ctx->timings.constraint_iterations = ci;
+    ctx->timings.algorithmic_bytes = bytes;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_synchronize(bepucuda_ctx* ctx) {
+    if (!ctx) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_download_bodies(bepucuda_ctx* ctx, void* out, int32_t body_count) {
+    if (!ctx || !out || body_count < 0 || body_count > ctx->body_count) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "download_bodies: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_down_begin, ctx->stream));
+    launch_merge_bodies(ctx->raw_bodies.ptr, body_count, ctx->B, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->raw_bodies.ptr, (size_t)body_count * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_down_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_down = true;
+    ctx->timings.d2h_bytes = (int64_t)body_count * 128;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_download_impulses(bepucuda_ctx* ctx) {
+    if (!ctx) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "download_impulses before end_constraints");
+    CK(cudaSetDevice(ctx->device));
+    launch_transpose_out_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
+                             kTransposeImpulses, ctx->stream);
+    CK(cudaGetLastError());
+    int64_t bytes = 0;
+    for (auto& s : ctx->sources) {
+        CK(cudaMemcpyAsync(s.host_impulses, s.raw_impulses, s.impulse_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        bytes += (int64_t)s.impulse_bytes;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->timings.d2h_bytes += bytes;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_download_prestep(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index, float* prestep_out) {
+    if (!ctx || !prestep_out) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "download_prestep: bad arguments");
+    if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "download_prestep before end_constraints");
+    CK(cudaSetDevice(ctx->device));
+    for (auto& s : ctx->sources)
+        if (s.batch_index == batch_index && s.type_batch_index == type_batch_index) {
+            launch_transpose_out_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
+                                     kTransposePrestep, ctx->stream);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(prestep_out, s.raw_prestep, s.prestep_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            return BEPUCUDA_OK;
+        }
+    return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "download_prestep: unknown type batch");
+}
+
+int32_t bepucuda_get_timings(bepucuda_ctx* ctx, bepucuda_timings* out) {
+    if (!ctx || !out) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->have_solve) cudaEventElapsedTime(&ctx->timings.solve_ms, ctx->ev_solve_begin, ctx->ev_solve_end);
+    if (ctx->have_up && !ctx->up_open) cudaEventElapsedTime(&ctx->timings.upload_ms, ctx->ev_up_begin, ctx->ev_up_end);
+    if (ctx->have_down) cudaEventElapsedTime(&ctx->timings.download_ms, ctx->ev_down_begin, ctx->ev_down_end);
+    *out = ctx->timings;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_set_boundary_bodies(bepucuda_ctx* ctx, const int32_t* body_indices, int32_t count, bepucuda_exchange_fn exchange, void* user) {
+    (void)body_indices; (void)count; (void)exchange; (void)user;
+    return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "set_boundary_bodies: cross-device constraint graphs are not supported yet; shard independent islands across contexts");
+}
+
+}  // extern "C"

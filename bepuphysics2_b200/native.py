@@ -1,0 +1,327 @@
+"""ctypes view of the C ABI (include/bepucuda.h) and of the C++ host mirror (csrc/host/bepu_host.cpp).
+
+Class names follow the reference: `Simulation` (BepuPhysics/Simulation.cs) owns `Bodies` + `Solver` state in the reference's own
+buffer layouts; `CudaTimestepper` is the ITimestepper (BepuPhysics/ITimestepper.cs:L15-34) whose Solve slot runs on the GPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = None
+
+
+class BepuCudaError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("bepucuda error %d: %s" % (code, message))
+        self.code = code
+
+
+class IntegratorDesc(C.Structure):
+    """bepucuda_integrator_desc — declarative IPoseIntegratorCallbacks (Demos/DemoCallbacks.cs:L12-105)."""
+
+    _fields_ = [
+        ("gravity", C.c_float * 3),
+        ("linear_damping", C.c_float),
+        ("angular_damping", C.c_float),
+        ("angular_integration_mode", C.c_int32),
+        ("allow_substeps_for_unconstrained", C.c_int32),
+        ("integrate_velocity_for_kinematics", C.c_int32),
+    ]
+
+    @staticmethod
+    def default():
+        d = IntegratorDesc()
+        d.gravity[0], d.gravity[1], d.gravity[2] = 0.0, -10.0, 0.0
+        d.linear_damping = 0.03
+        d.angular_damping = 0.03
+        return d
+
+
+class Config(C.Structure):
+    _fields_ = [("device_ordinal", C.c_int32), ("strict_fp", C.c_int32), ("execution_mode", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class Timings(C.Structure):
+    _fields_ = [
+        ("solve_ms", C.c_float),
+        ("upload_ms", C.c_float),
+        ("download_ms", C.c_float),
+        ("constraint_count", C.c_int64),
+        ("constraint_iterations", C.c_int64),
+        ("stage_count", C.c_int64),
+        ("kernel_launches", C.c_int64),
+        ("algorithmic_bytes", C.c_int64),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
+        ("device_batch_count", C.c_int32),
+        ("fallback_level_count", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class TypeBatchView(C.Structure):
+    _fields_ = [
+        ("type_id", C.c_int32),
+        ("constraint_count", C.c_int32),
+        ("bodies", C.c_int32),
+        ("prestep_rows", C.c_int32),
+        ("impulse_rows", C.c_int32),
+        ("bundle_count", C.c_int32),
+        ("body_references", C.POINTER(C.c_int32)),
+        ("prestep", C.POINTER(C.c_float)),
+        ("accumulated_impulses", C.POINTER(C.c_float)),
+    ]
+
+
+EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM = 0, 1, 2
+
+# Every symbol include/bepucuda.h declares (checked by the CPU test-suite).
+C_ABI_SYMBOLS = [
+    "bepucuda_create", "bepucuda_destroy", "bepucuda_last_error", "bepucuda_type_info", "bepucuda_host_register", "bepucuda_host_unregister",
+    "bepucuda_set_solve_description", "bepucuda_set_integrator", "bepucuda_upload_bodies", "bepucuda_begin_constraints", "bepucuda_upload_type_batch",
+    "bepucuda_set_constrained_kinematics", "bepucuda_end_constraints", "bepucuda_update_type_batch", "bepucuda_solve", "bepucuda_synchronize",
+    "bepucuda_download_bodies", "bepucuda_download_impulses", "bepucuda_download_prestep", "bepucuda_get_timings", "bepucuda_set_boundary_bodies",
+]
+
+
+def load_libraries():
+    """Loads libbepucuda.so and libbepuhost.so from the package directory. Fails loudly if they are missing: there is no fallback."""
+    global _LIBS
+    if _LIBS is not None:
+        return _LIBS
+    cuda_path = os.path.join(HERE, "libbepucuda.so")
+    host_path = os.path.join(HERE, "libbepuhost.so")
+    for p in (cuda_path, host_path):
+        if not os.path.exists(p):
+            raise ImportError("%s is missing: run `python -m bepuphysics2_b200._build` (or __graft_entry__.build()); there is no CPU fallback" % p)
+    cuda = C.CDLL(cuda_path, mode=C.RTLD_GLOBAL)
+    host = C.CDLL(host_path)
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    cuda.bepucuda_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    cuda.bepucuda_destroy.argtypes = [vp]
+    cuda.bepucuda_last_error.argtypes = [vp]
+    cuda.bepucuda_last_error.restype = C.c_char_p
+    cuda.bepucuda_type_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    cuda.bepucuda_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    cuda.bepucuda_solve.argtypes = [vp, f32]
+    cuda.bepucuda_synchronize.argtypes = [vp]
+    cuda.bepucuda_set_solve_description.argtypes = [vp, i32, C.POINTER(i32), i32]
+    cuda.bepucuda_set_integrator.argtypes = [vp, C.POINTER(IntegratorDesc)]
+    cuda.bepucuda_upload_bodies.argtypes = [vp, vp, i32]
+    cuda.bepucuda_begin_constraints.argtypes = [vp, i32, i32]
+    cuda.bepucuda_upload_type_batch.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
+    cuda.bepucuda_set_constrained_kinematics.argtypes = [vp, vp, i32]
+    cuda.bepucuda_end_constraints.argtypes = [vp]
+    cuda.bepucuda_update_type_batch.argtypes = [vp, i32, i32, vp, vp]
+    cuda.bepucuda_download_bodies.argtypes = [vp, vp, i32]
+    cuda.bepucuda_download_impulses.argtypes = [vp]
+    cuda.bepucuda_download_prestep.argtypes = [vp, i32, i32, vp]
+    cuda.bepucuda_host_register.argtypes = [vp, vp, C.c_int64]
+    cuda.bepucuda_host_unregister.argtypes = [vp, vp]
+
+    host.bepuhost_create.restype = vp
+    host.bepuhost_create.argtypes = [i32, i32]
+    host.bepuhost_destroy.argtypes = [vp]
+    host.bepuhost_last_error.argtypes = [vp]
+    host.bepuhost_last_error.restype = C.c_char_p
+    host.bepuhost_set_solve_description.argtypes = [vp, i32, C.POINTER(i32)]
+    host.bepuhost_set_integrator.argtypes = [vp, C.POINTER(IntegratorDesc)]
+    host.bepuhost_add_bodies.argtypes = [vp, vp, i32]
+    host.bepuhost_body_dynamics.argtypes = [vp]
+    host.bepuhost_body_dynamics.restype = C.POINTER(C.c_float)
+    host.bepuhost_body_count.argtypes = [vp]
+    host.bepuhost_add_constraints.argtypes = [vp, i32, i32, vp, vp]
+    host.bepuhost_constraint_location.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    host.bepuhost_constraint_count.argtypes = [vp]
+    host.bepuhost_batch_count.argtypes = [vp]
+    host.bepuhost_type_batch_count.argtypes = [vp, i32]
+    host.bepuhost_get_type_batch.argtypes = [vp, i32, i32, C.POINTER(TypeBatchView)]
+    host.bepuhost_constrained_kinematic_count.argtypes = [vp]
+    host.bepuhost_constrained_kinematics.argtypes = [vp]
+    host.bepuhost_constrained_kinematics.restype = C.POINTER(i32)
+    host.bepuhost_substep_count.argtypes = [vp]
+    host.bepuhost_velocity_iterations.argtypes = [vp]
+    host.bepuhost_velocity_iterations.restype = C.POINTER(i32)
+    for name in ("bepuhost_cuda_describe", "bepuhost_cuda_refresh", "bepuhost_cuda_download_prestep", "bepuhost_cuda_register_buffers", "bepuhost_cuda_unregister_buffers"):
+        getattr(host, name).argtypes = [vp, vp]
+    host.bepuhost_cuda_solve.argtypes = [vp, vp, f32, i32]
+    _LIBS = (cuda, host)
+    return _LIBS
+
+
+def type_info(type_id):
+    """(bodies per constraint, prestep floats, accumulated impulse floats) of a constraint type id, or None if unsupported."""
+    cuda, _ = load_libraries()
+    b, p, d = C.c_int32(), C.c_int32(), C.c_int32()
+    if cuda.bepucuda_type_info(type_id, C.byref(b), C.byref(p), C.byref(d)) != 0:
+        return None
+    return b.value, p.value, d.value
+
+
+class TypeBatch:
+    """A numpy view of one reference-layout type batch (Constraints/TypeBatch.cs:L10-27). Arrays alias the host mirror's memory."""
+
+    def __init__(self, batch_index, type_batch_index, view, W):
+        self.batch_index, self.type_batch_index = batch_index, type_batch_index
+        self.type_id, self.constraint_count = view.type_id, view.constraint_count
+        self.bodies, self.prestep_rows, self.impulse_rows, self.bundle_count = view.bodies, view.prestep_rows, view.impulse_rows, view.bundle_count
+        n = view.bundle_count
+        self.body_references = np.ctypeslib.as_array(view.body_references, shape=(n, view.bodies, W))
+        self.prestep = np.ctypeslib.as_array(view.prestep, shape=(n, view.prestep_rows, W))
+        self.accumulated_impulses = np.ctypeslib.as_array(view.accumulated_impulses, shape=(n, view.impulse_rows, W))
+        self.view = view
+
+
+class Simulation:
+    """Host-side state in the reference's layouts: `bodies` is Bodies.ActiveSet.DynamicsState (n x 32 floats, BodyProperties.cs:L318-338),
+    `type_batches()` walks Solver.ActiveSet.Batches[b].TypeBatches[t]. Constraint adds follow Solver.Add's greedy batch assignment."""
+
+    def __init__(self, bundle_width=8, fallback_batch_threshold=64, substeps=1, velocity_iterations=1, integrator=None):
+        _, self._host = load_libraries()
+        self._sim = self._host.bepuhost_create(bundle_width, fallback_batch_threshold)
+        if not self._sim:
+            raise ValueError("bad bundle width / fallback threshold")
+        self.bundle_width = bundle_width
+        self.fallback_batch_threshold = fallback_batch_threshold
+        self.set_solve_description(substeps, velocity_iterations)
+        self.integrator = integrator or IntegratorDesc.default()
+        self._host.bepuhost_set_integrator(self._sim, C.byref(self.integrator))
+
+    def __del__(self):
+        if getattr(self, "_sim", None):
+            self._host.bepuhost_destroy(self._sim)
+            self._sim = None
+
+    def set_solve_description(self, substeps, velocity_iterations):
+        """SolveDescription(velocityIterationCount, substepCount); `velocity_iterations` may be a per-substep list (SolveDescription.cs:L21-38)."""
+        its = [velocity_iterations] * substeps if np.isscalar(velocity_iterations) else list(velocity_iterations)
+        assert len(its) == substeps
+        self.velocity_iterations = its
+        arr = (C.c_int32 * substeps)(*its)
+        self._host.bepuhost_set_solve_description(self._sim, substeps, arr)
+
+    def set_integrator(self, integrator):
+        self.integrator = integrator
+        self._host.bepuhost_set_integrator(self._sim, C.byref(integrator))
+
+    def add_bodies(self, dynamics):
+        d = np.ascontiguousarray(dynamics, dtype=np.float32).reshape(-1, 32)
+        return self._host.bepuhost_add_bodies(self._sim, d.ctypes.data, d.shape[0])
+
+    @property
+    def body_count(self):
+        return self._host.bepuhost_body_count(self._sim)
+
+    @property
+    def bodies(self):
+        n = self.body_count
+        return np.ctypeslib.as_array(self._host.bepuhost_body_dynamics(self._sim), shape=(max(n, 1), 32))[:n]
+
+    def add_constraints(self, type_id, body_handles, prestep):
+        info = type_info(type_id)
+        if info is None:
+            raise ValueError("unsupported constraint type %d" % type_id)
+        nb, p, _ = info
+        h = np.ascontiguousarray(body_handles, dtype=np.int32).reshape(-1, nb)
+        pre = np.ascontiguousarray(prestep, dtype=np.float32).reshape(-1, p)
+        assert h.shape[0] == pre.shape[0]
+        if h.shape[0] == 0:
+            return -1
+        first = self._host.bepuhost_add_constraints(self._sim, type_id, h.shape[0], h.ctypes.data, pre.ctypes.data)
+        if first < 0:
+            raise ValueError(self._host.bepuhost_last_error(self._sim).decode())
+        return first
+
+    @property
+    def constraint_count(self):
+        return self._host.bepuhost_constraint_count(self._sim)
+
+    @property
+    def batch_count(self):
+        return self._host.bepuhost_batch_count(self._sim)
+
+    def constraint_location(self, handle):
+        b, t, i = C.c_int32(), C.c_int32(), C.c_int32()
+        if self._host.bepuhost_constraint_location(self._sim, handle, C.byref(b), C.byref(t), C.byref(i)) != 0:
+            raise IndexError(handle)
+        return b.value, t.value, i.value
+
+    def type_batches(self):
+        out = []
+        for b in range(self.batch_count):
+            for t in range(self._host.bepuhost_type_batch_count(self._sim, b)):
+                v = TypeBatchView()
+                self._host.bepuhost_get_type_batch(self._sim, b, t, C.byref(v))
+                out.append(TypeBatch(b, t, v, self.bundle_width))
+        return out
+
+    @property
+    def constrained_kinematics(self):
+        n = self._host.bepuhost_constrained_kinematic_count(self._sim)
+        if n == 0:
+            return np.zeros(0, dtype=np.int32)
+        return np.ctypeslib.as_array(self._host.bepuhost_constrained_kinematics(self._sim), shape=(n,)).copy()
+
+
+class CudaTimestepper:
+    """The Solve slot of DefaultTimestepper.Timestep (DefaultTimestepper.cs:L28-43) on the GPU, through the C ABI only."""
+
+    def __init__(self, simulation, device=0, strict_fp=False, execution_mode=EXEC_GRAPH):
+        self._cuda, self._host = load_libraries()
+        self.sim = simulation
+        cfg = Config()
+        cfg.device_ordinal, cfg.strict_fp, cfg.execution_mode = device, int(bool(strict_fp)), execution_mode
+        ctx = C.c_void_p()
+        rc = self._cuda.bepucuda_create(C.byref(cfg), C.byref(ctx))
+        if rc != 0:
+            raise BepuCudaError(rc, "bepucuda_create failed (no usable CUDA device? there is no CPU fallback)")
+        self._ctx = ctx
+        self._registered = False
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            if self._registered:
+                self._host.bepuhost_cuda_unregister_buffers(self.sim._sim, self._ctx)
+            self._cuda.bepucuda_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BepuCudaError(rc, self._cuda.bepucuda_last_error(self._ctx).decode())
+
+    def register_host_buffers(self):
+        """Page-locks the simulation's buffers (a C# host would register its BufferPool blocks once)."""
+        self._check(self._host.bepuhost_cuda_register_buffers(self.sim._sim, self._ctx))
+        self._registered = True
+
+    def describe(self):
+        """Uploads bodies + every type batch and rebuilds device topology (call after any add/remove)."""
+        self._check(self._host.bepuhost_cuda_describe(self.sim._sim, self._ctx))
+
+    def refresh(self):
+        """Per-frame upload with unchanged topology: body state + prestep/impulse data."""
+        self._check(self._host.bepuhost_cuda_refresh(self.sim._sim, self._ctx))
+
+    def solve(self, dt, download=True):
+        self._check(self._host.bepuhost_cuda_solve(self.sim._sim, self._ctx, dt, 1 if download else 0))
+
+    def synchronize(self):
+        self._check(self._cuda.bepucuda_synchronize(self._ctx))
+
+    def download_prestep(self):
+        self._check(self._host.bepuhost_cuda_download_prestep(self.sim._sim, self._ctx))
+
+    def timings(self):
+        t = Timings()
+        self._check(self._cuda.bepucuda_get_timings(self._ctx, C.byref(t)))
+        return t

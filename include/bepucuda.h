@@ -1,0 +1,172 @@
+/*
+ * libbepucuda — C ABI of the B200-native constraint solver + integrator for bepuphysics2.
+ *
+ * This is the drop-in boundary. The reference has no FFI at this seam: the
+ * solver is a C# class constructed inside Simulation.Create. The entry points below are what
+ * a C# `CudaTimestepper : ITimestepper` (BepuPhysics/ITimestepper.cs:L15-34) P/Invokes in
+ * place of `simulation.Solve(dt, threadDispatcher)` (BepuPhysics/Simulation.cs:L278-290).
+ * Every pointer is a raw host pointer taken straight from the reference's own pinned
+ * `Buffer<T>.Memory` fields (BepuUtilities/Memory/Buffer.cs:L13-21); no layout conversion is
+ * required on the C# side. INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns an int32 status: 0 = ok, negative = error; the message for the
+ *     last error on a context is available through bepucuda_last_error.
+ *   - no exceptions cross the boundary; a context is used from one thread at a time.
+ *   - the context owns all device memory, streams, CUDA graphs and events.
+ *   - there is NO CPU fallback: if no CUDA device is usable, bepucuda_create fails with
+ *     BEPUCUDA_ERR_NO_DEVICE.
+ */
+#ifndef BEPUCUDA_H
+#define BEPUCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEPUCUDA_OK 0
+#define BEPUCUDA_ERR_INVALID_ARGUMENT (-1)
+#define BEPUCUDA_ERR_NO_DEVICE (-2)
+#define BEPUCUDA_ERR_CUDA (-3)
+/* Unknown constraint type id: the host shim should fall back to Simulation.Solve for the frame. */
+#define BEPUCUDA_ERR_UNSUPPORTED_TYPE (-4)
+/* A synchronized batch references the same dynamic body twice (ConstraintBatch invariant,
+ * BepuPhysics/Solver.cs:L348-960 debug validators). */
+#define BEPUCUDA_ERR_BATCH_INVARIANT (-5)
+#define BEPUCUDA_ERR_BAD_STATE (-6)
+#define BEPUCUDA_ERR_OUT_OF_MEMORY (-7)
+
+typedef struct bepucuda_ctx bepucuda_ctx;
+
+/* How the (substep, stage, batch) sequence of Solver.Solve (Solver_Solve.cs:L1419-1479) is sequenced
+ * on the device. */
+enum bepucuda_execution_mode {
+    BEPUCUDA_EXEC_GRAPH = 0,      /* one kernel per (batch, stage), whole frame captured in a CUDA graph */
+    BEPUCUDA_EXEC_PERSISTENT = 1, /* one cooperative kernel per frame, grid barrier per (batch, stage) */
+    BEPUCUDA_EXEC_STREAM = 2      /* plain stream launches, no graph (debug / profiling with ncu) */
+};
+
+typedef struct bepucuda_config {
+    int32_t device_ordinal;   /* CUDA device to own; one context <-> one GPU */
+    /* 1 = kernels compiled with -fmad=false: bit-identical to a non-contracting fp32 CPU evaluation
+     * (RyuJIT does not contract Vector<float> expressions). 0 = FMA contraction on (fast). */
+    int32_t strict_fp;
+    int32_t execution_mode;   /* enum bepucuda_execution_mode */
+    int32_t reserved[5];
+} bepucuda_config;
+
+/* Declarative stand-in for the user's IPoseIntegratorCallbacks struct (BepuPhysics/PoseIntegrator.cs:L42-94).
+ * Covers Demos/DemoCallbacks.cs:L12-105 (DemoPoseIntegratorCallbacks) exactly:
+ *   PrepareForIntegration(dt): linearDampingDt = pow(clamp(1 - linear_damping, 0, 1), dt), same angular, gravityDt = gravity * dt
+ *   IntegrateVelocity: v.linear = (v.linear + gravityDt) * linearDampingDt; v.angular *= angularDampingDt
+ * This is the one API narrowing of the drop-in (SURVEY.md §7 hard part 4). */
+typedef struct bepucuda_integrator_desc {
+    float gravity[3];
+    float linear_damping;
+    float angular_damping;
+    int32_t angular_integration_mode;           /* AngularIntegrationMode: 0 Nonconserving, 1 ConserveMomentum, 2 ConserveMomentumWithGyroscopicTorque */
+    int32_t allow_substeps_for_unconstrained;   /* IPoseIntegratorCallbacks.AllowSubstepsForUnconstrainedBodies */
+    int32_t integrate_velocity_for_kinematics;  /* IPoseIntegratorCallbacks.IntegrateVelocityForKinematics */
+} bepucuda_integrator_desc;
+
+/* Replaces SimulationProfiler's Solver / PoseIntegrator stage timers (BepuPhysics/SimulationProfiler.cs:L6-75). */
+typedef struct bepucuda_timings {
+    float solve_ms;                 /* device time of the last bepucuda_solve (CUDA events on the context stream) */
+    float upload_ms;                /* device-side time of the uploads since the previous solve (H2D copies + transposes) */
+    float download_ms;              /* device-side time of the last downloads */
+    int64_t constraint_count;       /* active constraints (empty fallback lanes excluded) */
+    int64_t constraint_iterations;  /* sum over substeps of constraint_count * velocity_iterations(substep) */
+    int64_t stage_count;            /* (batch, stage) barriers executed per solve */
+    int64_t kernel_launches;        /* kernels launched (or graph kernel nodes executed) by the last solve */
+    int64_t algorithmic_bytes;      /* SURVEY.md §8d compulsory-traffic model for the last solve */
+    int64_t h2d_bytes;              /* bytes copied host->device since the previous solve */
+    int64_t d2h_bytes;              /* bytes copied device->host by the last downloads */
+    int32_t device_batch_count;     /* synchronized batches + fallback dependency levels */
+    int32_t fallback_level_count;   /* dependency levels the sequential fallback batch was split into */
+} bepucuda_timings;
+
+/* Lifetime. Replaces: construction of Solver<TIntegrationCallbacks> in Simulation.Create (Simulation.cs:L135-141). */
+int32_t bepucuda_create(const bepucuda_config* cfg, bepucuda_ctx** out);
+int32_t bepucuda_destroy(bepucuda_ctx* ctx);
+const char* bepucuda_last_error(bepucuda_ctx* ctx);
+
+/* Static type registry query (mirrors TypeProcessor.BodiesPerConstraint / ConstrainedDegreesOfFreedom,
+ * Constraints/TypeProcessor.cs:L31-39, and sizeof(TPrestepData)/sizeof(Vector<float>)).
+ * Returns BEPUCUDA_ERR_UNSUPPORTED_TYPE for ids the device cannot solve. */
+int32_t bepucuda_type_info(int32_t type_id, int32_t* bodies_per_constraint, int32_t* prestep_floats, int32_t* impulse_floats);
+
+/* Optional: page-lock a host range (e.g. a BufferPool block, BepuUtilities/Memory/BufferPool.cs:L42) so the
+ * per-frame copies run at full PCIe/C2C speed. */
+int32_t bepucuda_host_register(bepucuda_ctx* ctx, void* ptr, int64_t bytes);
+int32_t bepucuda_host_unregister(bepucuda_ctx* ctx, void* ptr);
+
+/* Replaces: Solver.SubstepCount / VelocityIterationCount / VelocityIterationScheduler / FallbackBatchThreshold
+ * (BepuPhysics/SolveDescription.cs:L21-38). The scheduler is pre-evaluated host-side into one iteration count per
+ * substep (Solver_Solve.cs:L743-751). Batches with index >= fallback_batch_threshold are treated as the
+ * sequential fallback batch (Solver.cs:L1878-1884). */
+int32_t bepucuda_set_solve_description(bepucuda_ctx* ctx, int32_t substep_count,
+                                       const int32_t* velocity_iterations_per_substep,
+                                       int32_t fallback_batch_threshold);
+/* Replaces: the TIntegrationCallbacks type argument of Solver<T>/PoseIntegrator<T>. */
+int32_t bepucuda_set_integrator(bepucuda_ctx* ctx, const bepucuda_integrator_desc* desc);
+
+/* Replaces: reads of Bodies.ActiveSet.DynamicsState (BepuPhysics/BodySet.cs:L33). `body_dynamics` is the raw
+ * Buffer<BodyDynamics>.Memory: body_count records of 128 B (BepuPhysics/BodyProperties.cs:L11-46,L318-338). */
+int32_t bepucuda_upload_bodies(bepucuda_ctx* ctx, const void* body_dynamics, int32_t body_count);
+
+/* Replaces: iteration over Solver.ActiveSet.Batches[b].TypeBatches[t] (BepuPhysics/Solver.cs:L24-29,
+ * Constraints/TypeBatch.cs:L10-27). source_bundle_width = Vector<float>.Count on the host. */
+int32_t bepucuda_begin_constraints(bepucuda_ctx* ctx, int32_t source_bundle_width, int32_t batch_count);
+/* body_references / prestep / accumulated_impulses are TypeBatch.BodyReferences / PrestepData / AccumulatedImpulses
+ * .Memory in the reference's AOSOA layout (row = Vector<T>; bundle k lane i = constraint k*W+i,
+ * BepuUtilities/BundleIndexing.cs:L50). constraint_count = TypeBatch.ConstraintCount (includes interior empty
+ * lanes in the fallback batch). The accumulated_impulses pointer is retained until the next
+ * bepucuda_begin_constraints so bepucuda_download_impulses can write results back in place. */
+int32_t bepucuda_upload_type_batch(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index, int32_t type_id,
+                                   int32_t constraint_count,
+                                   const int32_t* body_references, const float* prestep, float* accumulated_impulses);
+/* Replaces: Solver.ConstrainedKinematicHandles (Solver.cs:L68), already mapped handle->index through
+ * Bodies.HandleToLocation. */
+int32_t bepucuda_set_constrained_kinematics(bepucuda_ctx* ctx, const int32_t* body_indices, int32_t count);
+/* Replaces: Solver.PrepareConstraintIntegrationResponsibilities (Solver_Solve.cs:L1072-1388): validates the batch
+ * invariant, levelises the fallback batch, computes which constraint lane owns each body's integration, builds the
+ * stage program and (re)captures the CUDA graph when topology changed. */
+int32_t bepucuda_end_constraints(bepucuda_ctx* ctx);
+
+/* Refresh only the per-frame contact data of an already-uploaded type batch (same topology): what the narrow phase
+ * rewrites every frame (CollisionDetection/NarrowPhaseConstraintUpdate.cs:L81-135). */
+int32_t bepucuda_update_type_batch(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index,
+                                   const float* prestep, float* accumulated_impulses);
+
+/* Replaces: Solver.Solve (Solver_Solve.cs:L1415-1484) + PoseIntegrator.IntegrateAfterSubstepping
+ * (PoseIntegrator.cs:L707-726). Asynchronous on the context stream. */
+int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt);
+/* Blocks until prior work is done. */
+int32_t bepucuda_synchronize(bepucuda_ctx* ctx);
+
+/* Replaces: the in-place writes to Bodies.ActiveSet.DynamicsState done by ScatterVelocities/ScatterPose/ScatterInertia
+ * (Bodies_GatherScatter.cs:L484-753). Writes pose, velocity and world inertia into 128-B records; local inertia and
+ * padding floats of the destination are left untouched. Blocks until done. */
+int32_t bepucuda_download_bodies(bepucuda_ctx* ctx, void* body_dynamics_out, int32_t body_count);
+/* Replaces: in-place accumulated impulse updates in TypeBatch.AccumulatedImpulses. Writes every registered host
+ * impulse buffer (the narrow phase reads them next frame). Blocks until done. */
+int32_t bepucuda_download_impulses(bepucuda_ctx* ctx);
+/* Replaces: in-place prestep mutation by IncrementallyUpdateForSubstep (contact depths). Test/diagnostic use. */
+int32_t bepucuda_download_prestep(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index, float* prestep_out);
+
+int32_t bepucuda_get_timings(bepucuda_ctx* ctx, bepucuda_timings* out);
+
+/* Multi-GPU (no reference counterpart). One context per rank/GPU, one process per GPU. Marks which
+ * local bodies are replicated on other ranks ("boundary bodies") and installs an exchange callback invoked on the
+ * context stream after every (batch, stage) that wrote a boundary body. The callback runs host-side stream-ordered
+ * work (e.g. enqueues an NCCL all-reduce of `count` floats at `delta` on `cuda_stream`); it must not block. */
+typedef int32_t (*bepucuda_exchange_fn)(void* user, void* delta, int64_t count, void* cuda_stream);
+int32_t bepucuda_set_boundary_bodies(bepucuda_ctx* ctx, const int32_t* body_indices, int32_t count,
+                                     bepucuda_exchange_fn exchange, void* user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEPUCUDA_H */

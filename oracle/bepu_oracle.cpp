@@ -1,0 +1,718 @@
+// ORACLE — test infrastructure only (see bepu_math.h). Driver: body gather/scatter, embedded integration, the substep loop,
+// integration responsibilities and the final pose pass, restated from the reference's single-threaded executable spec.
+// PARITY UNPINNED: no golden vectors exist in the reference for this path; fidelity is by construction + self-checks.
+#include "bepu_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "bepu_contacts.h"
+#include "bepu_joints.h"
+
+namespace bepu_oracle {
+
+// BepuPhysics/Bodies_GatherScatter.cs:L107-139
+static constexpr uint32_t kDynamicLimit = 1u << 30;
+static constexpr int32_t kBodyReferenceMask = (int32_t)~((1u << 31) | (1u << 30));
+
+template <class F> struct BodyIn {
+    V3<F> pos;
+    Q4<F> q;
+    Inertia<F> inertia;
+};
+
+template <class F> struct TypeOps {
+    int bodies = 0, prestep_rows = 0, impulse_rows = 0;
+    void (*warm_start)(const BodyIn<F>*, const Rows<F>&, const Rows<F>&, Velocity<F>*) = nullptr;
+    void (*solve)(const BodyIn<F>*, float, float, const Rows<F>&, const Rows<F>&, Velocity<F>*) = nullptr;
+    void (*incremental)(float, const Velocity<F>*, const Rows<F>&) = nullptr;
+};
+
+// ---- adapters from the typed functions to the uniform table -----------------------------------------------------
+template <class F, class T> struct Adapt2 {  // two-body contact style: only inertias needed
+    static void ws(const BodyIn<F>* b, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) { T::warm_start(b[0].inertia, b[1].inertia, p, a, v[0], v[1]); }
+    static void sv(const BodyIn<F>* b, float dt, float idt, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) { T::solve(b[0].inertia, b[1].inertia, dt, idt, p, a, v[0], v[1]); }
+    static void inc(float dt, const Velocity<F>* v, const Rows<F>& p) { T::incremental_update(dt, v[0], v[1], p); }
+};
+template <class F, class T> struct Adapt1 {
+    static void ws(const BodyIn<F>* b, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) { T::warm_start(b[0].inertia, p, a, v[0]); }
+    static void sv(const BodyIn<F>* b, float dt, float idt, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) { T::solve(b[0].inertia, dt, idt, p, a, v[0]); }
+    static void inc(float dt, const Velocity<F>* v, const Rows<F>& p) { T::incremental_update(dt, v[0], p); }
+};
+// joint style: full pose + inertia per body; T::warm_start(const BodyIn<F>*, p, a, v), T::solve(const BodyIn<F>*, dt, idt, p, a, v)
+template <class F, class T> struct AdaptJ {
+    static void ws(const BodyIn<F>* b, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) {
+        T::warm_start(b[0].pos, b[0].q, b[0].inertia, b[1].pos, b[1].q, b[1].inertia, p, a, v[0], v[1]);
+    }
+    static void sv(const BodyIn<F>* b, float dt, float idt, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) {
+        T::solve(b[0].pos, b[0].q, b[0].inertia, b[1].pos, b[1].q, b[1].inertia, dt, idt, p, a, v[0], v[1]);
+    }
+};
+template <class F, class T> struct AdaptJ1 {
+    static void ws(const BodyIn<F>* b, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) { T::warm_start(b[0].pos, b[0].q, b[0].inertia, p, a, v[0]); }
+    static void sv(const BodyIn<F>* b, float dt, float idt, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) {
+        T::solve(b[0].pos, b[0].q, b[0].inertia, dt, idt, p, a, v[0]);
+    }
+};
+
+template <class F> struct Registry {
+    TypeOps<F> ops[64];
+    template <class T> void contact2(int id) {
+        ops[id].bodies = 2; ops[id].prestep_rows = T::L::kPrestepRows; ops[id].impulse_rows = T::L::kImpulseRows;
+        ops[id].warm_start = &Adapt2<F, T>::ws; ops[id].solve = &Adapt2<F, T>::sv; ops[id].incremental = &Adapt2<F, T>::inc;
+    }
+    template <class T> void contact1(int id) {
+        ops[id].bodies = 1; ops[id].prestep_rows = T::L::kPrestepRows; ops[id].impulse_rows = T::L::kImpulseRows;
+        ops[id].warm_start = &Adapt1<F, T>::ws; ops[id].solve = &Adapt1<F, T>::sv; ops[id].incremental = &Adapt1<F, T>::inc;
+    }
+    template <class T> void joint2(int id) {
+        ops[id].bodies = 2; ops[id].prestep_rows = T::kPrestepRows; ops[id].impulse_rows = T::kImpulseRows;
+        ops[id].warm_start = &AdaptJ<F, T>::ws; ops[id].solve = &AdaptJ<F, T>::sv; ops[id].incremental = nullptr;
+    }
+    template <class T> void joint1(int id) {
+        ops[id].bodies = 1; ops[id].prestep_rows = T::kPrestepRows; ops[id].impulse_rows = T::kImpulseRows;
+        ops[id].warm_start = &AdaptJ1<F, T>::ws; ops[id].solve = &AdaptJ1<F, T>::sv; ops[id].incremental = nullptr;
+    }
+    Registry() {
+        // BatchTypeId constants: Contact/ContactConvexTypes.cs, ContactNonconvexTypes.cs and each joint file.
+        contact1<ConvexOneBody<F, 1>>(0); contact1<ConvexOneBody<F, 2>>(1); contact1<ConvexOneBody<F, 3>>(2); contact1<ConvexOneBody<F, 4>>(3);
+        contact2<ConvexTwoBody<F, 1>>(4); contact2<ConvexTwoBody<F, 2>>(5); contact2<ConvexTwoBody<F, 3>>(6); contact2<ConvexTwoBody<F, 4>>(7);
+        contact1<NonconvexOneBody<F, 2>>(8); contact1<NonconvexOneBody<F, 3>>(9); contact1<NonconvexOneBody<F, 4>>(10);
+        contact2<NonconvexTwoBody<F, 2>>(15); contact2<NonconvexTwoBody<F, 3>>(16); contact2<NonconvexTwoBody<F, 4>>(17);
+        register_joints(*this);
+    }
+};
+template <class F> static const Registry<F>& registry() {
+    static Registry<F> r;
+    return r;
+}
+
+// ---- gather / scatter: Bodies_GatherScatter.cs:L267-478 (gather), L484-549 (pose), L553-622 (inertia), L626-753 (velocity) ----
+template <class F>
+static inline void gather_state(const float* bodies, const int32_t* refs, bool worldInertia, BodyIn<F>& b, Velocity<F>& v) {
+    constexpr int PW = LaneTraits<F>::Width;
+    for (int l = 0; l < PW; ++l) {
+        int32_t enc = refs[l];
+        if (enc < 0) {  // empty lane -> zeros
+            set_lane(b.q.x, l, 0.f); set_lane(b.q.y, l, 0.f); set_lane(b.q.z, l, 0.f); set_lane(b.q.w, l, 0.f);
+            set_lane(b.pos.x, l, 0.f); set_lane(b.pos.y, l, 0.f); set_lane(b.pos.z, l, 0.f);
+            set_lane(v.lin.x, l, 0.f); set_lane(v.lin.y, l, 0.f); set_lane(v.lin.z, l, 0.f);
+            set_lane(v.ang.x, l, 0.f); set_lane(v.ang.y, l, 0.f); set_lane(v.ang.z, l, 0.f);
+            set_lane(b.inertia.t.xx, l, 0.f); set_lane(b.inertia.t.yx, l, 0.f); set_lane(b.inertia.t.yy, l, 0.f);
+            set_lane(b.inertia.t.zx, l, 0.f); set_lane(b.inertia.t.zy, l, 0.f); set_lane(b.inertia.t.zz, l, 0.f);
+            set_lane(b.inertia.inv_mass, l, 0.f);
+            continue;
+        }
+        const float* s = bodies + (size_t)(enc & kBodyReferenceMask) * 32;
+        set_lane(b.q.x, l, s[0]); set_lane(b.q.y, l, s[1]); set_lane(b.q.z, l, s[2]); set_lane(b.q.w, l, s[3]);
+        set_lane(b.pos.x, l, s[4]); set_lane(b.pos.y, l, s[5]); set_lane(b.pos.z, l, s[6]);
+        set_lane(v.lin.x, l, s[8]); set_lane(v.lin.y, l, s[9]); set_lane(v.lin.z, l, s[10]);
+        set_lane(v.ang.x, l, s[12]); set_lane(v.ang.y, l, s[13]); set_lane(v.ang.z, l, s[14]);
+        const float* in = s + (worldInertia ? 24 : 16);
+        set_lane(b.inertia.t.xx, l, in[0]); set_lane(b.inertia.t.yx, l, in[1]); set_lane(b.inertia.t.yy, l, in[2]);
+        set_lane(b.inertia.t.zx, l, in[3]); set_lane(b.inertia.t.zy, l, in[4]); set_lane(b.inertia.t.zz, l, in[5]);
+        set_lane(b.inertia.inv_mass, l, in[6]);
+    }
+}
+template <class F> static inline void scatter_velocities(float* bodies, const int32_t* refs, const Velocity<F>& v) {
+    constexpr int PW = LaneTraits<F>::Width;
+    for (int l = 0; l < PW; ++l) {
+        uint32_t enc = (uint32_t)refs[l];
+        if (enc >= kDynamicLimit) continue;  // kinematic or empty
+        float* s = bodies + (size_t)enc * 32;
+        s[8] = get_lane(v.lin.x, l); s[9] = get_lane(v.lin.y, l); s[10] = get_lane(v.lin.z, l);
+        s[12] = get_lane(v.ang.x, l); s[13] = get_lane(v.ang.y, l); s[14] = get_lane(v.ang.z, l);
+    }
+}
+template <class F> static inline void scatter_pose(float* bodies, const int32_t* refs, const bool* mask, const V3<F>& pos, const Q4<F>& q) {
+    constexpr int PW = LaneTraits<F>::Width;
+    for (int l = 0; l < PW; ++l) {
+        if (!mask[l]) continue;
+        float* s = bodies + (size_t)(refs[l] & kBodyReferenceMask) * 32;
+        s[0] = get_lane(q.x, l); s[1] = get_lane(q.y, l); s[2] = get_lane(q.z, l); s[3] = get_lane(q.w, l);
+        s[4] = get_lane(pos.x, l); s[5] = get_lane(pos.y, l); s[6] = get_lane(pos.z, l);
+    }
+}
+template <class F> static inline void scatter_world_inertia(float* bodies, const int32_t* refs, const bool* mask, const Inertia<F>& in) {
+    constexpr int PW = LaneTraits<F>::Width;
+    for (int l = 0; l < PW; ++l) {
+        if (!mask[l]) continue;
+        float* s = bodies + (size_t)(refs[l] & kBodyReferenceMask) * 32 + 24;
+        s[0] = get_lane(in.t.xx, l); s[1] = get_lane(in.t.yx, l); s[2] = get_lane(in.t.yy, l);
+        s[3] = get_lane(in.t.zx, l); s[4] = get_lane(in.t.zy, l); s[5] = get_lane(in.t.zz, l);
+        s[6] = get_lane(in.inv_mass, l);
+    }
+}
+template <class F> static inline MaskOf<F> make_mask(const bool* m);
+template <> inline bool make_mask<float>(const bool* m) { return m[0]; }
+template <> inline i8 make_mask<f8>(const bool* m) {
+    i8 r = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 8; ++i) r[i] = m[i] ? -1 : 0;
+    return r;
+}
+
+// ---- integration: PoseIntegrator.cs:L99-261, Demos/DemoCallbacks.cs:L79-105 ----------------------------------------
+struct Callbacks {
+    float gravity[3];
+    float linear_damping, angular_damping;
+    int angular_mode;
+    bool allow_substeps_unconstrained, integrate_kinematic_velocity;
+    // PrepareForIntegration products
+    float gravity_dt[3];
+    float linear_damping_dt, angular_damping_dt;
+    void prepare(float dt) {  // DemoCallbacks.cs:L79-86
+        auto clamp01 = [](float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); };
+        linear_damping_dt = powf(clamp01(1 - linear_damping), dt);
+        angular_damping_dt = powf(clamp01(1 - angular_damping), dt);
+        for (int i = 0; i < 3; ++i) gravity_dt[i] = gravity[i] * dt;
+    }
+    template <class F> void integrate_velocity(Velocity<F>& v) const {  // DemoCallbacks.cs:L99-102
+        V3<F> g{bc<F>(gravity_dt[0]), bc<F>(gravity_dt[1]), bc<F>(gravity_dt[2])};
+        v.lin = scale(add(v.lin, g), bc<F>(linear_damping_dt));
+        v.ang = scale(v.ang, bc<F>(angular_damping_dt));
+    }
+};
+
+// PoseIntegrator.cs:L146-164 Integrate(QuaternionWide)
+template <class F> static inline Q4<F> integrate_orientation(const Q4<F>& start, const V3<F>& angularVelocity, const F& halfDt) {
+    F speed = length(angularVelocity);
+    F halfAngle = speed * halfDt;
+    F s = sin_approx(halfAngle);
+    F scl = s / speed;
+    Q4<F> q{angularVelocity.x * scl, angularVelocity.y * scl, angularVelocity.z * scl, cos_approx(halfAngle)};
+    Q4<F> end = normalize(concatenate(start, q));
+    MaskOf<F> speedValid = gt(speed, bc<F>(1e-15f));
+    return sel4<F>(speedValid, end, start);
+}
+// PoseIntegrator.cs:L166-175
+template <class F> static inline Sym3<F> rotate_inverse_inertia(const Sym3<F>& local, const Q4<F>& q) {
+    M33<F> r = matrix_from_quaternion(q);
+    return rotation_sandwich(r, local);
+}
+// Matrix3x3Wide.cs Invert (general 3x3, adjugate form), used by the gyroscopic mode.
+template <class F> static inline M33<F> invert33(const M33<F>& m) {
+    F m11 = m.y.y * m.z.z - m.z.y * m.y.z;
+    F m21 = m.y.z * m.z.x - m.z.z * m.y.x;
+    F m31 = m.y.x * m.z.y - m.z.x * m.y.y;
+    F determinantInverse = bc<F>(1.0f) / (m11 * m.x.x + m21 * m.x.y + m31 * m.x.z);
+    F m12 = m.z.y * m.x.z - m.x.y * m.z.z;
+    F m22 = m.z.z * m.x.x - m.x.z * m.z.x;
+    F m32 = m.z.x * m.x.y - m.x.x * m.z.y;
+    F m13 = m.x.y * m.y.z - m.y.y * m.x.z;
+    F m23 = m.x.z * m.y.x - m.y.z * m.x.x;
+    F m33 = m.x.x * m.y.y - m.y.x * m.x.y;
+    M33<F> r;
+    r.x.x = m11 * determinantInverse; r.y.x = m21 * determinantInverse; r.z.x = m31 * determinantInverse;
+    r.x.y = m12 * determinantInverse; r.y.y = m22 * determinantInverse; r.z.y = m32 * determinantInverse;
+    r.x.z = m13 * determinantInverse; r.y.z = m23 * determinantInverse; r.z.z = m33 * determinantInverse;
+    return r;
+}
+// PoseIntegrator.cs:L180-190
+template <class F> static inline void fallback_if_inertia_incompatible(const V3<F>& previous, V3<F>& w) {
+    F inf = bc<F>(INFINITY);
+    MaskOf<F> useNew = mand(lt(vabs(w.x), inf), mand(lt(vabs(w.y), inf), lt(vabs(w.z), inf)));
+    w = sel3<F>(useNew, w, previous);
+}
+// PoseIntegrator.cs:L192-206
+template <class F>
+static inline void integrate_angular_conserve_momentum(const Q4<F>& previousOrientation, const Sym3<F>& localInverseInertia, const Sym3<F>& worldInverseInertia, V3<F>& w) {
+    M33<F> prevR = matrix_from_quaternion(previousOrientation);
+    V3<F> localPrevW = transform_by_transposed(w, prevR);
+    Sym3<F> localInertiaTensor = invert(localInverseInertia);
+    V3<F> localAngularMomentum = transform(localPrevW, localInertiaTensor);
+    V3<F> angularMomentum = transform(localAngularMomentum, prevR);
+    V3<F> previous = w;
+    w = transform(angularMomentum, worldInverseInertia);
+    fallback_if_inertia_incompatible(previous, w);
+}
+// PoseIntegrator.cs:L208-253
+template <class F>
+static inline void integrate_angular_gyroscopic(const Q4<F>& orientation, const Sym3<F>& localInverseInertia, V3<F>& w, const F& dt) {
+    M33<F> R = matrix_from_quaternion(orientation);
+    V3<F> localW = transform_by_transposed(w, R);
+    Sym3<F> I = invert(localInverseInertia);
+    V3<F> localMomentum = transform(localW, I);
+    V3<F> residual = scale(cross(localMomentum, localW), dt);
+    // Matrix3x3Wide.CreateCrossProduct: X = (0, -v.Z, v.Y), Y = (v.Z, 0, -v.X), Z = (-v.Y, v.X, 0)
+    F zero = bc<F>(0.0f);
+    M33<F> skewMomentum{{zero, -localMomentum.z, localMomentum.y}, {localMomentum.z, zero, -localMomentum.x}, {-localMomentum.y, localMomentum.x, zero}};
+    M33<F> skewVelocity{{zero, -localW.z, localW.y}, {localW.z, zero, -localW.x}, {-localW.y, localW.x, zero}};
+    M33<F> transformedSkewVelocity = multiply(skewVelocity, I);
+    M33<F> change;
+    change.x = scale(sub(transformedSkewVelocity.x, skewMomentum.x), dt);
+    change.y = scale(sub(transformedSkewVelocity.y, skewMomentum.y), dt);
+    change.z = scale(sub(transformedSkewVelocity.z, skewMomentum.z), dt);
+    // jacobian = localInertiaTensor + change (Symmetric3x3Wide + Matrix3x3Wide)
+    M33<F> J;
+    J.x = {I.xx + change.x.x, I.yx + change.x.y, I.zx + change.x.z};
+    J.y = {I.yx + change.y.x, I.yy + change.y.y, I.zy + change.y.z};
+    J.z = {I.zx + change.z.x, I.zy + change.z.y, I.zz + change.z.z};
+    M33<F> invJ = invert33(J);
+    V3<F> newtonStep = transform(residual, invJ);
+    localW = sub(localW, newtonStep);
+    V3<F> previous = w;
+    w = transform(localW, R);
+    fallback_if_inertia_incompatible(previous, w);
+}
+
+// TypeProcessor.cs:L1204-1248 IntegratePoseAndVelocity
+template <class F>
+static inline void integrate_pose_and_velocity(const Callbacks& cb, const Inertia<F>& local, float dt, const MaskOf<F>& mask, V3<F>& pos, Q4<F>& q, Velocity<F>& v, Inertia<F>& world) {
+    F dtWide = bc<F>(dt);
+    V3<F> newPosition = add(pos, scale(v.lin, dtWide));
+    pos = sel3<F>(mask, newPosition, pos);
+    world.inv_mass = local.inv_mass;
+    Velocity<F> previousVelocity = v;
+    F halfDt = dtWide * bc<F>(0.5f);
+    if (cb.angular_mode == 1) {
+        Q4<F> previousOrientation = q;
+        Q4<F> newOrientation = integrate_orientation(q, v.ang, halfDt);
+        q = sel4<F>(mask, newOrientation, q);
+        world.t = rotate_inverse_inertia(local.t, q);
+        integrate_angular_conserve_momentum(previousOrientation, local.t, world.t, v.ang);
+    } else if (cb.angular_mode == 2) {
+        Q4<F> newOrientation = integrate_orientation(q, v.ang, halfDt);
+        q = sel4<F>(mask, newOrientation, q);
+        world.t = rotate_inverse_inertia(local.t, q);
+        integrate_angular_gyroscopic(q, local.t, v.ang, dtWide);
+    } else {
+        Q4<F> newOrientation = integrate_orientation(q, v.ang, halfDt);
+        q = sel4<F>(mask, newOrientation, q);
+        world.t = rotate_inverse_inertia(local.t, q);
+    }
+    cb.integrate_velocity(v);
+    v.lin = sel3<F>(mask, v.lin, previousVelocity.lin);
+    v.ang = sel3<F>(mask, v.ang, previousVelocity.ang);
+}
+// TypeProcessor.cs:L1251-1283 IntegrateVelocity
+template <class F>
+static inline void integrate_velocity_only(const Callbacks& cb, const Inertia<F>& local, float dt, const MaskOf<F>& mask, bool conditional, const Q4<F>& q, Velocity<F>& v, Inertia<F>& world) {
+    world.inv_mass = local.inv_mass;
+    world.t = rotate_inverse_inertia(local.t, q);
+    if (cb.angular_mode == 1) {
+        Q4<F> previousOrientation = integrate_orientation(q, v.ang, bc<F>(dt * -0.5f));
+        integrate_angular_conserve_momentum(previousOrientation, local.t, world.t, v.ang);
+    } else if (cb.angular_mode == 2) {
+        integrate_angular_gyroscopic(q, local.t, v.ang, bc<F>(dt));
+    }
+    if (conditional) {
+        Velocity<F> previousVelocity = v;
+        cb.integrate_velocity(v);
+        v.lin = sel3<F>(mask, v.lin, previousVelocity.lin);
+        v.ang = sel3<F>(mask, v.ang, previousVelocity.ang);
+    } else {
+        cb.integrate_velocity(v);
+    }
+}
+
+// ---- solver state ---------------------------------------------------------------------------------------------------
+struct Bitset {
+    std::vector<uint64_t> w;
+    void resize(size_t bits) { w.assign((bits + 63) / 64, 0); }
+    bool get(size_t i) const { return (w[i >> 6] >> (i & 63)) & 1; }
+    void set(size_t i) { w[i >> 6] |= (uint64_t)1 << (i & 63); }
+    bool any() const {
+        for (auto x : w) if (x) return true;
+        return false;
+    }
+};
+
+struct TypeBatchFlags {
+    Bitset slot[4];
+    bool coarse = false;
+};
+
+struct Solver {
+    oracle_scene* sc;
+    Callbacks cb;
+    std::vector<std::vector<TypeBatchFlags>> flags;  // [batch][typeBatch], batch 0 unused
+    Bitset constrained;                              // merged constrained body set (+ constrained kinematics)
+};
+
+enum BundleMode { kNone = 0, kPartial = 1, kAll = 2 };
+// TypeProcessor.cs:L1155-1202 BundleShouldIntegrate
+static inline BundleMode bundle_should_integrate(const Bitset& f, int bundleIndex, int W, int constraintCount, bool* laneMask) {
+    int start = bundleIndex * W;
+    int set = 0;
+    for (int i = 0; i < W; ++i) {
+        int idx = start + i;
+        bool b = idx < constraintCount && f.get(idx);
+        laneMask[i] = b;
+        set += b;
+    }
+    if (set == W) return kAll;
+    if (set > 0) return kPartial;
+    return kNone;
+}
+
+// Solver_Solve.cs:L1072-1388 PrepareConstraintIntegrationResponsibilities (+ L951-1044)
+static void prepare_integration_responsibilities(Solver& s) {
+    oracle_scene& sc = *s.sc;
+    const int W = sc.bundle_width;
+    s.constrained.resize(sc.body_count);
+    s.flags.assign(sc.batch_count, {});
+    Bitset merged;
+    merged.resize(sc.body_count);
+    for (int b = 0; b < sc.batch_count; ++b) {
+        oracle_batch& batch = sc.batches[b];
+        // batchReferencedHandles[b]: dynamic bodies referenced by this batch
+        Bitset referenced;
+        referenced.resize(sc.body_count);
+        for (int t = 0; t < batch.type_batch_count; ++t) {
+            oracle_type_batch& tb = batch.type_batches[t];
+            int nb = registry<float>().ops[tb.type_id].bodies;
+            int bundles = (tb.constraint_count + W - 1) / W;
+            for (int k = 0; k < bundles; ++k)
+                for (int slot = 0; slot < nb; ++slot)
+                    for (int l = 0; l < W; ++l) {
+                        int32_t enc = tb.body_references[((size_t)k * nb + slot) * W + l];
+                        if ((uint32_t)enc < kDynamicLimit) referenced.set(enc);
+                    }
+        }
+        if (b > 0) {
+            // bodiesFirstObservedInBatches[b] = referenced & ~merged
+            Bitset first;
+            first.resize(sc.body_count);
+            for (size_t i = 0; i < first.w.size(); ++i) first.w[i] = referenced.w[i] & ~merged.w[i];
+            const bool isFallback = b == sc.fallback_batch_threshold;
+            // For the fallback: earliest (typeBatchIndex, indexInTypeBatch) among each body's constraints (L996-1019).
+            std::vector<uint64_t> earliest;
+            if (isFallback) {
+                earliest.assign(sc.body_count, UINT64_MAX);
+                for (int t = 0; t < batch.type_batch_count; ++t) {
+                    oracle_type_batch& tb = batch.type_batches[t];
+                    int nb = registry<float>().ops[tb.type_id].bodies;
+                    for (int c = 0; c < tb.constraint_count; ++c)
+                        for (int slot = 0; slot < nb; ++slot) {
+                            int32_t enc = tb.body_references[((size_t)(c / W) * nb + slot) * W + (c % W)];
+                            if (enc == -1) continue;
+                            int idx = enc & kBodyReferenceMask;
+                            uint64_t cand = ((uint64_t)t << 32) | (uint32_t)c;
+                            if (cand < earliest[idx]) earliest[idx] = cand;
+                        }
+                }
+            }
+            s.flags[b].resize(batch.type_batch_count);
+            for (int t = 0; t < batch.type_batch_count; ++t) {
+                oracle_type_batch& tb = batch.type_batches[t];
+                int nb = registry<float>().ops[tb.type_id].bodies;
+                TypeBatchFlags& tf = s.flags[b][t];
+                for (int slot = 0; slot < nb; ++slot) tf.slot[slot].resize(tb.constraint_count);
+                for (int c = 0; c < tb.constraint_count; ++c)
+                    for (int slot = 0; slot < nb; ++slot) {
+                        int32_t enc = tb.body_references[((size_t)(c / W) * nb + slot) * W + (c % W)];
+                        if (enc == -1) continue;
+                        int idx = enc & kBodyReferenceMask;
+                        if (!first.get(idx)) continue;
+                        if (isFallback) {
+                            uint64_t slotKey = ((uint64_t)t << 32) | (uint32_t)c;
+                            if (slotKey == earliest[idx]) tf.slot[slot].set(c);
+                        } else {
+                            tf.slot[slot].set(c);
+                        }
+                    }
+                tf.coarse = false;
+                for (int slot = 0; slot < nb; ++slot) tf.coarse = tf.coarse || tf.slot[slot].any();
+            }
+        }
+        for (size_t i = 0; i < merged.w.size(); ++i) merged.w[i] |= referenced.w[i];
+    }
+    s.constrained = merged;
+    for (int i = 0; i < sc.constrained_kinematic_count; ++i) s.constrained.set(sc.constrained_kinematics[i]);  // L1372-1381
+}
+
+// ---- per-bundle stage evaluation -----------------------------------------------------------------------------------
+// WarmStart: {One,Two,...}BodyTypeProcessor.WarmStart (TwoBodyTypeProcessor.cs:L168-203) + GatherAndIntegrate (TypeProcessor.cs:L1298-1397)
+template <class F>
+static void warm_start_bundle(Solver& s, const TypeOps<F>& ops, oracle_type_batch& tb, int bundle, int batchIndex, const TypeBatchFlags* tf, bool allowPose, float dt) {
+    oracle_scene& sc = *s.sc;
+    const int W = sc.bundle_width;
+    constexpr int PW = LaneTraits<F>::Width;
+    const int nb = ops.bodies;
+    BundleMode mode[4];
+    bool laneMask[4][32];
+    for (int slot = 0; slot < nb; ++slot) {
+        const int32_t* refs = tb.body_references + ((size_t)bundle * nb + slot) * W;
+        if (batchIndex == 0) {
+            mode[slot] = kAll;  // BatchShouldAlwaysIntegrate: mask = dynamic lanes
+            for (int l = 0; l < W; ++l) laneMask[slot][l] = (uint32_t)refs[l] < kDynamicLimit;
+        } else if (!tf->coarse) {
+            mode[slot] = kNone;  // BatchShouldNeverIntegrate
+        } else {
+            mode[slot] = bundle_should_integrate(tf->slot[slot], bundle, W, tb.constraint_count, laneMask[slot]);
+        }
+    }
+    for (int chunk = 0; chunk < W / PW; ++chunk) {
+        BodyIn<F> body[4];
+        Velocity<F> vel[4];
+        for (int slot = 0; slot < nb; ++slot) {
+            const int32_t* refs = tb.body_references + ((size_t)bundle * nb + slot) * W + chunk * PW;
+            if (mode[slot] == kNone) {
+                gather_state<F>(sc.bodies, refs, true, body[slot], vel[slot]);
+                continue;
+            }
+            BodyIn<F> g;
+            gather_state<F>(sc.bodies, refs, false, g, vel[slot]);
+            const bool* m = laneMask[slot] + chunk * PW;
+            MaskOf<F> mask = make_mask<F>(m);
+            body[slot].pos = g.pos;
+            body[slot].q = g.q;
+            if (allowPose) {
+                integrate_pose_and_velocity<F>(s.cb, g.inertia, dt, mask, body[slot].pos, body[slot].q, vel[slot], body[slot].inertia);
+                scatter_pose<F>(sc.bodies, refs, m, body[slot].pos, body[slot].q);
+                scatter_world_inertia<F>(sc.bodies, refs, m, body[slot].inertia);
+            } else {
+                integrate_velocity_only<F>(s.cb, g.inertia, dt, mask, batchIndex != 0, body[slot].q, vel[slot], body[slot].inertia);
+                scatter_world_inertia<F>(sc.bodies, refs, m, body[slot].inertia);
+            }
+        }
+        Rows<F> p{tb.prestep + (size_t)bundle * ops.prestep_rows * W + chunk * PW, W};
+        Rows<F> a{tb.accumulated_impulses + (size_t)bundle * ops.impulse_rows * W + chunk * PW, W};
+        ops.warm_start(body, p, a, vel);
+        for (int slot = 0; slot < nb; ++slot) {
+            const int32_t* refs = tb.body_references + ((size_t)bundle * nb + slot) * W + chunk * PW;
+            scatter_velocities<F>(sc.bodies, refs, vel[slot]);
+        }
+    }
+}
+// Solve: TwoBodyTypeProcessor.cs:L205-225
+template <class F> static void solve_bundle(Solver& s, const TypeOps<F>& ops, oracle_type_batch& tb, int bundle, float dt, float inverseDt) {
+    oracle_scene& sc = *s.sc;
+    const int W = sc.bundle_width;
+    constexpr int PW = LaneTraits<F>::Width;
+    const int nb = ops.bodies;
+    for (int chunk = 0; chunk < W / PW; ++chunk) {
+        BodyIn<F> body[4];
+        Velocity<F> vel[4];
+        for (int slot = 0; slot < nb; ++slot)
+            gather_state<F>(sc.bodies, tb.body_references + ((size_t)bundle * nb + slot) * W + chunk * PW, true, body[slot], vel[slot]);
+        Rows<F> p{tb.prestep + (size_t)bundle * ops.prestep_rows * W + chunk * PW, W};
+        Rows<F> a{tb.accumulated_impulses + (size_t)bundle * ops.impulse_rows * W + chunk * PW, W};
+        ops.solve(body, dt, inverseDt, p, a, vel);
+        for (int slot = 0; slot < nb; ++slot)
+            scatter_velocities<F>(sc.bodies, tb.body_references + ((size_t)bundle * nb + slot) * W + chunk * PW, vel[slot]);
+    }
+}
+// IncrementallyUpdateForSubstep: TwoBodyTypeProcessor.cs:L228-241
+template <class F> static void incremental_bundle(Solver& s, const TypeOps<F>& ops, oracle_type_batch& tb, int bundle, float dt) {
+    oracle_scene& sc = *s.sc;
+    const int W = sc.bundle_width;
+    constexpr int PW = LaneTraits<F>::Width;
+    const int nb = ops.bodies;
+    for (int chunk = 0; chunk < W / PW; ++chunk) {
+        BodyIn<F> body[4];
+        Velocity<F> vel[4];
+        for (int slot = 0; slot < nb; ++slot)
+            gather_state<F>(sc.bodies, tb.body_references + ((size_t)bundle * nb + slot) * W + chunk * PW, true, body[slot], vel[slot]);
+        Rows<F> p{tb.prestep + (size_t)bundle * ops.prestep_rows * W + chunk * PW, W};
+        ops.incremental(dt, vel, p);
+    }
+}
+
+// ---- kinematic prepasses: PoseIntegrator.cs:L451-487, L493-535 -----------------------------------------------------
+static void integrate_kinematic_velocities(Solver& s) {
+    oracle_scene& sc = *s.sc;
+    for (int i = 0; i < sc.constrained_kinematic_count; ++i) {
+        int32_t idx = sc.constrained_kinematics[i];
+        BodyIn<float> b;
+        Velocity<float> v;
+        gather_state<float>(sc.bodies, &idx, false, b, v);
+        s.cb.integrate_velocity(v);
+        scatter_velocities<float>(sc.bodies, &idx, v);
+    }
+}
+static void integrate_kinematic_poses_and_velocities(Solver& s, float dt) {
+    oracle_scene& sc = *s.sc;
+    for (int i = 0; i < sc.constrained_kinematic_count; ++i) {
+        int32_t idx = sc.constrained_kinematics[i];
+        BodyIn<float> b;
+        Velocity<float> v;
+        gather_state<float>(sc.bodies, &idx, false, b, v);
+        b.pos = add(b.pos, scale(v.lin, dt));
+        b.q = integrate_orientation<float>(b.q, v.ang, dt * 0.5f);
+        bool m = true;
+        scatter_pose<float>(sc.bodies, &idx, &m, b.pos, b.q);
+        if (s.cb.integrate_kinematic_velocity) {
+            s.cb.integrate_velocity(v);
+            scatter_velocities<float>(sc.bodies, &idx, v);
+        }
+    }
+}
+
+// ---- final pass: PoseIntegrator.cs:L537-693 IntegrateBundlesAfterSubstepping ---------------------------------------
+static void integrate_after_substepping(Solver& s, float dt, int substepCount) {
+    oracle_scene& sc = *s.sc;
+    float substepDt = dt / substepCount;
+    float velocityIntegrationTimestep = s.cb.allow_substeps_unconstrained ? substepDt : dt;
+    s.cb.prepare(velocityIntegrationTimestep);  // L710-712
+#pragma omp parallel for schedule(static) num_threads(sc.threads > 0 ? sc.threads : 1)
+    for (int i = 0; i < sc.body_count; ++i) {
+        int32_t idx = i;
+        bool unconstrained = !s.constrained.get(i);
+        float effectiveDt = s.cb.allow_substeps_unconstrained ? substepDt : (unconstrained ? dt : substepDt);
+        float halfDt = effectiveDt * 0.5f;
+        BodyIn<float> b;
+        Velocity<float> v;
+        gather_state<float>(sc.bodies, &idx, false, b, v);
+        bool m = true;
+        if (!unconstrained) {
+            // Constrained bodies take one pose step of substep length (L684-691 and the masked first step of L632-682).
+            Q4<float> q = integrate_orientation<float>(b.q, v.ang, halfDt);
+            V3<float> p = add(b.pos, scale(v.lin, effectiveDt));
+            scatter_pose<float>(sc.bodies, &idx, &m, p, q);
+            continue;
+        }
+        bool kinematic = b.inertia.inv_mass == 0 && b.inertia.t.xx == 0 && b.inertia.t.yx == 0 && b.inertia.t.yy == 0 && b.inertia.t.zx == 0 && b.inertia.t.zy == 0 &&
+                         b.inertia.t.zz == 0;
+        bool integrateVelocity = s.cb.integrate_kinematic_velocity || !kinematic;
+        int steps = s.cb.allow_substeps_unconstrained ? substepCount : 1;
+        for (int step = 0; step < steps; ++step) {
+            if (integrateVelocity) s.cb.integrate_velocity(v);
+            b.pos = add(b.pos, scale(v.lin, effectiveDt));
+            if (s.cb.angular_mode == 1) {
+                Q4<float> previousOrientation = b.q;
+                b.q = integrate_orientation<float>(b.q, v.ang, halfDt);
+                Sym3<float> world = rotate_inverse_inertia(b.inertia.t, b.q);
+                V3<float> w = v.ang;
+                integrate_angular_conserve_momentum(previousOrientation, b.inertia.t, world, w);
+                v.ang = w;
+            } else if (s.cb.angular_mode == 2) {
+                b.q = integrate_orientation<float>(b.q, v.ang, halfDt);
+                V3<float> w = v.ang;
+                integrate_angular_gyroscopic(b.q, b.inertia.t, w, effectiveDt);
+                v.ang = w;
+            } else {
+                b.q = integrate_orientation<float>(b.q, v.ang, halfDt);
+            }
+            scatter_pose<float>(sc.bodies, &idx, &m, b.pos, b.q);
+            if (integrateVelocity) scatter_velocities<float>(sc.bodies, &idx, v);
+        }
+    }
+}
+
+// ---- the substep loop: Solver_Solve.cs:L1415-1479 ------------------------------------------------------------------
+template <class F> static void run_solve(Solver& s, float totalDt) {
+    oracle_scene& sc = *s.sc;
+    const int W = sc.bundle_width;
+    const auto& reg = registry<F>();
+    const int substepCount = sc.substep_count;
+    float substepDt = totalDt / substepCount;
+    s.cb.prepare(substepDt);
+    float inverseDt = 1.0f / substepDt;
+    const int threads = sc.threads > 0 ? sc.threads : 1;
+
+    // flattened (typeBatch, bundle) work lists per batch for the parallel driver
+    struct Work { int t, bundle; };
+    std::vector<std::vector<Work>> work(sc.batch_count);
+    for (int b = 0; b < sc.batch_count; ++b)
+        for (int t = 0; t < sc.batches[b].type_batch_count; ++t) {
+            int bundles = (sc.batches[b].type_batches[t].constraint_count + W - 1) / W;
+            for (int k = 0; k < bundles; ++k) work[b].push_back({t, k});
+        }
+
+    for (int substep = 0; substep < substepCount; ++substep) {
+        if (substep > 0) {
+            for (int b = 0; b < sc.batch_count; ++b) {
+                const int n = (int)work[b].size();
+#pragma omp parallel for schedule(static) num_threads(threads)
+                for (int i = 0; i < n; ++i) {
+                    oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
+                    const TypeOps<F>& ops = reg.ops[tb.type_id];
+                    if (ops.incremental) incremental_bundle<F>(s, ops, tb, work[b][i].bundle, substepDt);
+                }
+            }
+            integrate_kinematic_poses_and_velocities(s, substepDt);
+        } else if (s.cb.integrate_kinematic_velocity) {
+            integrate_kinematic_velocities(s);
+        }
+        for (int b = 0; b < sc.batch_count; ++b) {
+            const int n = (int)work[b].size();
+            const bool sequential = b >= sc.fallback_batch_threshold || threads == 1;
+            if (sequential) {
+                for (int i = 0; i < n; ++i) {
+                    oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
+                    warm_start_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, b, b > 0 ? &s.flags[b][work[b][i].t] : nullptr, substep > 0, substepDt);
+                }
+            } else {
+#pragma omp parallel for schedule(static) num_threads(threads)
+                for (int i = 0; i < n; ++i) {
+                    oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
+                    warm_start_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, b, b > 0 ? &s.flags[b][work[b][i].t] : nullptr, substep > 0, substepDt);
+                }
+            }
+        }
+        const int iterations = sc.velocity_iterations[substep];
+        for (int it = 0; it < iterations; ++it) {
+            for (int b = 0; b < sc.batch_count; ++b) {
+                const int n = (int)work[b].size();
+                const bool sequential = b >= sc.fallback_batch_threshold || threads == 1;
+                if (sequential) {
+                    for (int i = 0; i < n; ++i) {
+                        oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
+                        solve_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, substepDt, inverseDt);
+                    }
+                } else {
+#pragma omp parallel for schedule(static) num_threads(threads)
+                    for (int i = 0; i < n; ++i) {
+                        oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
+                        solve_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, substepDt, inverseDt);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace bepu_oracle
+
+using namespace bepu_oracle;
+
+extern "C" int32_t oracle_type_info(int32_t type_id, int32_t* bodies, int32_t* prestep_floats, int32_t* impulse_floats) {
+    if (type_id < 0 || type_id >= 64) return -1;
+    const TypeOps<float>& o = registry<float>().ops[type_id];
+    if (!o.solve) return -1;
+    if (bodies) *bodies = o.bodies;
+    if (prestep_floats) *prestep_floats = o.prestep_rows;
+    if (impulse_floats) *impulse_floats = o.impulse_rows;
+    return 0;
+}
+
+extern "C" int32_t oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+extern "C" int32_t oracle_solve(oracle_scene* sc, float dt) {
+    if (!sc || sc->substep_count < 1 || sc->bundle_width < 1 || sc->bundle_width > 32) return -1;
+    if (sc->simd && sc->bundle_width != 8) return -2;
+    for (int b = 0; b < sc->batch_count; ++b)
+        for (int t = 0; t < sc->batches[b].type_batch_count; ++t) {
+            int id = sc->batches[b].type_batches[t].type_id;
+            if (id < 0 || id >= 64 || !registry<float>().ops[id].solve) return -3;
+        }
+    Solver s;
+    s.sc = sc;
+    std::copy(sc->gravity, sc->gravity + 3, s.cb.gravity);
+    s.cb.linear_damping = sc->linear_damping;
+    s.cb.angular_damping = sc->angular_damping;
+    s.cb.angular_mode = sc->angular_integration_mode;
+    s.cb.allow_substeps_unconstrained = sc->allow_substeps_for_unconstrained != 0;
+    s.cb.integrate_kinematic_velocity = sc->integrate_velocity_for_kinematics != 0;
+    // Simulation.Solve: Simulation.cs:L278-290
+    prepare_integration_responsibilities(s);
+    if (sc->simd)
+        run_solve<f8>(s, dt);
+    else
+        run_solve<float>(s, dt);
+    integrate_after_substepping(s, dt, sc->substep_count);
+    return 0;
+}

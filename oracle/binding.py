@@ -1,0 +1,110 @@
+"""ORACLE — test infrastructure only. ctypes loader for oracle/libbepu_oracle.so and a helper that runs it on a host `Simulation`'s buffers
+(in place, like the reference's Simulation.Solve). PARITY UNPINNED: the reference has no golden vectors for this path and cannot run here."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OracleTypeBatch(C.Structure):
+    _fields_ = [("type_id", C.c_int32), ("constraint_count", C.c_int32), ("body_references", C.c_void_p), ("prestep", C.c_void_p), ("accumulated_impulses", C.c_void_p)]
+
+
+class OracleBatch(C.Structure):
+    _fields_ = [("type_batch_count", C.c_int32), ("type_batches", C.POINTER(OracleTypeBatch))]
+
+
+class OracleScene(C.Structure):
+    _fields_ = [
+        ("bodies", C.c_void_p), ("body_count", C.c_int32), ("batch_count", C.c_int32), ("batches", C.POINTER(OracleBatch)), ("bundle_width", C.c_int32),
+        ("substep_count", C.c_int32), ("velocity_iterations", C.POINTER(C.c_int32)), ("fallback_batch_threshold", C.c_int32),
+        ("gravity", C.c_float * 3), ("linear_damping", C.c_float), ("angular_damping", C.c_float), ("angular_integration_mode", C.c_int32),
+        ("allow_substeps_for_unconstrained", C.c_int32), ("integrate_velocity_for_kinematics", C.c_int32),
+        ("constrained_kinematics", C.c_void_p), ("constrained_kinematic_count", C.c_int32), ("threads", C.c_int32), ("simd", C.c_int32),
+    ]
+
+
+def build(force=False):
+    lib = os.path.join(HERE, "libbepu_oracle.so")
+    srcs = [os.path.join(HERE, f) for f in ("bepu_oracle.cpp", "bepu_oracle.h", "bepu_math.h", "bepu_contacts.h", "bepu_joints.h")]
+    if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
+        r = subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + r.stdout)
+    return lib
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(HERE, "libbepu_oracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.oracle_solve.argtypes = [C.POINTER(OracleScene), C.c_float]
+        _LIB.oracle_type_info.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    return _LIB
+
+
+def type_info(type_id):
+    b, p, d = C.c_int32(), C.c_int32(), C.c_int32()
+    if load().oracle_type_info(type_id, C.byref(b), C.byref(p), C.byref(d)) != 0:
+        return None
+    return b.value, p.value, d.value
+
+
+def max_threads():
+    return load().oracle_max_threads()
+
+
+def solve(simulation, dt, threads=1, simd=False):
+    """Runs the oracle's Simulation.Solve restatement in place on `simulation`'s buffers (bodies, prestep depths, accumulated impulses)."""
+    lib = load()
+    tbs = simulation.type_batches()
+    batch_count = simulation.batch_count
+    per_batch = [[] for _ in range(batch_count)]
+    for tb in tbs:
+        per_batch[tb.batch_index].append(tb)
+    keep = []
+    batches = (OracleBatch * max(batch_count, 1))()
+    for b in range(batch_count):
+        arr = (OracleTypeBatch * max(len(per_batch[b]), 1))()
+        for i, tb in enumerate(per_batch[b]):
+            arr[i].type_id = tb.type_id
+            arr[i].constraint_count = tb.constraint_count
+            arr[i].body_references = tb.body_references.ctypes.data
+            arr[i].prestep = tb.prestep.ctypes.data
+            arr[i].accumulated_impulses = tb.accumulated_impulses.ctypes.data
+        keep.append(arr)
+        batches[b].type_batch_count = len(per_batch[b])
+        batches[b].type_batches = arr
+    sc = OracleScene()
+    bodies = simulation.bodies
+    sc.bodies = bodies.ctypes.data if simulation.body_count else None
+    sc.body_count = simulation.body_count
+    sc.batch_count = batch_count
+    sc.batches = batches
+    sc.bundle_width = simulation.bundle_width
+    its = (C.c_int32 * len(simulation.velocity_iterations))(*simulation.velocity_iterations)
+    sc.substep_count = len(simulation.velocity_iterations)
+    sc.velocity_iterations = its
+    sc.fallback_batch_threshold = simulation.fallback_batch_threshold
+    d = simulation.integrator
+    for i in range(3):
+        sc.gravity[i] = d.gravity[i]
+    sc.linear_damping, sc.angular_damping = d.linear_damping, d.angular_damping
+    sc.angular_integration_mode = d.angular_integration_mode
+    sc.allow_substeps_for_unconstrained = d.allow_substeps_for_unconstrained
+    sc.integrate_velocity_for_kinematics = d.integrate_velocity_for_kinematics
+    kin = np.ascontiguousarray(simulation.constrained_kinematics, dtype=np.int32)
+    sc.constrained_kinematics = kin.ctypes.data if kin.size else None
+    sc.constrained_kinematic_count = int(kin.size)
+    sc.threads = threads
+    sc.simd = 1 if simd else 0
+    rc = lib.oracle_solve(C.byref(sc), dt)
+    if rc != 0:
+        raise RuntimeError("oracle_solve failed: %d" % rc)

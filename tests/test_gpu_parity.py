@@ -1,0 +1,87 @@
+"""GPU parity tests: libbepucuda (through the C ABI, via the host mirror's CudaTimestepper) against the CPU oracle on identical seeded
+scenes. Strict build (-fmad=false): bit-exact on body poses/velocities/world inertias, accumulated impulses and contact depths.
+Fast build (FMA contraction on): fp32 tolerance stated per test."""
+import numpy as np
+import pytest
+
+from bepuphysics2_b200 import scenes
+from bepuphysics2_b200.native import EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 60.0
+
+
+def _parity(scene, exact=True, mode=EXEC_GRAPH, frames=1, rtol=0.0, atol=0.0, **kw):
+    a = util.make_sim(scene, **kw)
+    b = util.make_sim(scene, **kw)
+    ref = util.run_oracle(a, DT, frames=frames)
+    got = util.run_gpu(b, DT, frames=frames, strict=exact, mode=mode)
+    util.compare(ref, got, exact=exact, rtol=rtol, atol=atol)
+    return got
+
+
+def test_box_stack_config1_bit_exact(libs):
+    """BASELINE config 1: 256-body box stack, Contact4 only, 1 velocity iteration."""
+    got = _parity(scenes.box_stacks(16, 16), substeps=1, velocity_iterations=1)
+    assert got["timings"]["constraint_count"] == 256
+    assert got["timings"]["device_batch_count"] == 2
+
+
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM])
+def test_box_stack_substepped_all_execution_modes(libs, mode):
+    _parity(scenes.box_stacks(8, 12), mode=mode, substeps=4, velocity_iterations=2, frames=3)
+
+
+def test_shape_pile_all_convex_types_bit_exact(libs):
+    """Types 0-7 (1-4 contacts, one and two body), 8 substeps x 2 iterations like BASELINE config 2, several frames."""
+    got = _parity(scenes.shape_pile(3000, seed=5), substeps=8, velocity_iterations=2, frames=2)
+    assert got["timings"]["constraint_iterations"] == got["timings"]["constraint_count"] * 16
+
+
+def test_shape_pile_nonconvex_types_bit_exact(libs):
+    _parity(scenes.shape_pile(2000, seed=7, nonconvex_fraction=0.5), substeps=3, velocity_iterations=[1, 2, 3])
+
+
+def test_shape_pile_persistent_mode_bit_exact(libs):
+    _parity(scenes.shape_pile(5000, seed=11), mode=EXEC_PERSISTENT, substeps=4, velocity_iterations=2, frames=2)
+
+
+def test_bundle_width_4_and_16_sources(libs):
+    """The host's Vector<float>.Count only changes the source layout; results are identical."""
+    for w in (4, 16):
+        _parity(scenes.shape_pile(800, seed=3), bundle_width=w, substeps=2, velocity_iterations=2)
+
+
+def test_sequential_fallback_batch_bit_exact(libs):
+    """Hub bodies exceed the fallback threshold: the fallback batch is levelised on the device, results match the sequential CPU loop."""
+    scene = scenes.fallback_stress(600, hubs=3, seed=5)
+    got = _parity(scene, fallback_batch_threshold=8, substeps=2, velocity_iterations=2, frames=2)
+    assert got["timings"]["fallback_level_count"] > 8
+
+
+def test_fast_build_within_tolerance(libs):
+    """FMA-contracted build: body velocities and accumulated impulses within 1e-3 relative (1e-4 absolute) of the oracle after one frame."""
+    _parity(scenes.shape_pile(3000, seed=5), exact=False, rtol=1e-3, atol=2e-4, substeps=8, velocity_iterations=2)
+
+
+def test_unconstrained_and_kinematic_bodies(libs):
+    """Bodies with no constraints take the IntegrateAfterSubstepping path; kinematics referenced by constraints take the prepass."""
+    scene = scenes.box_stacks(4, 4)
+    extra = scenes.make_bodies(np.array([[100, 5, 0], [120, 5, 0]], dtype=np.float32), linear=np.array([[1, 2, 3], [0, 0, 0]], dtype=np.float32),
+                               angular=np.array([[0.5, 0.1, -0.3], [0, 1, 0]], dtype=np.float32), inverse_mass=np.array([1, 0], dtype=np.float32),
+                               inverse_inertia=np.array([[2, 0, 2, 0, 0, 2], [0, 0, 0, 0, 0, 0]], dtype=np.float32))
+    scene["bodies"] = np.concatenate([scene["bodies"], extra])
+    scene["bodies"][0, 8:11] = (0.2, 0.0, 0.1)  # moving kinematic ground
+    scene["bodies"][0, 12:15] = (0.0, 0.3, 0.0)
+    for allow in (0, 1):
+        integ = util.bp.IntegratorDesc.default()
+        integ.allow_substeps_for_unconstrained = allow
+        _parity(scene, substeps=3, velocity_iterations=1, integrator=integ, frames=2)
+
+
+@pytest.mark.parametrize("angular_mode", [1, 2])
+def test_momentum_conserving_angular_modes(libs, angular_mode):
+    integ = util.bp.IntegratorDesc.default()
+    integ.angular_integration_mode = angular_mode
+    _parity(scenes.shape_pile(500, seed=9), substeps=3, velocity_iterations=1, integrator=integ)

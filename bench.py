@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — solver + integrator constraint-iterations/s (BASELINE.json metric) on synthetic scenes.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (libbepucuda through the C ABI)
+    python bench.py --impl reference --steps K --warmup W    reference arm: the CPU oracle (restatement of the reference; the C# reference
+                                                             itself cannot be built here) on all host cores, AVX2 8-wide like Vector<float>
+    N > 1: launched under torch.distributed.run, one rank per GPU. The path shards by independent islands: every rank
+    simulates its own pile, no data-path collective, weak scaling.
+
+A "step" is one Simulation.Solve: substeps x (incremental contact update, kinematic prepass, WarmStart with embedded integration per batch,
+velocity iterations x Solve per batch) + the final pose pass. Workload = BASELINE configs[1]: ShapePile-style pile, 100k bodies, 8 substeps x 2
+velocity iterations. Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 1.0 / 60.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bodies", type=int, default=100_000)
+    ap.add_argument("--substeps", type=int, default=8)
+    ap.add_argument("--iterations", type=int, default=2)
+    ap.add_argument("--scene", default="shape_pile", choices=["shape_pile", "ragdolls", "fallback_stress"])
+    ap.add_argument("--mode", default="persistent", choices=["graph", "persistent", "stream"])
+    ap.add_argument("--strict", action="store_true", help="use the -fmad=false build")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    return ap.parse_args()
+
+
+def make_scene(args, seed):
+    from bepuphysics2_b200 import scenes
+
+    if args.scene == "shape_pile":
+        return scenes.shape_pile(args.bodies, seed=seed)
+    if args.scene == "ragdolls":
+        return scenes.ragdolls(max(1, args.bodies // 16), seed=seed)
+    return scenes.fallback_stress(args.bodies, hubs=max(1, args.bodies // 1000), seed=seed)
+
+
+def build_sim(args, seed):
+    import bepuphysics2_b200 as bp
+    from bepuphysics2_b200 import scenes
+
+    scene = make_scene(args, seed)
+    sim = bp.Simulation(bundle_width=8, fallback_batch_threshold=64, substeps=args.substeps, velocity_iterations=args.iterations)
+    scenes.build(scene, sim)
+    return sim, scene["description"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                smax.append(float(s[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(args, steps, warmup, threads):
+    """The oracle (CPU restatement of the reference solver, AVX2 8-wide lanes, OpenMP over bundles within each batch stage) on the same workload."""
+    from oracle import binding as ob
+
+    sim, desc = build_sim(args, seed=5)
+    threads = threads or os.cpu_count() or 1
+    for _ in range(warmup):
+        ob.solve(sim, DT, threads=threads, simd=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ob.solve(sim, DT, threads=threads, simd=True)
+    dt = time.perf_counter() - t0
+    ci_per_step = sim.constraint_count * args.substeps * args.iterations
+    return {"value": ci_per_step * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": threads, "constraints": sim.constraint_count, "description": desc}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args, args.steps, args.warmup, args.cpu_threads)
+    line = {
+        "impl": "reference", "metric": "constraint-iterations/sec (solver+integrator)", "value": r["value"], "unit": "constraint-iterations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, r["description"]),
+        "cpu_baseline": {"value": r["value"], "unit": "constraint-iterations/s", "cores": r["cores"], "kind": "port",
+                         "sample": "%d full frames of the same workload (C++ restatement of the reference solver, AVX2 8-wide + OpenMP; the C# reference cannot be built here)" % args.steps},
+        "e2e": {"value": r["value"], "unit": "constraint-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, description):
+    return {"workload": "%s: %s; %d substeps x %d velocity iterations, dt 1/60" % (args.scene, description, args.substeps, args.iterations),
+            "bodies_per_gpu": args.bodies, "substeps": args.substeps, "velocity_iterations": args.iterations, "parallelism": "independent islands per GPU, no collective"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+
+    import bepuphysics2_b200 as bp
+    from bepuphysics2_b200.native import EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libbepucuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = {"graph": EXEC_GRAPH, "persistent": EXEC_PERSISTENT, "stream": EXEC_STREAM}[args.mode]
+
+    sim, description = build_sim(args, seed=5 + rank)  # every rank owns an independent pile (island)
+    ts = bp.CudaTimestepper(sim, device=local_rank, strict_fp=args.strict, execution_mode=mode)
+    ts.register_host_buffers()
+    ts.describe()
+    ts.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K solves, L2 flushed before each, timed with CUDA events on the context stream ----
+    def solve_once_timed():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ts.solve_device_only(DT)
+        return ts.timings().solve_ms  # get_timings synchronizes the context stream
+
+    for _ in range(max(args.warmup, 3)):
+        solve_once_timed()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        total_ms += solve_once_timed()
+    barrier()
+    clocks = sampler.stop()
+    t = ts.timings()
+    ci_per_step = int(t.constraint_iterations)
+    launches_per_step = int(t.kernel_launches)
+    alg_bytes_per_step = int(t.algorithmic_bytes)
+
+    # ---- end to end through the C ABI with host buffers: H2D of bodies + prestep + impulses, solve, D2H of bodies + impulses ----
+    for _ in range(2):
+        ts.refresh()
+        ts.solve(DT, download=True)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ts.refresh()
+        ts.solve(DT, download=True)
+    ts.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = ts.timings()
+    h2d, d2h = int(te.h2d_bytes), int(te.d2h_bytes)
+
+    # ---- per-stage device time (event pair around every launch) for the roofline of the dominant kernel ----
+    prof = None
+    if rank == 0:
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ts.profile_stages(DT)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        prof = ts.profile_stages(DT).as_dict()
+
+    times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([float(ci_per_step)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_ms_max = times.tolist()
+    ci_all = counts.item()
+
+    if rank == 0:
+        peak, peak_source = load_peaks()
+        value = ci_all * args.steps / (total_ms_max * 1e-3)
+        e2e_value = ci_all * e2e_steps / (e2e_ms_max * 1e-3)
+        if args.mode == "persistent":
+            # one kernel per step: the whole stage program
+            roof_bytes, roof_ms, roof_kernel = alg_bytes_per_step, total_ms / args.steps, "persistent_solve_kernel (whole step)"
+        else:
+            roof_bytes, roof_ms, roof_kernel = prof["solve"]["algorithmic_bytes"], prof["solve"]["ms"], "constraint_stage_kernel<Solve> (sum over %d launches per step)" % prof["solve"]["launches"]
+        achieved = roof_bytes / (roof_ms * 1e-3) / 1e9
+        line = {
+            "metric": "constraint-iterations/sec (solver+integrator)", "value": value, "unit": "constraint-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, description), execution_mode=args.mode, numerics="strict(-fmad=false)" if args.strict else "fast(fma)", l2="flushed (256 MiB write) before every timed step",
+                           constraints_per_gpu=int(t.constraint_count), device_batches=int(t.device_batch_count), stages_per_step=int(t.stage_count)),
+            "e2e": {"value": e2e_value, "unit": "constraint-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / e2e_steps, "steps": e2e_steps,
+                    "topology": "unchanged between steps (bodies + prestep + impulses re-uploaded, results downloaded)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_source, "algorithmic_bytes_per_step": alg_bytes_per_step},
+            "stage_profile_ms": {k: round(v["ms"], 4) for k, v in (prof or {}).items()},
+        }
+        if not args.no_cpu_baseline:
+            cb = cpu_reference_run(args, steps=3, warmup=1, threads=args.cpu_threads)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": "constraint-iterations/s", "cores": cb["cores"], "kind": "port",
+                                    "sample": "3 full frames of the same workload after 1 warm-up (C++ restatement of the reference solver, AVX2 8-wide + OpenMP over bundles; %.1f ms/frame)" % cb["ms_per_step"]}
+        print(json.dumps(line))
+    ts.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@ struct M23 { V3 x, y; };
 struct M33 { V3 x, y, z; };
 struct Velocity { V3 lin, ang; };
 struct Inertia { Sym3 t; float inv_mass; };
+struct BodyState { V3 pos; Q4 q; Inertia inertia; };  // what a constraint function may see of one body
 
 // minps / maxps semantics of Vector.Min / Vector.Max: (a < b) ? a : b, (a > b) ? a : b.
 BEPU_DI float fmin_ps(float a, float b) { return a < b ? a : b; }

@@ -19,7 +19,11 @@ namespace bepucuda {
 // Device body reference encoding (host encoding: Bodies_GatherScatter.cs:L107-139 has bit 30 = kinematic, -1 = empty).
 // The device adds bit 29: "this constraint lane owns the integration of this body" (the reference keeps that in
 // per-type-batch IndexSets, Solver_Solve.cs:L951-1044), so WarmStart needs no second flag stream.
-constexpr uint32_t kRefIndexMask = 0x1FFFFFFFu;
+// Bit 28: "some lane of this lane's SOURCE (host-width) bundle owns an integration for this body slot". Only consulted in the
+// momentum-conserving angular modes, where the reference's first-substep IntegrateVelocity applies the angular update to every
+// lane of a partially integrating bundle before masking (TypeProcessor.cs:L1251-1283), making results bundle-composition dependent.
+constexpr uint32_t kRefIndexMask = 0x0FFFFFFFu;
+constexpr uint32_t kRefBundleIntegratesBit = 1u << 28;
 constexpr uint32_t kRefIntegrateBit = 1u << 29;
 constexpr uint32_t kRefKinematicBit = 1u << 30;
 constexpr int32_t kRefEmpty = -1;

@@ -131,6 +131,29 @@ __global__ void ownership_pass2_kernel(const DeviceTypeBatch* __restrict__ tbs, 
         if (first_batch[idx] == tb.device_batch) *r = (int32_t)((uint32_t)enc | kRefIntegrateBit);
     }
 }
+// Pass 3: per SOURCE bundle and body slot, "does any lane integrate"; then broadcast that to every lane of the source bundle.
+__global__ void bundle_flags_pass_kernel(const DeviceTypeBatch* __restrict__ tbs, const TransposeDesc* __restrict__ descs, const WorkItem* __restrict__ work, int work_count,
+                                         int W, int32_t* source_bundle_flags, int phase) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const TransposeDesc d = descs[w.type_batch];
+    const int slot_index = w.bundle * 32 + lane;
+    const int c = d.map ? d.map[slot_index] : slot_index;
+    if (c < 0 || c >= d.src_count) return;
+    int32_t* flags = source_bundle_flags + ((size_t)d.src_bundle_base + (size_t)(c / W)) * 4;
+    for (int s = 0; s < d.bodies; ++s) {
+        int32_t* r = tb.refs + ((size_t)w.bundle * d.bodies + s) * 32 + lane;
+        const int32_t enc = *r;
+        if (enc < 0) continue;
+        if (phase == 0) {
+            if ((uint32_t)enc & kRefIntegrateBit) flags[s] = 1;
+        } else if (flags[s]) {
+            *r = (int32_t)((uint32_t)enc | kRefBundleIntegratesBit);
+        }
+    }
+}
 __global__ void check_invariant_kernel(int body_count, const int32_t* __restrict__ sync_refcount, const unsigned long long* __restrict__ sync_mask, int32_t* error_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= body_count) return;
@@ -172,11 +195,13 @@ void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
 }
 void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
                       int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
-                      int32_t* error_flag, cudaStream_t s) {
+                      int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s) {
     if (work_count > 0) {
         ownership_pass1_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, sync_batch_count, body_count, first_batch,
                                                                                          sync_refcount, sync_mask, error_flag);
         ownership_pass2_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, body_count, first_batch, constrained);
+        bundle_flags_pass_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, source_bundle_flags, 0);
+        bundle_flags_pass_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, source_bundle_flags, 1);
     }
     if (body_count > 0) check_invariant_kernel<<<blocks_for(body_count, 256), 256, 0, s>>>(body_count, sync_refcount, sync_mask, error_flag);
     if (kinematic_count > 0) mark_kinematics_kernel<<<blocks_for(kinematic_count, 128), 128, 0, s>>>(kinematics, kinematic_count, body_count, constrained, error_flag);

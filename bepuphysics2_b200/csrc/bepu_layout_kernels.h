@@ -14,6 +14,8 @@ struct TransposeDesc {
     const int32_t* map;   // destination slot -> source constraint index (fallback levels), or nullptr for identity
     int32_t src_count;    // TypeBatch.ConstraintCount of the source
     int32_t bodies, prestep_rows, impulse_rows;
+    int32_t src_bundle_base;  // index of the source type batch's first host-width bundle in the per-bundle flag array
+    int32_t pad;
 };
 enum { kTransposeRefs = 1, kTransposePrestep = 2, kTransposeImpulses = 4 };
 void launch_transpose_in_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s);
@@ -21,7 +23,7 @@ void launch_transpose_out_all(const DeviceTypeBatch* tbs, const TransposeDesc* d
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s);
 void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
                       int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
-                      int32_t* error_flag, cudaStream_t s);
+                      int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s);
 
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
 struct SolverLaunchers {

@@ -96,12 +96,6 @@ __device__ __noinline__ void integrate_angular_gyroscopic(Q4 orientation, Sym3 l
     fallback_if_inertia_incompatible(previous, w);
 }
 
-struct BodyState {
-    V3 pos;
-    Q4 q;
-    Inertia inertia;
-};
-
 // GatherAndIntegrate for one body slot of one lane (TypeProcessor.cs:L1298-1397). The lane integrates iff the device body
 // reference carries kRefIntegrateBit; all other lanes read the world inertia their owner constraint stored earlier in this
 // substep, which is bit-identical to what the reference's bundle-wide recompute would give them.
@@ -138,6 +132,18 @@ BEPU_DI void gather_for_warm_start(uint32_t enc, const BodyBuffers& B, const Fra
     } else {
         load_inertia(B.inertia_world, idx, b.inertia);
         if (NeedsPose) load_pose(B.pose, idx, b.pos, b.q);
+        if (STAGE == kStageWarmStartFirst && fp.angular_mode != 0 && (enc & kRefBundleIntegratesBit) && !(enc & kRefKinematicBit)) {
+            // Reference quirk, reproduced for identical results: in the first substep IntegrateVelocity runs the momentum-conserving angular
+            // update on EVERY lane of a bundle that contains an integrating lane and only masks the callback afterwards
+            // (TypeProcessor.cs:L1259-1281), so non-owning dynamic lanes of such a (host-width) bundle get the update too.
+            Inertia local;
+            load_inertia(B.inertia_local, idx, local);
+            V3 pos;
+            Q4 q;
+            load_pose(B.pose, idx, pos, q);
+            if (fp.angular_mode == 1) integrate_angular_conserve_momentum(integrate_orientation(q, v.ang, fp.dt * -0.5f), local.t, b.inertia.t, v.ang);
+            else integrate_angular_gyroscopic(q, local.t, v.ang, fp.dt);
+        }
     }
 }
 

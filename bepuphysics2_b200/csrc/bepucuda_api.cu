@@ -157,10 +157,11 @@ struct bepucuda_ctx {
     bool constraints_open = false, constraints_ready = false, data_dirty = false;
     std::vector<SourceTypeBatch> sources;
     ChunkArena raw_arena, pinned_arena;
-    DeviceBuffer refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
+    DeviceBuffer source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
     std::vector<DeviceTypeBatch> tbs;
     std::vector<TransposeDesc> tdescs;
     std::vector<WorkItem> work;                 // grouped by device batch, then the incremental list
+    std::vector<int32_t> bundle_live;           // live constraints per work item (parallel to `work`)
     std::vector<std::pair<int, int>> batch_work; // per device batch: (begin, count) into work
     int inc_work_begin = 0, inc_work_count = 0;
     int all_work_count = 0;                     // work[0 .. all_work_count) covers every bundle once
@@ -175,6 +176,8 @@ struct bepucuda_ctx {
 
     bepucuda_timings timings{};
     int64_t h2d_accum = 0;
+    cudaEvent_t user_events[16] = {};
+    std::vector<cudaEvent_t> profile_events;
 };
 
 namespace {
@@ -358,12 +361,15 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
     DeviceBuffer* bufs[] = {&ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
-                            &ctx->sync_mask, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
+                            &ctx->sync_mask, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev};
     for (auto b : bufs) b->release();
     ctx->raw_arena.release();
     ctx->pinned_arena.release();
     if (ctx->frame_params_host) cudaFreeHost(ctx->frame_params_host);
+    for (auto ev : ctx->user_events)
+        if (ev) cudaEventDestroy(ev);
+    for (auto ev : ctx->profile_events) cudaEventDestroy(ev);
     cudaEvent_t evs[] = {ctx->ev_solve_begin, ctx->ev_solve_end, ctx->ev_up_begin, ctx->ev_up_end, ctx->ev_down_begin, ctx->ev_down_end};
     for (auto ev : evs)
         if (ev) cudaEventDestroy(ev);
@@ -521,6 +527,13 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
         return a.batch_index != b.batch_index ? a.batch_index < b.batch_index : a.type_batch_index < b.type_batch_index;
     });
 
+    std::vector<int32_t> source_bundle_base(ctx->sources.size());
+    int32_t total_source_bundles = 0;
+    for (size_t si = 0; si < ctx->sources.size(); ++si) {
+        source_bundle_base[si] = total_source_bundles;
+        total_source_bundles += (ctx->sources[si].count + W - 1) / W;
+    }
+
     // ---- device batches: synchronized batches in order, then dependency levels of the sequential fallback batch ----
     ctx->tbs.clear();
     ctx->tdescs.clear();
@@ -542,7 +555,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
             d.type_id = s.type_id;
             d.bundle_count = (s.count + 31) / 32;
             d.device_batch = (int)batch_tbs.size() - 1;
-            TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows};
+            TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows, source_bundle_base[si], 0};
             s.device_tbs.push_back((int)ctx->tbs.size());
             batch_tbs.back().push_back((int)ctx->tbs.size());
             ctx->tbs.push_back(d);
@@ -623,7 +636,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
                     map_offset.push_back(maps.size());
                     for (size_t q = i; q < j; ++q) maps.push_back(slots[q].constraint);
                     for (int q = n; q < d.bundle_count * 32; ++q) maps.push_back(-1);
-                    TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows};
+                    TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows, source_bundle_base[source], 0};
                     s.device_tbs.push_back((int)ctx->tbs.size());
                     batch_tbs.back().push_back((int)ctx->tbs.size());
                     ctx->tbs.push_back(d);
@@ -657,18 +670,26 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
 
     // ---- work lists: per device batch (one warp per bundle), then the incremental-update list over all contact bundles ----
     ctx->work.clear();
+    ctx->bundle_live.clear();
     ctx->batch_work.clear();
+    auto live_in_bundle = [&](int tb, int k) {
+        // identity-mapped type batches: lanes beyond the source count are padding; mapped (fallback level) ones: -1 entries are padding
+        if (map_offset[tb] == SIZE_MAX) return std::max(0, std::min(32, ctx->tdescs[tb].src_count - k * 32));
+        int n = 0;
+        for (int l = 0; l < 32; ++l) n += maps[map_offset[tb] + (size_t)k * 32 + l] >= 0;
+        return n;
+    };
     for (auto& list : batch_tbs) {
         const int begin = (int)ctx->work.size();
         for (int tb : list)
-            for (int k = 0; k < ctx->tbs[tb].bundle_count; ++k) ctx->work.push_back({tb, k});
+            for (int k = 0; k < ctx->tbs[tb].bundle_count; ++k) { ctx->work.push_back({tb, k}); ctx->bundle_live.push_back(live_in_bundle(tb, k)); }
         ctx->batch_work.push_back({begin, (int)ctx->work.size() - begin});
     }
     ctx->all_work_count = (int)ctx->work.size();
     ctx->inc_work_begin = (int)ctx->work.size();
     for (size_t tb = 0; tb < ctx->tbs.size(); ++tb)
         if (get_type_info(ctx->tbs[tb].type_id)->incremental)
-            for (int k = 0; k < ctx->tbs[tb].bundle_count; ++k) ctx->work.push_back({(int)tb, k});
+            for (int k = 0; k < ctx->tbs[tb].bundle_count; ++k) { ctx->work.push_back({(int)tb, k}); ctx->bundle_live.push_back(live_in_bundle((int)tb, k)); }
     ctx->inc_work_count = (int)ctx->work.size() - ctx->inc_work_begin;
 
     // ---- upload tables ----
@@ -698,9 +719,12 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->sync_mask.ptr, 0, nb * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->constrained.ptr, 0, nb, ctx->stream));
     CK(cudaMemsetAsync(ctx->error_dev.ptr, 0, 4, ctx->stream));
+    CK(ctx->source_bundle_flags.reserve((size_t)std::max(total_source_bundles, 1) * 16));
+    CK(cudaMemsetAsync(ctx->source_bundle_flags.ptr, 0, (size_t)std::max(total_source_bundles, 1) * 16, ctx->stream));
     launch_ownership(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), ctx->sync_batch_count,
                      ctx->body_count, ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (unsigned long long*)ctx->sync_mask.ptr, ctx->constrained.as<uint8_t>(),
-                     ctx->kinematics_dev.as<int32_t>(), (int)ctx->kinematics.size(), ctx->error_dev.as<int32_t>(), ctx->stream);
+                     ctx->kinematics_dev.as<int32_t>(), (int)ctx->kinematics.size(), ctx->error_dev.as<int32_t>(), ctx->tdesc_table.as<TransposeDesc>(), W,
+                     ctx->source_bundle_flags.as<int32_t>(), ctx->stream);
     CK(cudaGetLastError());
     int32_t err = 0;
     CK(cudaMemcpyAsync(&err, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -870,6 +894,84 @@ int32_t bepucuda_get_timings(bepucuda_ctx* ctx, bepucuda_timings* out) {
     if (ctx->have_up && !ctx->up_open) cudaEventElapsedTime(&ctx->timings.upload_ms, ctx->ev_up_begin, ctx->ev_up_end);
     if (ctx->have_down) cudaEventElapsedTime(&ctx->timings.download_ms, ctx->ev_down_begin, ctx->ev_down_end);
     *out = ctx->timings;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_event_record(bepucuda_ctx* ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot >= 16) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "event_record: bad slot");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->user_events[slot]) CK(cudaEventCreate(&ctx->user_events[slot]));
+    CK(cudaEventRecord(ctx->user_events[slot], ctx->stream));
+    return BEPUCUDA_OK;
+}
+int32_t bepucuda_event_elapsed_ms(bepucuda_ctx* ctx, int32_t a, int32_t b, float* ms) {
+    if (!ctx || !ms || a < 0 || a >= 16 || b < 0 || b >= 16 || !ctx->user_events[a] || !ctx->user_events[b]) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "event_elapsed_ms: bad slots");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->user_events[b]));
+    CK(cudaEventElapsedTime(ms, ctx->user_events[a], ctx->user_events[b]));
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_profile* out) {
+    if (!ctx || !out || !(dt > 0)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "profile_stages: bad arguments");
+    if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages before end_constraints");
+    CK(cudaSetDevice(ctx->device));
+    std::memset(out, 0, sizeof(*out));
+    if (ctx->data_dirty) {
+        launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
+                                kTransposePrestep | kTransposeImpulses, ctx->stream);
+        ctx->data_dirty = false;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    compute_frame_params(ctx, dt, ctx->frame_params_host);
+    CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t need = ctx->program.size() * 2;
+    while (ctx->profile_events.size() < need) {
+        cudaEvent_t ev;
+        CK(cudaEventCreate(&ev));
+        ctx->profile_events.push_back(ev);
+    }
+    const DeviceTypeBatch* tbs = ctx->tb_table.as<DeviceTypeBatch>();
+    const WorkItem* work = ctx->work_table.as<WorkItem>();
+    const FrameParams* fp = ctx->frame_params_dev.as<FrameParams>();
+    const int32_t* kin = ctx->kinematics_dev.as<int32_t>();
+    std::vector<int> launched(ctx->program.size(), 0);
+    for (size_t i = 0; i < ctx->program.size(); ++i) {
+        const StageOp& op = ctx->program[i];
+        const bool has_work = op.stage == kStageFinalPose ? ctx->B.count > 0 : op.work_count > 0;
+        if (!has_work) continue;
+        CK(cudaEventRecord(ctx->profile_events[2 * i], ctx->stream));
+        if (op.stage <= kStageIncremental) ctx->launchers->constraint_stage(op.stage, tbs, work + op.work_begin, op.work_count, ctx->B, fp, ctx->stream);
+        else if (op.stage <= kStageKinematic) ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, ctx->stream);
+        else ctx->launchers->final_pose(ctx->B, fp, ctx->stream);
+        CK(cudaEventRecord(ctx->profile_events[2 * i + 1], ctx->stream));
+        launched[i] = 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    for (size_t i = 0; i < ctx->program.size(); ++i) {
+        if (!launched[i]) continue;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->profile_events[2 * i], ctx->profile_events[2 * i + 1]));
+        const StageOp& op = ctx->program[i];
+        out->ms[op.stage] += ms;
+        out->launches[op.stage] += 1;
+        int64_t bytes = 0;
+        if (op.stage <= kStageIncremental) {
+            // live constraints per work item are not tracked per bundle; use 32 lanes per bundle minus padding via the per-type-batch totals
+            for (int w = 0; w < op.work_count; ++w) {
+                const WorkItem& wi = ctx->work[op.work_begin + w];
+                const TypeInfo* t = get_type_info(ctx->tbs[wi.type_batch].type_id);
+                const int per = op.stage == kStageSolve ? t->solve_bytes : op.stage == kStageIncremental ? t->incremental_bytes : t->warm_start_bytes;
+                bytes += (int64_t)per * ctx->bundle_live[(size_t)op.work_begin + w];
+            }
+        } else if (op.stage == kStageFinalPose) {
+            bytes = (int64_t)ctx->body_count * 108;
+        } else {
+            bytes = (int64_t)op.work_count * 108;
+        }
+        out->algorithmic_bytes[op.stage] += bytes;
+    }
     return BEPUCUDA_OK;
 }
 

@@ -77,6 +77,15 @@ class TypeBatchView(C.Structure):
     ]
 
 
+class StageProfile(C.Structure):
+    _fields_ = [("ms", C.c_float * 8), ("launches", C.c_int64 * 8), ("algorithmic_bytes", C.c_int64 * 8)]
+
+    STAGE_NAMES = ["warm_start_first", "warm_start", "solve", "incremental_update", "kinematic_first", "kinematic", "final_pose", "unused"]
+
+    def as_dict(self):
+        return {n: {"ms": self.ms[i], "launches": self.launches[i], "algorithmic_bytes": self.algorithmic_bytes[i]} for i, n in enumerate(self.STAGE_NAMES) if self.launches[i]}
+
+
 EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM = 0, 1, 2
 
 # Every symbol include/bepucuda.h declares (checked by the CPU test-suite).
@@ -85,6 +94,7 @@ C_ABI_SYMBOLS = [
     "bepucuda_set_solve_description", "bepucuda_set_integrator", "bepucuda_upload_bodies", "bepucuda_begin_constraints", "bepucuda_upload_type_batch",
     "bepucuda_set_constrained_kinematics", "bepucuda_end_constraints", "bepucuda_update_type_batch", "bepucuda_solve", "bepucuda_synchronize",
     "bepucuda_download_bodies", "bepucuda_download_impulses", "bepucuda_download_prestep", "bepucuda_get_timings", "bepucuda_set_boundary_bodies",
+    "bepucuda_event_record", "bepucuda_event_elapsed_ms", "bepucuda_profile_stages",
 ]
 
 
@@ -120,6 +130,9 @@ def load_libraries():
     cuda.bepucuda_download_bodies.argtypes = [vp, vp, i32]
     cuda.bepucuda_download_impulses.argtypes = [vp]
     cuda.bepucuda_download_prestep.argtypes = [vp, i32, i32, vp]
+    cuda.bepucuda_event_record.argtypes = [vp, i32]
+    cuda.bepucuda_event_elapsed_ms.argtypes = [vp, i32, i32, C.POINTER(f32)]
+    cuda.bepucuda_profile_stages.argtypes = [vp, f32, C.POINTER(StageProfile)]
     cuda.bepucuda_host_register.argtypes = [vp, vp, C.c_int64]
     cuda.bepucuda_host_unregister.argtypes = [vp, vp]
 
@@ -320,6 +333,24 @@ class CudaTimestepper:
 
     def download_prestep(self):
         self._check(self._host.bepuhost_cuda_download_prestep(self.sim._sim, self._ctx))
+
+    def event_record(self, slot):
+        self._check(self._cuda.bepucuda_event_record(self._ctx, slot))
+
+    def event_elapsed_ms(self, slot_begin, slot_end):
+        ms = C.c_float()
+        self._check(self._cuda.bepucuda_event_elapsed_ms(self._ctx, slot_begin, slot_end, C.byref(ms)))
+        return ms.value
+
+    def profile_stages(self, dt):
+        """One frame as plain stream launches with a CUDA event pair around every stage launch; returns per-stage-kind ms / launches / algorithmic bytes."""
+        p = StageProfile()
+        self._check(self._cuda.bepucuda_profile_stages(self._ctx, dt, C.byref(p)))
+        return p
+
+    def solve_device_only(self, dt):
+        """bepucuda_solve without downloads (state stays resident in HBM)."""
+        self._check(self._cuda.bepucuda_solve(self._ctx, dt))
 
     def timings(self):
         t = Timings()

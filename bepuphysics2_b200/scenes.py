@@ -305,6 +305,194 @@ def fallback_stress(body_count=50_000, hubs=50, seed=5, neighbour_manifolds_per_
     return {"bodies": bodies, "constraints": constraints, "description": "fallback stress: %d bodies, %d hubs, %d manifolds" % (n, hubs, total)}
 
 
+# ---- quaternion helpers in the reference's conventions (BepuUtilities/QuaternionEx.cs) ----
+def qcat(a, b):
+    """QuaternionEx.Concatenate(a, b): the rotation a followed by the rotation b. Arrays [..., 4] as xyzw."""
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    return np.stack([aw * bx + ax * bw + az * by - ay * bz, aw * by + ay * bw + ax * bz - az * bx, aw * bz + az * bw + ay * bx - ax * by,
+                     aw * bw - ax * bx - ay * by - az * bz], axis=-1).astype(np.float32)
+
+
+def qconj(q):
+    return (q * np.array([-1, -1, -1, 1], dtype=np.float32)).astype(np.float32)
+
+
+def qrot(v, q):
+    """QuaternionEx.Transform(v, q)."""
+    u = q[..., :3]
+    w = q[..., 3:4]
+    t = 2.0 * np.cross(u, v)
+    return (v + w * t + np.cross(u, t)).astype(np.float32)
+
+
+def basis_quaternion(z, x):
+    """RagdollDemo.CreateBasis(z, x) (Demos/Demos/RagdollDemo.cs:L183-192): quaternion whose local Z maps to z and local X towards x."""
+    z = np.asarray(z, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    bz = z / np.linalg.norm(z)
+    by = np.cross(bz, x)
+    by /= np.linalg.norm(by)
+    bx = np.cross(by, bz)
+    m = np.stack([bx, by, bz], axis=1)  # columns = images of the unit axes
+    tr = m[0, 0] + m[1, 1] + m[2, 2]
+    if tr > 0:
+        s = math.sqrt(tr + 1.0) * 2
+        q = [(m[2, 1] - m[1, 2]) / s, (m[0, 2] - m[2, 0]) / s, (m[1, 0] - m[0, 1]) / s, 0.25 * s]
+    elif m[0, 0] > m[1, 1] and m[0, 0] > m[2, 2]:
+        s = math.sqrt(1.0 + m[0, 0] - m[1, 1] - m[2, 2]) * 2
+        q = [0.25 * s, (m[0, 1] + m[1, 0]) / s, (m[0, 2] + m[2, 0]) / s, (m[2, 1] - m[1, 2]) / s]
+    elif m[1, 1] > m[2, 2]:
+        s = math.sqrt(1.0 + m[1, 1] - m[0, 0] - m[2, 2]) * 2
+        q = [(m[0, 1] + m[1, 0]) / s, 0.25 * s, (m[1, 2] + m[2, 1]) / s, (m[0, 2] - m[2, 0]) / s]
+    else:
+        s = math.sqrt(1.0 + m[2, 2] - m[0, 0] - m[1, 1]) * 2
+        q = [(m[0, 2] + m[2, 0]) / s, (m[1, 2] + m[2, 1]) / s, 0.25 * s, (m[1, 0] - m[0, 1]) / s]
+    return np.asarray(q, dtype=np.float32)
+
+
+# Ragdoll skeleton (Demos/Demos/RagdollDemo.cs:L428-545 AddRagdoll): 16 bodies, 15 connections, 58 joints =
+# 11 BallSocket + 15 SwingLimit + 9 TwistLimit + 4 TwistServo + 2 SwivelHinge + 2 Hinge + 15 AngularMotor.
+# (name, local position, half extents used for the inertia box, mass)
+_RAGDOLL_BODIES = [
+    ("hips", (0, 1.1, 0), (0.2, 0.1, 0.12), 8), ("abdomen", (0, 1.3, 0), (0.18, 0.1, 0.11), 7), ("chest", (0, 1.6, 0), (0.22, 0.18, 0.13), 10), ("head", (0, 1.95, 0), (0.1, 0.12, 0.1), 5),
+    ("upper_arm_r", (0.45, 1.7, 0), (0.225, 0.1, 0.1), 5), ("lower_arm_r", (0.9, 1.7, 0), (0.225, 0.09, 0.09), 5), ("hand_r", (1.225, 1.7, 0), (0.1, 0.05, 0.1), 2),
+    ("upper_arm_l", (-0.45, 1.7, 0), (0.225, 0.1, 0.1), 5), ("lower_arm_l", (-0.9, 1.7, 0), (0.225, 0.09, 0.09), 5), ("hand_l", (-1.225, 1.7, 0), (0.1, 0.05, 0.1), 2),
+    ("upper_leg_r", (0.15, 0.8, 0), (0.12, 0.25, 0.12), 5), ("lower_leg_r", (0.15, 0.3, 0), (0.11, 0.25, 0.11), 5), ("foot_r", (0.15, -0.025, 0.05), (0.1, 0.075, 0.15), 2),
+    ("upper_leg_l", (-0.15, 0.8, 0), (0.12, 0.25, 0.12), 5), ("lower_leg_l", (-0.15, 0.3, 0), (0.11, 0.25, 0.11), 5), ("foot_l", (-0.15, -0.025, 0.05), (0.1, 0.075, 0.15), 2),
+]
+# (body a, body b, anchor, position joint, twist joint, swing axis, max swing angle, twist axis)
+_RAGDOLL_CONNECTIONS = [
+    (0, 1, (0, 1.2, 0), "ball", "limit", (0, 1, 0), 0.25 * math.pi, (0, 1, 0)), (1, 2, (0, 1.4, 0), "ball", "limit", (0, 1, 0), 0.25 * math.pi, (0, 1, 0)),
+    (2, 3, (0, 1.8, 0), "ball", "limit", (0, 1, 0), 0.35 * math.pi, (0, 1, 0)),
+    (2, 4, (0.225, 1.7, 0), "ball", "limit", (1, 0, 0), 0.56 * math.pi, (1, 0, 0)), (4, 5, (0.675, 1.7, 0), "swivel", "limit", (1, 0, 0), 0.5 * math.pi, (1, 0, 0)),
+    (5, 6, (1.125, 1.7, 0), "ball", "servo", (1, 0, 0), 0.5 * math.pi, (1, 0, 0)),
+    (2, 7, (-0.225, 1.7, 0), "ball", "limit", (-1, 0, 0), 0.56 * math.pi, (-1, 0, 0)), (7, 8, (-0.675, 1.7, 0), "swivel", "limit", (-1, 0, 0), 0.5 * math.pi, (-1, 0, 0)),
+    (8, 9, (-1.125, 1.7, 0), "ball", "servo", (-1, 0, 0), 0.5 * math.pi, (-1, 0, 0)),
+    (0, 10, (0.15, 1.05, 0), "ball", "limit", (0, -1, 0), 0.45 * math.pi, (0, -1, 0)), (10, 11, (0.15, 0.55, 0), "hinge", None, (0, -1, 0), 0.5 * math.pi, (0, -1, 0)),
+    (11, 12, (0.15, 0.05, 0), "ball", "servo", (0, -1, 0), 0.3 * math.pi, (0, -1, 0)),
+    (0, 13, (-0.15, 1.05, 0), "ball", "limit", (0, -1, 0), 0.45 * math.pi, (0, -1, 0)), (13, 14, (-0.15, 0.55, 0), "hinge", None, (0, -1, 0), 0.5 * math.pi, (0, -1, 0)),
+    (14, 15, (-0.15, 0.05, 0), "ball", "servo", (0, -1, 0), 0.3 * math.pi, (0, -1, 0)),
+]
+
+
+def ragdolls(count=10_000, seed=5, contacts_per_body=2.0, motor="motor", spacing=2.5):
+    """Config 3: `count` ragdolls with the RagdollDemo.AddRagdoll joint topology at random poses in a kinematic rotating tube, joint springs
+    SpringSettings(15 Hz, 1) (RagdollDemo.cs:L443), AngularMotor settings MotorSettings(float.MaxValue, 0.01) (L200) or, with motor="servo", the
+    AngularServo variant the demo comments mention (L199). Plus `contacts_per_body` contact manifolds per body: against the kinematic tube
+    (two-body contacts with a kinematic B, tube material spring 10 Hz / friction 2, RagdollTubeDemo.cs:L29) and against other ragdolls."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nb = len(_RAGDOLL_BODIES)
+    n = count * nb + 1  # + the kinematic tube (body 0)
+    local_pos = np.array([b[1] for b in _RAGDOLL_BODIES], dtype=np.float32)
+    half = np.array([b[2] for b in _RAGDOLL_BODIES], dtype=np.float32)
+    mass = np.array([b[3] for b in _RAGDOLL_BODIES], dtype=np.float32)
+    # box inertia about the body's own axes; bodies are axis aligned in the ragdoll frame, so the body orientation is the ragdoll's
+    full = 2 * half
+    ixx = mass / 12 * (full[:, 1] ** 2 + full[:, 2] ** 2)
+    iyy = mass / 12 * (full[:, 0] ** 2 + full[:, 2] ** 2)
+    izz = mass / 12 * (full[:, 0] ** 2 + full[:, 1] ** 2)
+    inv_inertia_local = np.zeros((nb, 6), dtype=np.float32)
+    inv_inertia_local[:, 0], inv_inertia_local[:, 2], inv_inertia_local[:, 5] = 1 / ixx, 1 / iyy, 1 / izz
+    side = int(math.ceil(count ** (1.0 / 3.0)))
+    rid = np.arange(count)
+    base = np.stack([rid % side, (rid // side) % side, rid // (side * side)], axis=1).astype(np.float32) * np.float32(spacing)
+    base += rng.uniform(-0.2, 0.2, size=(count, 3)).astype(np.float32)
+    rq = _random_unit_quaternions(rng, count)
+    pos = base[:, None, :] + qrot(np.broadcast_to(local_pos, (count, nb, 3)), rq[:, None, :])
+    orient = np.broadcast_to(rq[:, None, :], (count, nb, 4))
+    lin = rng.uniform(-0.5, 0.5, size=(count, 1, 3)).astype(np.float32) + rng.uniform(-0.2, 0.2, size=(count, nb, 3)).astype(np.float32)
+    ang = rng.uniform(-0.5, 0.5, size=(count, nb, 3)).astype(np.float32)
+    bodies = np.zeros((n, 32), dtype=np.float32)
+    bodies[0] = make_bodies(np.array([[0, 0, 0]], dtype=np.float32), angular=np.array([[0, 0, 0.25]], dtype=np.float32))[0]  # kinematic tube, rotating
+    bodies[1:] = make_bodies(pos.reshape(-1, 3), orientation=orient.reshape(-1, 4), linear=lin.reshape(-1, 3), angular=ang.reshape(-1, 3),
+                             inverse_mass=np.broadcast_to(1 / mass, (count, nb)).reshape(-1), inverse_inertia=np.broadcast_to(inv_inertia_local, (count, nb, 6)).reshape(-1, 6))
+    handle = 1 + rid[:, None] * nb + np.arange(nb)[None, :]  # [count, nb]
+    joint_spring = spring(15, 1)
+    fmax = np.float32(np.finfo(np.float32).max)
+    per_type = {22: [], 25: [], 26: [], 27: [], 29: [], 30: [], 46: [], 47: []}
+
+    def add(type_id, a, b, row):
+        row = np.asarray(row, dtype=np.float32)
+        per_type[type_id].append((handle[:, a], handle[:, b], np.broadcast_to(row, (count, row.shape[0]))))
+
+    ident = np.array([0, 0, 0, 1], dtype=np.float32)
+    for a, b, anchor, pos_joint, twist, swing_axis, swing_angle, twist_axis in _RAGDOLL_CONNECTIONS:
+        anchor = np.asarray(anchor, dtype=np.float32)
+        off_a, off_b = anchor - local_pos[a], anchor - local_pos[b]  # bodies share the ragdoll frame, so local offsets are frame offsets
+        if pos_joint == "ball":
+            add(22, a, b, np.r_[off_a, off_b, joint_spring])
+        elif pos_joint == "swivel":
+            add(46, a, b, np.r_[off_a, np.asarray(twist_axis, np.float32), off_b, [0, 1, 0], joint_spring])
+        else:
+            add(47, a, b, np.r_[off_a, [1, 0, 0], off_b, [1, 0, 0], joint_spring])
+        add(25, a, b, np.r_[np.asarray(swing_axis, np.float32), np.asarray(swing_axis, np.float32), [math.cos(swing_angle)], joint_spring])
+        tz = np.asarray(twist_axis, dtype=np.float32)
+        tx = np.array([0, 0, -1], dtype=np.float32)
+        basis = basis_quaternion(tz, tx)
+        if twist == "limit":
+            add(27, a, b, np.r_[basis, basis, [-0.55 * math.pi, 0.55 * math.pi], joint_spring])
+        elif twist == "servo":
+            add(26, a, b, np.r_[basis, basis, [0.0], joint_spring, [fmax, 0.0, fmax]])
+        if motor == "servo":
+            add(29, a, b, np.r_[ident, joint_spring, [fmax, 0.0, fmax]])
+        else:
+            add(30, a, b, np.r_[[0, 0, 0], [fmax, 100.0]])
+    # Interleave like AddRagdoll does (all joints of ragdoll 0, then ragdoll 1, ...) is what the reference's batching would see; adding type by type
+    # is equally valid input and keeps generation vectorised. Constraints of one type are ordered by ragdoll, then connection.
+    constraints = []
+    for type_id, items in per_type.items():
+        if not items:
+            continue
+        ha = np.stack([i[0] for i in items], axis=1).reshape(-1)
+        hb = np.stack([i[1] for i in items], axis=1).reshape(-1)
+        pre = np.stack([i[2] for i in items], axis=1).reshape(ha.shape[0], -1)
+        constraints.append((type_id, np.stack([ha, hb], axis=1).astype(np.int32), np.ascontiguousarray(pre, dtype=np.float32)))
+    # contacts
+    body_pos = bodies[1:, 4:7]
+    total_dyn = count * nb
+    m = int(round(total_dyn * contacts_per_body))
+    m_tube = m // 2
+    m_pair = m - m_tube
+    tube_spring = spring(10, 1)
+
+    def geometry(k, pa, normal):
+        counts = rng.choice(np.array([1, 2, 3, 4]), size=k, p=[0.3, 0.3, 0.1, 0.3])
+        t1, t2 = _tangent_frame(normal)
+        ang_ = rng.uniform(0, 2 * math.pi, size=(k, 1)).astype(np.float32) + np.arange(4, dtype=np.float32)[None, :] * np.float32(math.pi / 2)
+        rad = rng.uniform(0.02, 0.08, size=(k, 4)).astype(np.float32)
+        offs = (-normal * np.float32(0.1))[:, None, :] + (np.cos(ang_) * rad)[:, :, None] * t1[:, None, :] + (np.sin(ang_) * rad)[:, :, None] * t2[:, None, :]
+        return counts, offs.astype(np.float32), rng.uniform(-0.01, 0.03, size=(k, 4)).astype(np.float32)
+
+    if m_tube > 0:
+        ta = rng.integers(0, total_dyn, size=m_tube)
+        normal = rng.standard_normal((m_tube, 3)).astype(np.float32)
+        normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+        counts, offs, depths = geometry(m_tube, body_pos[ta], normal)
+        offset_b = bodies[0, 4:7][None, :] - body_pos[ta]
+        for N in (1, 2, 3, 4):
+            sel = counts == N
+            if sel.any():
+                pre = convex_prestep(offs[sel][:, :N], depths[sel][:, :N], normal[sel], offset_b[sel], friction=2.0, spring_settings=tube_spring, max_recovery=fmax)
+                constraints.append((CONVEX_TWO_BODY[N], np.stack([ta[sel] + 1, np.zeros(int(sel.sum()), dtype=np.int64)], axis=1).astype(np.int32), pre))
+    if m_pair > 0 and count > 1:
+        pa_ = rng.integers(0, total_dyn, size=m_pair)
+        shift = rng.integers(nb, min(total_dyn - 1, 4 * nb) + 1, size=m_pair)  # a body of a nearby but different ragdoll
+        pb_ = (pa_ + shift) % total_dyn
+        d = body_pos[pa_] - body_pos[pb_]
+        normal = (d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-3)).astype(np.float32)
+        counts, offs, depths = geometry(m_pair, body_pos[pa_], normal)
+        offset_b = (-normal * np.float32(0.2)).astype(np.float32)
+        for N in (1, 2, 3, 4):
+            sel = counts == N
+            if sel.any():
+                pre = convex_prestep(offs[sel][:, :N], depths[sel][:, :N], normal[sel], offset_b[sel])
+                constraints.append((CONVEX_TWO_BODY[N], np.stack([pa_[sel] + 1, pb_[sel] + 1], axis=1).astype(np.int32), pre))
+    total = sum(c[1].shape[0] for c in constraints)
+    return {"bodies": bodies, "constraints": constraints,
+            "description": "%d ragdolls (%d bodies, %d joints) + kinematic tube, %d constraints total" % (count, total_dyn, 58 * count, total)}
+
+
 def build(scene, simulation):
     """Adds a scene to a host Simulation (Bodies.Add, then Solver.Add per constraint in list order)."""
     simulation.add_bodies(scene["bodies"])

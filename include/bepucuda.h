@@ -158,6 +158,20 @@ int32_t bepucuda_download_prestep(bepucuda_ctx* ctx, int32_t batch_index, int32_
 
 int32_t bepucuda_get_timings(bepucuda_ctx* ctx, bepucuda_timings* out);
 
+/* Replaces SimulationProfiler.Start/End (SimulationProfiler.cs:L25-60): CUDA events on the context stream, 16 slots. */
+int32_t bepucuda_event_record(bepucuda_ctx* ctx, int32_t slot);
+int32_t bepucuda_event_elapsed_ms(bepucuda_ctx* ctx, int32_t slot_begin, int32_t slot_end, float* ms);
+
+/* Per-stage-kind device time of ONE frame, measured with a CUDA event pair around every stage launch (plain stream launches, no graph).
+ * Index by stage kind: 0 WarmStart(first substep), 1 WarmStart, 2 Solve, 3 IncrementallyUpdateForSubstep, 4/5 kinematic prepasses, 6 final pose pass.
+ * algorithmic_bytes follows SURVEY.md §8d. Advances the simulation exactly like bepucuda_solve(ctx, dt). */
+typedef struct bepucuda_stage_profile {
+    float ms[8];
+    int64_t launches[8];
+    int64_t algorithmic_bytes[8];
+} bepucuda_stage_profile;
+int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_profile* out);
+
 /* Multi-GPU (no reference counterpart). One context per rank/GPU, one process per GPU. Marks which
  * local bodies are replicated on other ranks ("boundary bodies") and installs an exchange callback invoked on the
  * context stream after every (batch, stage) that wrote a boundary body. The callback runs host-side stream-ordered

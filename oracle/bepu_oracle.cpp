@@ -62,6 +62,7 @@ template <class F, class T> struct AdaptJ1 {
 };
 
 template <class F> struct Registry {
+    typedef F Lane;
     TypeOps<F> ops[64];
     template <class T> void contact2(int id) {
         ops[id].bodies = 2; ops[id].prestep_rows = T::L::kPrestepRows; ops[id].impulse_rows = T::L::kImpulseRows;

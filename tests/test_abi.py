@@ -1,0 +1,62 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol include/bepucuda.h declares, its type
+registry agrees with the oracle's, and there is no CPU fallback."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import bepuphysics2_b200 as bp
+from bepuphysics2_b200 import native
+from oracle import binding as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(libs):
+    cuda, _ = bp.load_libraries()
+    header = open(os.path.join(ROOT, "include", "bepucuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(bepucuda_[a-z_0-9]+)\s*\(", header)) - {"bepucuda_exchange_fn"})
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(cuda, name), "libbepucuda.so does not export %s" % name
+    assert sorted(native.C_ABI_SYMBOLS) == declared
+
+
+def test_type_registry_matches_oracle_and_reference_sizes(libs):
+    # (bodies, prestep floats, impulse floats) from the reference's struct definitions
+    expected = {0: (1, 11, 4), 1: (1, 15, 5), 2: (1, 19, 6), 3: (1, 23, 7), 4: (2, 14, 4), 5: (2, 18, 5), 6: (2, 22, 6), 7: (2, 26, 7),
+                8: (1, 18, 6), 9: (1, 25, 9), 10: (1, 32, 12), 15: (2, 21, 6), 16: (2, 28, 9), 17: (2, 35, 12),
+                22: (2, 8, 3), 25: (2, 9, 1), 26: (2, 14, 1), 27: (2, 12, 1), 29: (2, 9, 3), 30: (2, 5, 3), 46: (2, 14, 4), 47: (2, 14, 5)}
+    for type_id in range(64):
+        ours, theirs = bp.type_info(type_id), ob.type_info(type_id)
+        assert ours == theirs, "type %d: device registry %s vs oracle %s" % (type_id, ours, theirs)
+        if type_id in expected:
+            assert ours == expected[type_id]
+
+
+def test_unsupported_type_is_reported(libs):
+    cuda, _ = bp.load_libraries()
+    assert cuda.bepucuda_type_info(63, None, None, None) == -4  # BEPUCUDA_ERR_UNSUPPORTED_TYPE
+
+
+def test_no_cpu_fallback_without_a_device(libs):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sim = bp.Simulation()
+    with pytest.raises(bp.BepuCudaError) as e:
+        bp.CudaTimestepper(sim)
+    assert e.value.code == -2  # BEPUCUDA_ERR_NO_DEVICE
+
+
+def test_product_sources_never_reference_the_oracle():
+    pkg = os.path.join(ROOT, "bepuphysics2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inc")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text.lower(), "%s mentions the oracle" % os.path.join(dirpath, f)

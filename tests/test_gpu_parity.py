@@ -85,3 +85,18 @@ def test_momentum_conserving_angular_modes(libs, angular_mode):
     integ = util.bp.IntegratorDesc.default()
     integ.angular_integration_mode = angular_mode
     _parity(scenes.shape_pile(500, seed=9), substeps=3, velocity_iterations=1, integrator=integ)
+
+
+def test_ragdolls_all_joint_types_bit_exact(libs):
+    """BASELINE config 3 topology: BallSocket, SwingLimit, TwistLimit, TwistServo, SwivelHinge, Hinge, AngularMotor + contacts vs a kinematic tube."""
+    got = _parity(scenes.ragdolls(60, seed=5), substeps=1, velocity_iterations=4, frames=3)
+    assert got["timings"]["constraint_count"] > 60 * 58
+
+
+def test_ragdolls_substepped_servo_variant_bit_exact(libs):
+    """AngularServo variant (RagdollDemo.cs:L199) with 8 substeps x 2 iterations."""
+    _parity(scenes.ragdolls(40, seed=6, motor="servo"), substeps=8, velocity_iterations=2, frames=2)
+
+
+def test_ragdolls_persistent_fast_within_tolerance(libs):
+    _parity(scenes.ragdolls(60, seed=5), exact=False, mode=EXEC_PERSISTENT, rtol=2e-3, atol=5e-4, substeps=1, velocity_iterations=4)

@@ -1,0 +1,126 @@
+"""CPU tests that pin the oracle itself. The reference ships no golden numeric vectors for the solver path (parity unpinned), so the
+oracle is anchored on analytic known answers and internal consistency: scalar vs 8-wide evaluation, thread-count invariance, bundle-width invariance,
+momentum conservation, steady-state stack impulses, and joint error decay."""
+import numpy as np
+import pytest
+
+import bepuphysics2_b200 as bp
+from bepuphysics2_b200 import scenes
+from tests import util
+
+DT = 1.0 / 60.0
+
+
+def test_stacked_boxes_carry_the_weight_above_them(libs):
+    """Steady state: the penetration impulses of the manifold under k boxes sum to (k) * m * g * dt (SURVEY.md §8c known answer)."""
+    sim = util.make_sim(scenes.box_stacks(2, 8), substeps=1, velocity_iterations=8)
+    for _ in range(200):
+        util.ob.solve(sim, DT)
+    g_dt = 10.0 * DT
+    for tb in sim.type_batches():
+        W = sim.bundle_width
+        for c in range(tb.constraint_count):
+            a = int(tb.body_references[c // W, 0, c % W])
+            level = (a - 1) % 8  # boxes are numbered bottom-up within a column
+            carried = 8 - level
+            pen = tb.accumulated_impulses[c // W, 2:6, c % W].sum()
+            assert pen == pytest.approx(carried * g_dt, rel=2e-2)
+
+
+def test_scalar_and_simd_evaluation_are_bit_identical(libs):
+    scene = scenes.shape_pile(1500, seed=4, nonconvex_fraction=0.3)
+    a = util.run_oracle(util.make_sim(scene, substeps=4, velocity_iterations=2), DT, frames=2, simd=False)
+    b = util.run_oracle(util.make_sim(scene, substeps=4, velocity_iterations=2), DT, frames=2, simd=True)
+    util.compare(a, b, exact=True)
+
+
+def test_ragdolls_scalar_and_simd_are_bit_identical(libs):
+    scene = scenes.ragdolls(30, seed=4)
+    a = util.run_oracle(util.make_sim(scene, substeps=2, velocity_iterations=3), DT, frames=2, simd=False)
+    b = util.run_oracle(util.make_sim(scene, substeps=2, velocity_iterations=3), DT, frames=2, simd=True)
+    util.compare(a, b, exact=True)
+
+
+def test_thread_count_does_not_change_results(libs):
+    scene = scenes.shape_pile(3000, seed=8)
+    a = util.run_oracle(util.make_sim(scene, substeps=3, velocity_iterations=2), DT, threads=1, simd=True)
+    b = util.run_oracle(util.make_sim(scene, substeps=3, velocity_iterations=2), DT, threads=4, simd=True)
+    util.compare(a, b, exact=True)
+
+
+def test_bundle_width_does_not_change_results(libs):
+    """Synchronized batches commute, so the host's Vector<float>.Count must not matter (nonconserving angular mode)."""
+    scene = scenes.shape_pile(800, seed=3)
+    snaps = [util.run_oracle(util.make_sim(scene, bundle_width=w, substeps=2, velocity_iterations=2), DT) for w in (4, 8, 16)]
+    for s in snaps[1:]:
+        assert np.array_equal(snaps[0]["bodies"][:, util.MEANINGFUL], s["bodies"][:, util.MEANINGFUL])
+
+
+def test_two_body_contacts_conserve_linear_momentum(libs):
+    """With gravity and damping off, two-body constraints exchange momentum only: sum(m v) is conserved to rounding."""
+    scene = scenes.shape_pile(600, seed=6, one_body_fraction=0.0)
+    integ = bp.IntegratorDesc.default()
+    integ.gravity[1] = 0.0
+    integ.linear_damping = 0.0
+    integ.angular_damping = 0.0
+    sim = util.make_sim(scene, substeps=2, velocity_iterations=3, integrator=integ)
+    m = 1.0 / sim.bodies[:, 22]
+    before = (sim.bodies[:, 8:11] * m[:, None]).sum(axis=0)
+    util.ob.solve(sim, DT)
+    after = (sim.bodies[:, 8:11] * m[:, None]).sum(axis=0)
+    np.testing.assert_allclose(after, before, atol=2e-3)
+
+
+def test_zero_impulse_warm_start_is_identity_and_unconstrained_bodies_fall(libs):
+    """A body with no constraints integrates v = (v + g dt) * damping^dt, p += v dt (IntegrateAfterSubstepping, unconstrained path)."""
+    scene = {"bodies": scenes.make_bodies(np.array([[0, 10, 0]], dtype=np.float32), inverse_mass=np.array([1], dtype=np.float32), inverse_inertia=np.array([[1, 0, 1, 0, 0, 1]], dtype=np.float32)),
+             "constraints": [], "description": "one free body"}
+    sim = util.make_sim(scene, substeps=4, velocity_iterations=1)
+    util.ob.solve(sim, DT)
+    damp = np.float32(0.97) ** np.float32(DT)
+    v = np.float32(-10.0 * DT) * damp
+    assert sim.bodies[0, 9] == pytest.approx(v, rel=1e-6)
+    assert sim.bodies[0, 5] == pytest.approx(10.0 + v * DT, rel=1e-6)
+
+
+def test_ball_socket_pulls_anchors_together(libs):
+    """Two bodies joined by a BallSocket with separated anchors: the anchor error shrinks every frame (error * ERP bias, BallSocket.cs:L66-86)."""
+    bodies = scenes.make_bodies(np.array([[0, 0, 0], [1.5, 0, 0]], dtype=np.float32), inverse_mass=np.array([1, 1], dtype=np.float32),
+                                inverse_inertia=np.array([[1, 0, 1, 0, 0, 1]] * 2, dtype=np.float32))
+    pre = np.r_[[0.5, 0, 0], [-0.5, 0, 0], scenes.spring(30, 1)].astype(np.float32)[None, :]
+    scene = {"bodies": bodies, "constraints": [(22, np.array([[0, 1]], dtype=np.int32), pre)], "description": "ball socket"}
+    integ = bp.IntegratorDesc.default()
+    integ.gravity[1] = 0.0
+    sim = util.make_sim(scene, substeps=1, velocity_iterations=4, integrator=integ)
+    errors = []
+    for _ in range(30):
+        util.ob.solve(sim, DT)
+        b = sim.bodies
+        errors.append(abs((b[1, 4] - 0.5) - (b[0, 4] + 0.5)))
+    assert errors[-1] < 0.02 * 0.5
+    assert errors[10] < errors[0]
+
+
+def test_sin_cos_approximations_through_orientation_integration(libs):
+    """A free body spinning at w about z for one second returns a rotation of |w| radians: pins MathHelper.Sin/Cos restatements (error < 1e-5)."""
+    w = 2.0
+    scene = {"bodies": scenes.make_bodies(np.zeros((1, 3), dtype=np.float32), angular=np.array([[0, 0, w]], dtype=np.float32), inverse_mass=np.array([1], dtype=np.float32),
+                                          inverse_inertia=np.array([[1, 0, 1, 0, 0, 1]], dtype=np.float32)), "constraints": [], "description": "spinner"}
+    integ = bp.IntegratorDesc.default()
+    integ.gravity[1] = 0.0
+    integ.angular_damping = 0.0
+    sim = util.make_sim(scene, integrator=integ)
+    for _ in range(60):
+        util.ob.solve(sim, DT)
+    q = sim.bodies[0, 0:4]
+    assert q[2] == pytest.approx(np.sin(w / 2), abs=2e-5)
+    assert q[3] == pytest.approx(np.cos(w / 2), abs=2e-5)
+    assert np.linalg.norm(q) == pytest.approx(1.0, abs=1e-6)
+
+
+def test_fallback_batch_runs_sequentially(libs):
+    """With a tiny fallback threshold most constraints land in the fallback batch; parallel oracle threads must not change the result."""
+    scene = scenes.fallback_stress(300, hubs=2, seed=1)
+    a = util.run_oracle(util.make_sim(scene, fallback_batch_threshold=4, substeps=2, velocity_iterations=2), DT, threads=1)
+    b = util.run_oracle(util.make_sim(scene, fallback_batch_threshold=4, substeps=2, velocity_iterations=2), DT, threads=4)
+    util.compare(a, b, exact=True)

@@ -119,12 +119,26 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def usable_cpu_count():
+    """Threads we can really run: the scheduler affinity mask capped by the cgroup CPU quota (a 128-CPU box may grant a container far fewer)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) // int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference_run(args, steps, warmup, threads):
     """The oracle (CPU restatement of the reference solver, AVX2 8-wide lanes, OpenMP over bundles within each batch stage) on the same workload."""
     from oracle import binding as ob
 
     sim, desc = build_sim(args, seed=5)
-    threads = threads or os.cpu_count() or 1
+    threads = threads or usable_cpu_count()
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     for _ in range(warmup):
         ob.solve(sim, DT, threads=threads, simd=True)
     t0 = time.perf_counter()

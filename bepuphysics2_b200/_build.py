@@ -41,7 +41,7 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "bepucuda.h"))
     units = [
-        ("solver_fast.o", "bepu_solver_kernels.cu", ["-DBEPU_NS=bepu_fast"]),
+        ("solver_fast.o", "bepu_solver_kernels.cu", ["-DBEPU_NS=bepu_fast", "-prec-div=false", "-prec-sqrt=false"]),
         ("solver_strict.o", "bepu_solver_kernels.cu", ["-DBEPU_NS=bepu_strict", "-fmad=false"]),
         ("layout.o", "bepu_layout_kernels.cu", []),
         ("api.o", "bepucuda_api.cu", []),

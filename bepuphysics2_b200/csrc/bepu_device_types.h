@@ -79,6 +79,16 @@ struct WorkItem {
     int32_t bundle;
 };
 
+// What a solver warp needs to process one bundle, in ONE 32-byte record (two LDG.128): no dependent work-item -> type-batch -> pointer chain.
+// Pointers address the bundle's row 0, lane 0.
+struct alignas(32) WorkRecord {
+    int32_t* refs;
+    float* prestep;
+    float* impulses;
+    int32_t type_id;
+    int32_t live_lanes;
+};
+
 // Persistent-kernel stage program entry.
 struct StageOp {
     int32_t stage;

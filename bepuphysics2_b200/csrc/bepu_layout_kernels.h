@@ -28,13 +28,14 @@ void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
 struct SolverLaunchers {
     // Launches one constraint stage (kStageWarmStartFirst / kStageWarmStart / kStageSolve / kStageIncremental) over `work_count` bundles.
-    void (*constraint_stage)(int stage, const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
+    // pdl: launch with programmatic stream serialization (the kernel overlaps its prologue with the previous stage's tail).
+    void (*constraint_stage)(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
     void (*kinematic_stage)(int stage, const int32_t* kinematics, int count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
     void (*final_pose)(const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
     // Persistent cooperative kernel: runs a whole stage program with a grid barrier between ops. Returns a cudaError_t.
-    int (*persistent)(const StageOp* program, int op_count, const DeviceTypeBatch* tbs, const WorkItem* work, const int32_t* kinematics, const BodyBuffers& B,
-                      const FrameParams* fp, unsigned int* barrier_state, cudaStream_t s);
-    int (*persistent_grid_size)(void);
+    // barrier_counter must be zero at launch. blocks_per_sm <= 0 selects the default.
+    int (*persistent)(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
+                      unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
 };
 const SolverLaunchers* get_launchers_bepu_fast();
 const SolverLaunchers* get_launchers_bepu_strict();

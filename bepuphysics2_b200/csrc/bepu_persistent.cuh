@@ -1,7 +1,12 @@
 // Persistent cooperative solver kernel: the whole (substep, stage, batch) sequence of Solver.Solve
 // (Solver_Solve.cs:L1419-1479) + the final pose pass in ONE launch, with a grid-wide barrier where the reference's
-// multithreaded path has a sync point (Solver_Solve.cs:L395-401). One CTA set stays resident on all 148 SMs; work items
-// of a stage are dealt round-robin across CTAs so a small batch still spreads over the whole chip.
+// multithreaded path has a sync point (Solver_Solve.cs:L395-401).
+//
+// Latency engineering (a stage of a 100k-body pile is ~650 warps: one thin wave, so a stage costs one warp's critical path):
+//   - work items are dealt round-robin across CTAs so a small batch still spreads over all 148 SMs;
+//   - each warp fetches its NEXT stage's 32-B work record and body references BEFORE arriving at the barrier (they are
+//     immutable during a solve), so after the barrier the first thing issued is the body gather from L2;
+//   - the barrier is a single monotonically increasing counter: one red.add per CTA, ld.acquire polling, no reset phase.
 #pragma once
 #include "bepu_solver_kernels.cuh"
 
@@ -9,31 +14,34 @@ namespace BEPU_NS {
 
 constexpr int kPersistentThreads = 256;
 
-// Sense-free generation barrier: state[0] = arrival count, state[1] = generation. Same fence pattern as cooperative
-// groups' grid.sync(): block barrier, one thread publishes with a gpu-scope fence + atomic, spins on the generation,
-// fences again, block barrier. Requires all CTAs co-resident (cooperative launch).
-BEPU_DI void grid_barrier(unsigned int* state) {
+BEPU_DI void grid_barrier(unsigned int* counter, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        volatile unsigned int* gen_ptr = state + 1;
-        const unsigned int gen = *gen_ptr;
-        __threadfence();
-        const unsigned int prev = atomicAdd(state, 1u);
-        if (prev == gridDim.x - 1) {
-            state[0] = 0;
-            __threadfence();
-            atomicAdd(state + 1, 1u);
-        } else {
-            while (*gen_ptr == gen) { __nanosleep(20); }
-        }
-        __threadfence();
+        __threadfence();  // make this CTA's scatters visible at gpu scope before signalling
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kPersistentThreads, 1)
-persistent_solve_kernel(const StageOp* __restrict__ program, int op_count, const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work,
-                        const int32_t* __restrict__ kinematics, BodyBuffers B, const FrameParams* __restrict__ fpp, unsigned int* barrier_state) {
+BEPU_DI bool is_constraint_stage(int stage) { return stage <= kStageIncremental; }
+
+template <int STAGE>
+BEPU_DI void run_constraint_op(const StageOp& op, const WorkRecord* __restrict__ records, bool prefetched, const WorkRecord& rec0, uint32_t enc0, uint32_t enc1, int first_item, int stride,
+                               int lane, const BodyBuffers& B, const FrameParams& fp) {
+    if (first_item < op.work_count) {
+        if (prefetched) run_bundle<STAGE>(rec0, lane, enc0, enc1, B, fp);
+        else run_bundle<STAGE>(load_record(records + op.work_begin + first_item), lane, B, fp);
+        for (int i = first_item + stride; i < op.work_count; i += stride) run_bundle<STAGE>(load_record(records + op.work_begin + i), lane, B, fp);
+    }
+}
+
+__global__ void __launch_bounds__(kPersistentThreads, 2)
+persistent_solve_kernel(const StageOp* __restrict__ program, int op_count, const WorkRecord* __restrict__ records, const int32_t* __restrict__ kinematics, BodyBuffers B,
+                        const FrameParams* __restrict__ fpp, unsigned int* barrier_counter) {
     const FrameParams fp = *fpp;
     constexpr int kWarpsPerBlock = kPersistentThreads / 32;
     const int lane = threadIdx.x & 31;
@@ -42,33 +50,21 @@ persistent_solve_kernel(const StageOp* __restrict__ program, int op_count, const
     const int first_warp_item = warp_in_block * gridDim.x + blockIdx.x;  // item i -> CTA (i % grid), warp (i / grid) % warpsPerBlock
     const int total_threads = gridDim.x * kPersistentThreads;
     const int first_thread_item = threadIdx.x * gridDim.x + blockIdx.x;
+    unsigned int barrier_target = 0;
+
+    StageOp op = program[0];
+    WorkRecord rec{};
+    uint32_t enc0 = 0, enc1 = 0;
+    bool prefetched = false;
     for (int op_index = 0; op_index < op_count; ++op_index) {
-        const StageOp op = program[op_index];
+        StageOp next{};
+        const bool has_next = op_index + 1 < op_count;
+        if (has_next) next = program[op_index + 1];
         switch (op.stage) {
-            case kStageWarmStartFirst:
-                for (int i = first_warp_item; i < op.work_count; i += total_warps) {
-                    const WorkItem w = work[op.work_begin + i];
-                    run_bundle<kStageWarmStartFirst>(tbs[w.type_batch], w.bundle, lane, B, fp);
-                }
-                break;
-            case kStageWarmStart:
-                for (int i = first_warp_item; i < op.work_count; i += total_warps) {
-                    const WorkItem w = work[op.work_begin + i];
-                    run_bundle<kStageWarmStart>(tbs[w.type_batch], w.bundle, lane, B, fp);
-                }
-                break;
-            case kStageSolve:
-                for (int i = first_warp_item; i < op.work_count; i += total_warps) {
-                    const WorkItem w = work[op.work_begin + i];
-                    run_bundle<kStageSolve>(tbs[w.type_batch], w.bundle, lane, B, fp);
-                }
-                break;
-            case kStageIncremental:
-                for (int i = first_warp_item; i < op.work_count; i += total_warps) {
-                    const WorkItem w = work[op.work_begin + i];
-                    run_bundle<kStageIncremental>(tbs[w.type_batch], w.bundle, lane, B, fp);
-                }
-                break;
+            case kStageWarmStartFirst: run_constraint_op<kStageWarmStartFirst>(op, records, prefetched, rec, enc0, enc1, first_warp_item, total_warps, lane, B, fp); break;
+            case kStageWarmStart: run_constraint_op<kStageWarmStart>(op, records, prefetched, rec, enc0, enc1, first_warp_item, total_warps, lane, B, fp); break;
+            case kStageSolve: run_constraint_op<kStageSolve>(op, records, prefetched, rec, enc0, enc1, first_warp_item, total_warps, lane, B, fp); break;
+            case kStageIncremental: run_constraint_op<kStageIncremental>(op, records, prefetched, rec, enc0, enc1, first_warp_item, total_warps, lane, B, fp); break;
             case kStageKinematicFirst:
                 for (int i = first_thread_item; i < op.work_count; i += total_threads) run_kinematic<kStageKinematicFirst>(i, kinematics, B, fp);
                 break;
@@ -80,25 +76,37 @@ persistent_solve_kernel(const StageOp* __restrict__ program, int op_count, const
                 break;
             default: break;
         }
-        if (op_index + 1 < op_count) grid_barrier(barrier_state);
+        if (!has_next) break;
+        // Prefetch the next stage's record + body references while the rest of the grid is still finishing this stage.
+        prefetched = false;
+        if (is_constraint_stage(next.stage) && first_warp_item < next.work_count) {
+            rec = load_record(records + next.work_begin + first_warp_item);
+            enc0 = (uint32_t)__ldg(rec.refs + lane);
+            enc1 = (uint32_t)__ldg(rec.refs + kLanes + lane);
+            prefetched = true;
+        }
+        barrier_target += gridDim.x;
+        grid_barrier(barrier_counter, barrier_target);
+        op = next;
     }
 }
 
-static int persistent_grid_size() {
-    int device = 0, sms = 0, per_sm = 0;
-    if (cudaGetDevice(&device) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_solve_kernel, kPersistentThreads, 0) != cudaSuccess) return 0;
-    return sms * (per_sm < 1 ? 1 : per_sm);
-}
-
-static int launch_persistent(const StageOp* program, int op_count, const DeviceTypeBatch* tbs, const WorkItem* work, const int32_t* kinematics, const BodyBuffers& B,
-                             const FrameParams* fp, unsigned int* barrier_state, cudaStream_t s) {
-    static int grid = 0;
-    if (grid == 0) grid = persistent_grid_size();
-    if (grid <= 0) return (int)cudaErrorLaunchFailure;
+static int launch_persistent(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
+                             unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s) {
+    static int sms = 0, max_per_sm = 0;
+    if (sms == 0) {
+        int device = 0;
+        cudaError_t e = cudaGetDevice(&device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, persistent_solve_kernel, kPersistentThreads, 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (max_per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+    int per_sm = blocks_per_sm <= 0 ? 1 : blocks_per_sm;
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
+    const int grid = sms * per_sm;
     BodyBuffers Bc = B;
-    void* args[] = {(void*)&program, (void*)&op_count, (void*)&tbs, (void*)&work, (void*)&kinematics, (void*)&Bc, (void*)&fp, (void*)&barrier_state};
+    void* args[] = {(void*)&program, (void*)&op_count, (void*)&records, (void*)&kinematics, (void*)&Bc, (void*)&fp, (void*)&barrier_counter};
     return (int)cudaLaunchCooperativeKernel((const void*)persistent_solve_kernel, dim3(grid), dim3(kPersistentThreads), args, 0, s);
 }
 

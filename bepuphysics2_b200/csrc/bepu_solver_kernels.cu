@@ -5,14 +5,28 @@
 
 namespace BEPU_NS {
 
-static void launch_constraint_stage(int stage, const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s) {
-    if (work_count <= 0) return;
+template <int STAGE>
+static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
     const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kStageBlockThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE>, records, work_count, B, fp);
+}
+static void launch_constraint_stage(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+    if (work_count <= 0) return;
     switch (stage) {
-        case kStageWarmStartFirst: constraint_stage_kernel<kStageWarmStartFirst><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
-        case kStageWarmStart: constraint_stage_kernel<kStageWarmStart><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
-        case kStageSolve: constraint_stage_kernel<kStageSolve><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
-        case kStageIncremental: constraint_stage_kernel<kStageIncremental><<<blocks, kStageBlockThreads, 0, s>>>(tbs, work, work_count, B, fp); break;
+        case kStageWarmStartFirst: launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, pdl, s); break;
+        case kStageWarmStart: launch_stage_t<kStageWarmStart>(records, work_count, B, fp, pdl, s); break;
+        case kStageSolve: launch_stage_t<kStageSolve>(records, work_count, B, fp, pdl, s); break;
+        case kStageIncremental: launch_stage_t<kStageIncremental>(records, work_count, B, fp, pdl, s); break;
         default: break;
     }
 }
@@ -27,7 +41,7 @@ static void launch_final_pose(const BodyBuffers& B, const FrameParams* fp, cudaS
     final_pose_kernel<<<(unsigned)((B.count + 255) / 256), 256, 0, s>>>(B, fp);
 }
 
-static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent, &persistent_grid_size};
+static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent};
 
 }  // namespace BEPU_NS
 

@@ -165,17 +165,16 @@ template <class T> BEPU_DI void call_incremental(float dt, const Velocity* v, fl
     }
 }
 
-// One constraint lane of one stage.
+// One constraint lane of one stage. refs/p/a address this lane in row 0 of the bundle; enc0/enc1 are the (possibly prefetched) first two body references.
 template <class T, int STAGE>
-BEPU_DI void run_lane(const DeviceTypeBatch& tb, int bundle, int lane, const BodyBuffers& B, const FrameParams& fp) {
+BEPU_DI void run_lane(const int32_t* refs, float* p, float* a, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
     constexpr int NB = T::kBodies;
-    const int32_t* refs = tb.refs + ((size_t)bundle * NB) * kLanes + lane;
     uint32_t enc[NB];
+    enc[0] = enc0;
+    if constexpr (NB > 1) enc[1] = enc1;
 #pragma unroll
-    for (int s = 0; s < NB; ++s) enc[s] = (uint32_t)__ldg(refs + s * kLanes);
+    for (int s = 2; s < NB; ++s) enc[s] = (uint32_t)__ldg(refs + s * kLanes);
     if ((int32_t)enc[0] == kRefEmpty) return;  // trailing lane of the last bundle, or a hole in a fallback bundle
-    float* p = tb.prestep + ((size_t)bundle * T::kPrestepRows) * kLanes + lane;
-    float* a = tb.impulses + ((size_t)bundle * T::kImpulseRows) * kLanes + lane;
     BodyState b[NB];
     Velocity v[NB];
     if constexpr (STAGE == kStageIncremental) {
@@ -204,6 +203,17 @@ BEPU_DI void run_lane(const DeviceTypeBatch& tb, int bundle, int lane, const Bod
     }
 }
 
+BEPU_DI WorkRecord load_record(const WorkRecord* r) {
+    const int4 lo = __ldg(reinterpret_cast<const int4*>(r)), hi = __ldg(reinterpret_cast<const int4*>(r) + 1);
+    WorkRecord w;
+    w.refs = reinterpret_cast<int32_t*>((unsigned long long)(unsigned int)lo.x | ((unsigned long long)(unsigned int)lo.y << 32));
+    w.prestep = reinterpret_cast<float*>((unsigned long long)(unsigned int)lo.z | ((unsigned long long)(unsigned int)lo.w << 32));
+    w.impulses = reinterpret_cast<float*>((unsigned long long)(unsigned int)hi.x | ((unsigned long long)(unsigned int)hi.y << 32));
+    w.type_id = hi.z;
+    w.live_lanes = hi.w;
+    return w;
+}
+
 // Type registry: BatchTypeId constants of the reference (Contact/ContactConvexTypes.cs, ContactNonconvexTypes.cs, joint files).
 #define BEPU_CONTACT_TYPES(X)                                                                                                     \
     X(0, ConvexOneBody<1>) X(1, ConvexOneBody<2>) X(2, ConvexOneBody<3>) X(3, ConvexOneBody<4>)                                   \
@@ -212,29 +222,46 @@ BEPU_DI void run_lane(const DeviceTypeBatch& tb, int bundle, int lane, const Bod
     X(15, NonconvexTwoBody<2>) X(16, NonconvexTwoBody<3>) X(17, NonconvexTwoBody<4>)
 
 template <int STAGE>
-BEPU_DI void run_bundle(const DeviceTypeBatch& tb, int bundle, int lane, const BodyBuffers& B, const FrameParams& fp) {
-    switch (tb.type_id) {
+BEPU_DI void run_bundle(const WorkRecord& rec, int lane, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+    const int32_t* refs = rec.refs + lane;
+    float* p = rec.prestep + lane;
+    float* a = rec.impulses + lane;
+    switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \
-    case ID: run_lane<T, STAGE>(tb, bundle, lane, B, fp); break;
+    case ID: run_lane<T, STAGE>(refs, p, a, enc0, enc1, B, fp); break;
         BEPU_CONTACT_TYPES(BEPU_CASE)
         BEPU_JOINT_TYPES(BEPU_CASE)
 #undef BEPU_CASE
         default: break;
     }
 }
+// The reference arena is padded, so reading a second body-reference row is always in bounds (one-body types ignore it).
+template <int STAGE> BEPU_DI void run_bundle(const WorkRecord& rec, int lane, const BodyBuffers& B, const FrameParams& fp) {
+    const uint32_t enc0 = (uint32_t)__ldg(rec.refs + lane), enc1 = (uint32_t)__ldg(rec.refs + kLanes + lane);
+    run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
+}
 
 // ---- kernels ------------------------------------------------------------------------------------------------------------
 constexpr int kStageBlockThreads = 64;
 
 template <int STAGE>
-__global__ void __launch_bounds__(kStageBlockThreads) constraint_stage_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count,
-                                                                               BodyBuffers B, const FrameParams* __restrict__ fpp) {
+__global__ void __launch_bounds__(kStageBlockThreads) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp) {
+    // Programmatic dependent launch: let the NEXT stage's grid become resident right away, and do everything that does not depend on
+    // the previous stage (work record, body references, frame scalars: all immutable during a solve) before waiting for it.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int warp = (blockIdx.x * kStageBlockThreads + threadIdx.x) >> 5;
-    if (warp >= work_count) return;
-    const WorkItem w = work[warp];
-    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int lane = threadIdx.x & 31;
+    WorkRecord rec{};
+    uint32_t enc0 = (uint32_t)kRefEmpty, enc1 = 0;
+    const bool active = warp < work_count;
+    if (active) {
+        rec = load_record(records + warp);
+        enc0 = (uint32_t)__ldg(rec.refs + lane);
+        enc1 = (uint32_t)__ldg(rec.refs + kLanes + lane);
+    }
     const FrameParams fp = *fpp;
-    run_bundle<STAGE>(tb, w.bundle, threadIdx.x & 31, B, fp);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (active) run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
 }
 
 // IntegrateKinematicVelocities / IntegrateKinematicPosesAndVelocities (PoseIntegrator.cs:L451-487, L493-535)

@@ -157,11 +157,12 @@ struct bepucuda_ctx {
     bool constraints_open = false, constraints_ready = false, data_dirty = false;
     std::vector<SourceTypeBatch> sources;
     ChunkArena raw_arena, pinned_arena;
-    DeviceBuffer source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
+    DeviceBuffer record_table, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
     std::vector<DeviceTypeBatch> tbs;
     std::vector<TransposeDesc> tdescs;
     std::vector<WorkItem> work;                 // grouped by device batch, then the incremental list
     std::vector<int32_t> bundle_live;           // live constraints per work item (parallel to `work`)
+    std::vector<WorkRecord> records;            // what the solver kernels read (parallel to `work`)
     std::vector<std::pair<int, int>> batch_work; // per device batch: (begin, count) into work
     int inc_work_begin = 0, inc_work_count = 0;
     int all_work_count = 0;                     // work[0 .. all_work_count) covers every bundle once
@@ -230,15 +231,14 @@ void invalidate_graph(bepucuda_ctx* ctx) {
 // Issues the whole stage sequence of one frame as individual launches on `s` (used directly in STREAM mode and under
 // capture in GRAPH mode). Order: Solver_Solve.cs:L1419-1479, then PoseIntegrator.IntegrateAfterSubstepping.
 void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) {
-    const DeviceTypeBatch* tbs = ctx->tb_table.as<DeviceTypeBatch>();
-    const WorkItem* work = ctx->work_table.as<WorkItem>();
+    const WorkRecord* records = ctx->record_table.as<WorkRecord>();
     const FrameParams* fp = ctx->frame_params_dev.as<FrameParams>();
     const int32_t* kin = ctx->kinematics_dev.as<int32_t>();
     int64_t n = 0;
     for (const StageOp& op : ctx->program) {
         switch (op.stage) {
             case kStageWarmStartFirst: case kStageWarmStart: case kStageSolve: case kStageIncremental:
-                if (op.work_count > 0) { ctx->launchers->constraint_stage(op.stage, tbs, work + op.work_begin, op.work_count, ctx->B, fp, s); ++n; }
+                if (op.work_count > 0) { ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, ctx->cfg.reserved[1] == 0, s); ++n; }
                 break;
             case kStageKinematicFirst: case kStageKinematic:
                 if (op.work_count > 0) { ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, s); ++n; }
@@ -361,7 +361,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
     DeviceBuffer* bufs[] = {&ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
-                            &ctx->sync_mask, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
+                            &ctx->sync_mask, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev};
     for (auto b : bufs) b->release();
     ctx->raw_arena.release();
@@ -657,7 +657,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
         prestep_floats += (size_t)ctx->tbs[i].bundle_count * t->prestep_rows * 32;
         impulse_floats += (size_t)ctx->tbs[i].bundle_count * t->impulse_rows * 32;
     }
-    CK(ctx->refs32.reserve(refs_floats * 4 + 4));
+    CK(ctx->refs32.reserve(refs_floats * 4 + 1024));  // slack: solver warps always read two body-reference rows
     CK(ctx->prestep32.reserve(prestep_floats * 4 + 4));
     CK(ctx->impulses32.reserve(impulse_floats * 4 + 4));
     CK(ctx->map_table.reserve(maps.size() * 4 + 4));
@@ -692,17 +692,33 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
             for (int k = 0; k < ctx->tbs[tb].bundle_count; ++k) { ctx->work.push_back({(int)tb, k}); ctx->bundle_live.push_back(live_in_bundle((int)tb, k)); }
     ctx->inc_work_count = (int)ctx->work.size() - ctx->inc_work_begin;
 
+    ctx->records.resize(ctx->work.size());
+    for (size_t i = 0; i < ctx->work.size(); ++i) {
+        const WorkItem& w = ctx->work[i];
+        const DeviceTypeBatch& tb = ctx->tbs[w.type_batch];
+        const TypeInfo* t = get_type_info(tb.type_id);
+        WorkRecord r{};
+        r.refs = tb.refs + (size_t)w.bundle * t->bodies * 32;
+        r.prestep = tb.prestep + (size_t)w.bundle * t->prestep_rows * 32;
+        r.impulses = tb.impulses + (size_t)w.bundle * t->impulse_rows * 32;
+        r.type_id = tb.type_id;
+        r.live_lanes = ctx->bundle_live[i];
+        ctx->records[i] = r;
+    }
+
     // ---- upload tables ----
     int32_t bodies_per_type[64];
     for (int i = 0; i < 64; ++i) bodies_per_type[i] = get_type_info(i) ? get_type_info(i)->bodies : 0;
     CK(ctx->tb_table.reserve(ctx->tbs.size() * sizeof(DeviceTypeBatch) + 16));
     CK(ctx->tdesc_table.reserve(ctx->tdescs.size() * sizeof(TransposeDesc) + 16));
     CK(ctx->work_table.reserve(ctx->work.size() * sizeof(WorkItem) + 16));
+    CK(ctx->record_table.reserve(ctx->records.size() * sizeof(WorkRecord) + 64));
     CK(ctx->bodies_per_type.reserve(sizeof(bodies_per_type)));
     CK(ctx->kinematics_dev.reserve(ctx->kinematics.size() * 4 + 4));
     if (!ctx->tbs.empty()) CK(cudaMemcpyAsync(ctx->tb_table.ptr, ctx->tbs.data(), ctx->tbs.size() * sizeof(DeviceTypeBatch), cudaMemcpyHostToDevice, ctx->stream));
     if (!ctx->tdescs.empty()) CK(cudaMemcpyAsync(ctx->tdesc_table.ptr, ctx->tdescs.data(), ctx->tdescs.size() * sizeof(TransposeDesc), cudaMemcpyHostToDevice, ctx->stream));
     if (!ctx->work.empty()) CK(cudaMemcpyAsync(ctx->work_table.ptr, ctx->work.data(), ctx->work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->records.empty()) CK(cudaMemcpyAsync(ctx->record_table.ptr, ctx->records.data(), ctx->records.size() * sizeof(WorkRecord), cudaMemcpyHostToDevice, ctx->stream));
     if (!maps.empty()) CK(cudaMemcpyAsync(ctx->map_table.ptr, maps.data(), maps.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->bodies_per_type.ptr, bodies_per_type, sizeof(bodies_per_type), cudaMemcpyHostToDevice, ctx->stream));
     if (!ctx->kinematics.empty()) CK(cudaMemcpyAsync(ctx->kinematics_dev.ptr, ctx->kinematics.data(), ctx->kinematics.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -790,8 +806,9 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     CK(cudaEventRecord(ctx->ev_solve_begin, ctx->stream));
     int64_t launches = 0;
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_PERSISTENT) {
-        int rc = ctx->launchers->persistent(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(),
-                                            ctx->kinematics_dev.as<int32_t>(), ctx->B, ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->stream);
+        CK(cudaMemsetAsync(ctx->barrier_dev.ptr, 0, sizeof(unsigned int), ctx->stream));
+        int rc = ctx->launchers->persistent(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->record_table.as<WorkRecord>(), ctx->kinematics_dev.as<int32_t>(), ctx->B,
+                                            ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->cfg.reserved[0], ctx->stream);
         if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "persistent kernel launch");
         launches = 1;
     } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_GRAPH) {
@@ -931,8 +948,7 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
         CK(cudaEventCreate(&ev));
         ctx->profile_events.push_back(ev);
     }
-    const DeviceTypeBatch* tbs = ctx->tb_table.as<DeviceTypeBatch>();
-    const WorkItem* work = ctx->work_table.as<WorkItem>();
+    const WorkRecord* records = ctx->record_table.as<WorkRecord>();
     const FrameParams* fp = ctx->frame_params_dev.as<FrameParams>();
     const int32_t* kin = ctx->kinematics_dev.as<int32_t>();
     std::vector<int> launched(ctx->program.size(), 0);
@@ -941,7 +957,7 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
         const bool has_work = op.stage == kStageFinalPose ? ctx->B.count > 0 : op.work_count > 0;
         if (!has_work) continue;
         CK(cudaEventRecord(ctx->profile_events[2 * i], ctx->stream));
-        if (op.stage <= kStageIncremental) ctx->launchers->constraint_stage(op.stage, tbs, work + op.work_begin, op.work_count, ctx->B, fp, ctx->stream);
+        if (op.stage <= kStageIncremental) ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, false, ctx->stream);
         else if (op.stage <= kStageKinematic) ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, ctx->stream);
         else ctx->launchers->final_pose(ctx->B, fp, ctx->stream);
         CK(cudaEventRecord(ctx->profile_events[2 * i + 1], ctx->stream));

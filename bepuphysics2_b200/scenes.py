@@ -376,7 +376,7 @@ _RAGDOLL_CONNECTIONS = [
 ]
 
 
-def ragdolls(count=10_000, seed=5, contacts_per_body=2.0, motor="motor", spacing=2.5):
+def ragdolls(count=10_000, seed=5, contacts_per_body=2.0, motor="motor", spacing=2.5, pose_noise=0.15):
     """Config 3: `count` ragdolls with the RagdollDemo.AddRagdoll joint topology at random poses in a kinematic rotating tube, joint springs
     SpringSettings(15 Hz, 1) (RagdollDemo.cs:L443), AngularMotor settings MotorSettings(float.MaxValue, 0.01) (L200) or, with motor="servo", the
     AngularServo variant the demo comments mention (L199). Plus `contacts_per_body` contact manifolds per body: against the kinematic tube
@@ -401,6 +401,14 @@ def ragdolls(count=10_000, seed=5, contacts_per_body=2.0, motor="motor", spacing
     rq = _random_unit_quaternions(rng, count)
     pos = base[:, None, :] + qrot(np.broadcast_to(local_pos, (count, nb, 3)), rq[:, None, :])
     orient = np.broadcast_to(rq[:, None, :], (count, nb, 4))
+    if pose_noise > 0:
+        # ragdolls in motion, not in their exact rest pose: every body is rotated a little about a random axis (rest pose makes the twist/servo angle
+        # measurements sit exactly on acos(1), where the reference's formulation is numerically ill-conditioned)
+        axis = rng.standard_normal((count, nb, 3)).astype(np.float32)
+        axis /= np.linalg.norm(axis, axis=2, keepdims=True)
+        half = (rng.uniform(-pose_noise, pose_noise, size=(count, nb, 1)) * 0.5).astype(np.float32)
+        dq = np.concatenate([axis * np.sin(half), np.cos(half)], axis=2).astype(np.float32)
+        orient = qcat(dq, orient)
     lin = rng.uniform(-0.5, 0.5, size=(count, 1, 3)).astype(np.float32) + rng.uniform(-0.2, 0.2, size=(count, nb, 3)).astype(np.float32)
     ang = rng.uniform(-0.5, 0.5, size=(count, nb, 3)).astype(np.float32)
     bodies = np.zeros((n, 32), dtype=np.float32)

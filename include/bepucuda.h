@@ -54,7 +54,7 @@ typedef struct bepucuda_config {
      * (RyuJIT does not contract Vector<float> expressions). 0 = FMA contraction on (fast). */
     int32_t strict_fp;
     int32_t execution_mode;   /* enum bepucuda_execution_mode */
-    int32_t reserved[5];
+    int32_t reserved[5];      /* reserved[0]: persistent mode CTAs per SM (0 = default 1); reserved[1]: 1 disables programmatic dependent launch between stage kernels */
 } bepucuda_config;
 
 /* Declarative stand-in for the user's IPoseIntegratorCallbacks struct (BepuPhysics/PoseIntegrator.cs:L42-94).

@@ -44,6 +44,7 @@ def load():
         path = os.path.join(HERE, "libbepu_oracle.so")
         if not os.path.exists(path):
             build()
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # libgomp's default spin-wait collapses when the container has fewer CPUs than it reports
         _LIB = C.CDLL(path)
         _LIB.oracle_solve.argtypes = [C.POINTER(OracleScene), C.c_float]
         _LIB.oracle_type_info.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]

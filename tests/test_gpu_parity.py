@@ -12,12 +12,12 @@ pytestmark = pytest.mark.gpu
 DT = 1.0 / 60.0
 
 
-def _parity(scene, exact=True, mode=EXEC_GRAPH, frames=1, rtol=0.0, atol=0.0, **kw):
+def _parity(scene, exact=True, mode=EXEC_GRAPH, frames=1, rel_rms=1e-3, max_abs=5e-2, **kw):
     a = util.make_sim(scene, **kw)
     b = util.make_sim(scene, **kw)
     ref = util.run_oracle(a, DT, frames=frames)
     got = util.run_gpu(b, DT, frames=frames, strict=exact, mode=mode)
-    util.compare(ref, got, exact=exact, rtol=rtol, atol=atol)
+    util.compare(ref, got, exact=exact, rel_rms=rel_rms, max_abs=max_abs)
     return got
 
 
@@ -61,8 +61,9 @@ def test_sequential_fallback_batch_bit_exact(libs):
 
 
 def test_fast_build_within_tolerance(libs):
-    """FMA-contracted build: body velocities and accumulated impulses within 1e-3 relative (1e-4 absolute) of the oracle after one frame."""
-    _parity(scenes.shape_pile(3000, seed=5), exact=False, rtol=1e-3, atol=2e-4, substeps=8, velocity_iterations=2)
+    """FMA-contracted + approximate div/sqrt build on contacts: relative RMS error <= 1e-5 and max abs error <= 1e-4 on velocities, poses and
+    accumulated impulses after one frame of 8 substeps x 2 iterations (measured: ~4e-7 / 2e-6)."""
+    _parity(scenes.shape_pile(3000, seed=5), exact=False, rel_rms=1e-5, max_abs=1e-4, substeps=8, velocity_iterations=2)
 
 
 def test_unconstrained_and_kinematic_bodies(libs):
@@ -99,4 +100,6 @@ def test_ragdolls_substepped_servo_variant_bit_exact(libs):
 
 
 def test_ragdolls_persistent_fast_within_tolerance(libs):
-    _parity(scenes.ragdolls(60, seed=5), exact=False, mode=EXEC_PERSISTENT, rtol=2e-3, atol=5e-4, substeps=1, velocity_iterations=4)
+    """Fast build on joints: relative RMS error <= 1e-3, max abs error <= 2e-2 after one frame (measured ~3e-5 / 1e-3; the twist/servo angle
+    measurements go through acos near 1, which amplifies rounding: see tools/fast_error_stats.py)."""
+    _parity(scenes.ragdolls(60, seed=5), exact=False, mode=EXEC_PERSISTENT, rel_rms=1e-3, max_abs=2e-2, substeps=1, velocity_iterations=4)

@@ -36,7 +36,12 @@ def _run(cmd):
     return r.stdout
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: development A/B builds (libbepucuda_<variant>.so with extra -D flags, selected at run time with BEPUCUDA_VARIANT)."""
+    global BUILD, LIB_CUDA
+    if variant:
+        BUILD = os.path.join(CSRC, "build_" + variant)
+        LIB_CUDA = os.path.join(HERE, "libbepucuda_%s.so" % variant)
     os.makedirs(BUILD, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "bepucuda.h"))
@@ -51,7 +56,7 @@ def build(force=False, verbose=False):
         o = os.path.join(BUILD, obj)
         s = os.path.join(CSRC, src)
         if force or _newer(o, [s] + headers):
-            jobs.append([NVCC] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
+            jobs.append([NVCC] + NVCC_FLAGS + extra + list(defines) + ["-c", s, "-o", o])
     if jobs:
         with ThreadPoolExecutor(max_workers=4) as ex:
             for out in ex.map(_run, jobs):
@@ -60,6 +65,8 @@ def build(force=False, verbose=False):
     objs = [os.path.join(BUILD, u[0]) for u in units]
     if force or _newer(LIB_CUDA, objs):
         _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB_CUDA] + objs)
+    if variant:
+        return LIB_CUDA, LIB_HOST
     host_src = os.path.join(CSRC, "host", "bepu_host.cpp")
     if force or _newer(LIB_HOST, [host_src, LIB_CUDA] + headers):
         _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB_HOST, host_src, "-L" + HERE, "-lbepucuda", "-Wl,-rpath,$ORIGIN"])
@@ -67,5 +74,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    _variant = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    build(force="--force" in sys.argv, verbose=True, variant=_variant, defines=[a for a in sys.argv if a.startswith("-D")])
     print("built", LIB_CUDA, LIB_HOST)

@@ -15,34 +15,37 @@ namespace BEPU_NS {
 
 using namespace bepucuda;
 
-// ---- body records ---------------------------------------------------------------------------------------------------
+// ---- body records: one 32-byte record = one DRAM sector = ONE 256-bit load/store (LDG.E.256 / STG.E.256, new on sm_100) ----------------
+struct F8 { float a, b, c, d, e, f, g, h; };
+BEPU_DI F8 ld256(const float4* p) {
+    F8 r;
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a), "=f"(r.b), "=f"(r.c), "=f"(r.d), "=f"(r.e), "=f"(r.f), "=f"(r.g), "=f"(r.h)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+BEPU_DI void st256(float4* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+}
 BEPU_DI void load_velocity(const float4* vel, uint32_t i, Velocity& v) {
-    float4 a = __ldcg(vel + 2 * (size_t)i), b = __ldcg(vel + 2 * (size_t)i + 1);
-    v.lin = {a.x, a.y, a.z};
-    v.ang = {b.x, b.y, b.z};
+    const F8 r = ld256(vel + 2 * (size_t)i);
+    v.lin = {r.a, r.b, r.c};
+    v.ang = {r.e, r.f, r.g};
 }
-BEPU_DI void store_velocity(float4* vel, uint32_t i, const Velocity& v) {
-    __stcg(vel + 2 * (size_t)i, make_float4(v.lin.x, v.lin.y, v.lin.z, 0.0f));
-    __stcg(vel + 2 * (size_t)i + 1, make_float4(v.ang.x, v.ang.y, v.ang.z, 0.0f));
-}
+BEPU_DI void store_velocity(float4* vel, uint32_t i, const Velocity& v) { st256(vel + 2 * (size_t)i, v.lin.x, v.lin.y, v.lin.z, 0.0f, v.ang.x, v.ang.y, v.ang.z, 0.0f); }
 BEPU_DI void load_inertia(const float4* in, uint32_t i, Inertia& r) {
-    float4 a = __ldcg(in + 2 * (size_t)i), b = __ldcg(in + 2 * (size_t)i + 1);
-    r.t = {a.x, a.y, a.z, a.w, b.x, b.y};
-    r.inv_mass = b.z;
+    const F8 x = ld256(in + 2 * (size_t)i);
+    r.t = {x.a, x.b, x.c, x.d, x.e, x.f};
+    r.inv_mass = x.g;
 }
-BEPU_DI void store_inertia(float4* in, uint32_t i, const Inertia& r) {
-    __stcg(in + 2 * (size_t)i, make_float4(r.t.xx, r.t.yx, r.t.yy, r.t.zx));
-    __stcg(in + 2 * (size_t)i + 1, make_float4(r.t.zy, r.t.zz, r.inv_mass, 0.0f));
-}
+BEPU_DI void store_inertia(float4* in, uint32_t i, const Inertia& r) { st256(in + 2 * (size_t)i, r.t.xx, r.t.yx, r.t.yy, r.t.zx, r.t.zy, r.t.zz, r.inv_mass, 0.0f); }
 BEPU_DI void load_pose(const float4* pose, uint32_t i, V3& pos, Q4& q) {
-    float4 a = __ldcg(pose + 2 * (size_t)i), b = __ldcg(pose + 2 * (size_t)i + 1);
-    q = {a.x, a.y, a.z, a.w};
-    pos = {b.x, b.y, b.z};
+    const F8 x = ld256(pose + 2 * (size_t)i);
+    q = {x.a, x.b, x.c, x.d};
+    pos = {x.e, x.f, x.g};
 }
-BEPU_DI void store_pose(float4* pose, uint32_t i, V3 pos, Q4 q) {
-    __stcg(pose + 2 * (size_t)i, make_float4(q.x, q.y, q.z, q.w));
-    __stcg(pose + 2 * (size_t)i + 1, make_float4(pos.x, pos.y, pos.z, 0.0f));
-}
+BEPU_DI void store_pose(float4* pose, uint32_t i, V3 pos, Q4 q) { st256(pose + 2 * (size_t)i, q.x, q.y, q.z, q.w, pos.x, pos.y, pos.z, 0.0f); }
 
 // ---- integration (PoseIntegrator.cs:L99-261, TypeProcessor.cs:L1204-1283, Demos/DemoCallbacks.cs:L99-102) -----------
 BEPU_DI Q4 integrate_orientation(Q4 start, V3 w, float halfDt) {  // PoseIntegrator.cs:L146-164
@@ -243,9 +246,12 @@ template <int STAGE> BEPU_DI void run_bundle(const WorkRecord& rec, int lane, co
 
 // ---- kernels ------------------------------------------------------------------------------------------------------------
 constexpr int kStageBlockThreads = 64;
+#ifndef BEPU_STAGE_MIN_BLOCKS
+#define BEPU_STAGE_MIN_BLOCKS 1
+#endif
 
 template <int STAGE>
-__global__ void __launch_bounds__(kStageBlockThreads) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp) {
+__global__ void __launch_bounds__(kStageBlockThreads, BEPU_STAGE_MIN_BLOCKS) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp) {
     // Programmatic dependent launch: let the NEXT stage's grid become resident right away, and do everything that does not depend on
     // the previous stage (work record, body references, frame scalars: all immutable during a solve) before waiting for it.
     asm volatile("griddepcontrol.launch_dependents;");

@@ -103,7 +103,8 @@ def load_libraries():
     global _LIBS
     if _LIBS is not None:
         return _LIBS
-    cuda_path = os.path.join(HERE, "libbepucuda.so")
+    variant = os.environ.get("BEPUCUDA_VARIANT")  # development A/B builds only (see _build.py)
+    cuda_path = os.path.join(HERE, "libbepucuda_%s.so" % variant if variant else "libbepucuda.so")
     host_path = os.path.join(HERE, "libbepuhost.so")
     for p in (cuda_path, host_path):
         if not os.path.exists(p):

@@ -1,0 +1,50 @@
+// P/Invoke surface of libbepucuda (include/bepucuda.h). Not compiled in this repository (no .NET toolchain in the build image); it is the
+// binding a bepuphysics2 maintainer adds next to their application. Every entry point replaces the reference call cited in the header.
+using System;
+using System.Runtime.InteropServices;
+
+namespace BepuCuda
+{
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct Config { public int DeviceOrdinal, StrictFp, ExecutionMode; public fixed int Reserved[5]; }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct IntegratorDesc
+    {
+        public fixed float Gravity[3];
+        public float LinearDamping, AngularDamping;
+        public int AngularIntegrationMode, AllowSubstepsForUnconstrained, IntegrateVelocityForKinematics;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct Timings
+    {
+        public float SolveMs, UploadMs, DownloadMs;
+        public long ConstraintCount, ConstraintIterations, StageCount, KernelLaunches, AlgorithmicBytes, H2DBytes, D2HBytes;
+        public int DeviceBatchCount, FallbackLevelCount;
+    }
+
+    public static unsafe class Native
+    {
+        const string Lib = "bepucuda";
+        [DllImport(Lib)] public static extern int bepucuda_create(Config* cfg, IntPtr* ctx);
+        [DllImport(Lib)] public static extern int bepucuda_destroy(IntPtr ctx);
+        [DllImport(Lib)] public static extern IntPtr bepucuda_last_error(IntPtr ctx);
+        [DllImport(Lib)] public static extern int bepucuda_type_info(int typeId, int* bodies, int* prestepFloats, int* impulseFloats);
+        [DllImport(Lib)] public static extern int bepucuda_host_register(IntPtr ctx, void* ptr, long bytes);
+        [DllImport(Lib)] public static extern int bepucuda_host_unregister(IntPtr ctx, void* ptr);
+        [DllImport(Lib)] public static extern int bepucuda_set_solve_description(IntPtr ctx, int substepCount, int* velocityIterationsPerSubstep, int fallbackBatchThreshold);
+        [DllImport(Lib)] public static extern int bepucuda_set_integrator(IntPtr ctx, IntegratorDesc* desc);
+        [DllImport(Lib)] public static extern int bepucuda_upload_bodies(IntPtr ctx, void* bodyDynamics, int bodyCount);
+        [DllImport(Lib)] public static extern int bepucuda_begin_constraints(IntPtr ctx, int sourceBundleWidth, int batchCount);
+        [DllImport(Lib)] public static extern int bepucuda_upload_type_batch(IntPtr ctx, int batchIndex, int typeBatchIndex, int typeId, int constraintCount, void* bodyReferences, void* prestep, void* accumulatedImpulses);
+        [DllImport(Lib)] public static extern int bepucuda_set_constrained_kinematics(IntPtr ctx, int* bodyIndices, int count);
+        [DllImport(Lib)] public static extern int bepucuda_end_constraints(IntPtr ctx);
+        [DllImport(Lib)] public static extern int bepucuda_update_type_batch(IntPtr ctx, int batchIndex, int typeBatchIndex, void* prestep, void* accumulatedImpulses);
+        [DllImport(Lib)] public static extern int bepucuda_solve(IntPtr ctx, float dt);
+        [DllImport(Lib)] public static extern int bepucuda_synchronize(IntPtr ctx);
+        [DllImport(Lib)] public static extern int bepucuda_download_bodies(IntPtr ctx, void* bodyDynamicsOut, int bodyCount);
+        [DllImport(Lib)] public static extern int bepucuda_download_impulses(IntPtr ctx);
+        [DllImport(Lib)] public static extern int bepucuda_get_timings(IntPtr ctx, Timings* timings);
+    }
+}

@@ -58,12 +58,16 @@ def run(mode, bps=0, do_flush=True, strict=False, pdl=True):
     ts.close()
 
 
-run(EXEC_GRAPH)
-run(EXEC_GRAPH, pdl=False)
-run(EXEC_STREAM)
-run(EXEC_STREAM, pdl=False)
-run(EXEC_PERSISTENT, 1)
-run(EXEC_GRAPH, strict=True)
+if os.environ.get("SWEEP", "full") == "graph":
+    run(EXEC_GRAPH)
+    run(EXEC_GRAPH, pdl=False)
+else:
+    run(EXEC_GRAPH)
+    run(EXEC_GRAPH, pdl=False)
+    run(EXEC_STREAM)
+    run(EXEC_STREAM, pdl=False)
+    run(EXEC_PERSISTENT, 1)
+    run(EXEC_GRAPH, strict=True)
 
 if args.cpu:
     from oracle import binding as ob

@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--substeps", type=int, default=8)
     ap.add_argument("--iterations", type=int, default=2)
     ap.add_argument("--scene", default="shape_pile", choices=["shape_pile", "ragdolls", "fallback_stress"])
-    ap.add_argument("--mode", default="persistent", choices=["graph", "persistent", "stream"])
+    ap.add_argument("--mode", default="graph", choices=["graph", "persistent", "stream", "dataflow"])
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
@@ -178,7 +178,7 @@ def main():
     import torch
 
     import bepuphysics2_b200 as bp
-    from bepuphysics2_b200.native import EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
+    from bepuphysics2_b200.native import EXEC_DATAFLOW, EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,7 +192,7 @@ def main():
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mode = {"graph": EXEC_GRAPH, "persistent": EXEC_PERSISTENT, "stream": EXEC_STREAM}[args.mode]
+    mode = {"graph": EXEC_GRAPH, "persistent": EXEC_PERSISTENT, "stream": EXEC_STREAM, "dataflow": EXEC_DATAFLOW}[args.mode]
 
     sim, description = build_sim(args, seed=5 + rank)  # every rank owns an independent pile (island)
     ts = bp.CudaTimestepper(sim, device=local_rank, strict_fp=args.strict, execution_mode=mode)
@@ -247,7 +247,7 @@ def main():
 
     # ---- per-stage device time (event pair around every launch) for the roofline of the dominant kernel ----
     prof = None
-    if rank == 0:
+    if rank == 0 and args.mode != "dataflow":
         flush.fill_(1)
         torch.cuda.synchronize()
         ts.profile_stages(DT)
@@ -267,7 +267,7 @@ def main():
         peak, peak_source = load_peaks()
         value = ci_all * args.steps / (total_ms_max * 1e-3)
         e2e_value = ci_all * e2e_steps / (e2e_ms_max * 1e-3)
-        if args.mode == "persistent":
+        if args.mode in ("persistent", "dataflow"):
             # one kernel per step: the whole stage program
             roof_bytes, roof_ms, roof_kernel = alg_bytes_per_step, total_ms / args.steps, "persistent_solve_kernel (whole step)"
         else:

@@ -61,6 +61,7 @@ struct FrameParams {
     int32_t final_steps;       // integration steps for unconstrained bodies in the final pass
     int32_t angular_mode;
     int32_t integrate_velocity_for_kinematics;
+    uint32_t pass_base;        // dataflow mode: number of WarmStart/Solve passes executed since the body versions were last reset
 };
 
 enum Stage : int32_t {
@@ -71,6 +72,9 @@ enum Stage : int32_t {
     kStageKinematicFirst = 4,
     kStageKinematic = 5,
     kStageFinalPose = 6,
+    // Dataflow mode: one substep's WarmStart pass + all Solve passes with per-body version dependencies instead of barriers.
+    // work_count = bundles of the whole active set, pad = (solve passes << 1) | (first substep ? 1 : 0).
+    kStageRegion = 7,
 };
 
 // One entry per warp of a stage launch: which bundle of which device type batch.
@@ -96,6 +100,11 @@ struct StageOp {
     int32_t work_count;   // warps of work (constraint stages), bodies (final pose), kinematics (kinematic stages)
     int32_t pad;
 };
+
+// Dataflow chain word per (constraint, body slot), same shape as the body reference arena: (degree of the body << 16) | rank of this constraint among
+// the body's constraints in device batch order. A lane writing body X at pass P expects version P * degree + rank and publishes version + 1.
+constexpr int kChainDegreeShift = 16;
+constexpr uint32_t kChainRankMask = 0xFFFFu;
 
 struct TypeInfo {
     int32_t bodies, prestep_rows, impulse_rows, incremental;

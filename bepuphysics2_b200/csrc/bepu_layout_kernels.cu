@@ -154,6 +154,49 @@ __global__ void bundle_flags_pass_kernel(const DeviceTypeBatch* __restrict__ tbs
         }
     }
 }
+// Dataflow chain words. Phase 0 (one launch per device batch, in order): rank = how many earlier device batches reference the body as dynamic.
+// Phase 1 (one launch): or in the body's total degree. Also resets nothing else; version words are reset by reset_versions_kernel.
+__global__ void chain_rank_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
+                                  long long chain_delta, int32_t* body_counter) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int nb = bodies_per_type[tb.type_id];
+    for (int s = 0; s < nb; ++s) {
+        int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
+        uint32_t* c = reinterpret_cast<uint32_t*>(r + chain_delta);
+        const int32_t enc = *r;
+        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) { *c = 0; continue; }
+        const int idx = enc & kRefIndexMask;
+        const int rank = body_counter[idx];  // a dynamic body appears at most once per device batch: no race inside a launch
+        body_counter[idx] = rank + 1;
+        *c = (uint32_t)rank & kChainRankMask;
+    }
+}
+__global__ void chain_degree_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
+                                    long long chain_delta, const int32_t* __restrict__ body_counter, int32_t* error_flag) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int nb = bodies_per_type[tb.type_id];
+    for (int s = 0; s < nb; ++s) {
+        const int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
+        uint32_t* c = reinterpret_cast<uint32_t*>(const_cast<int32_t*>(r) + chain_delta);
+        const int32_t enc = *r;
+        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
+        const int degree = body_counter[enc & kRefIndexMask];
+        if (degree > 0xFFFF) atomicExch(error_flag, 3);
+        *c |= (uint32_t)degree << kChainDegreeShift;
+    }
+}
+__global__ void reset_versions_kernel(float4* velocity, int body_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= body_count) return;
+    velocity[2 * (size_t)i].w = 0.0f;
+    velocity[2 * (size_t)i + 1].w = 0.0f;
+}
 __global__ void check_invariant_kernel(int body_count, const int32_t* __restrict__ sync_refcount, const unsigned long long* __restrict__ sync_mask, int32_t* error_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= body_count) return;
@@ -169,6 +212,31 @@ __global__ void mark_kinematics_kernel(const int32_t* __restrict__ kinematics, i
 __global__ void fill_i32_kernel(int32_t* p, size_t n, int32_t v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+// Batched copy: ONE launch moves every (page-locked, device-mapped) host buffer of a frame across PCIe/C2C in either direction, replacing hundreds of
+// small cudaMemcpyAsync calls (one per type batch buffer). Chunks are <= 64 KiB; a CTA streams a chunk with 16-byte accesses, fully coalesced, so the
+// link sees maximum-size read/write requests and many of them in flight.
+__global__ void batched_copy_kernel(const CopyChunk* __restrict__ chunks, int chunk_count) {
+    for (int c = blockIdx.x; c < chunk_count; c += gridDim.x) {
+        const CopyChunk ch = chunks[c];
+        if ((((size_t)ch.dst | (size_t)ch.src | ch.bytes) & 15) == 0) {
+            const uint4* s = reinterpret_cast<const uint4*>(ch.src);
+            uint4* d = reinterpret_cast<uint4*>(ch.dst);
+            const size_t n = ch.bytes >> 4;
+            for (size_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        } else {
+            const uint32_t* s = reinterpret_cast<const uint32_t*>(ch.src);
+            uint32_t* d = reinterpret_cast<uint32_t*>(ch.dst);
+            const size_t n = ch.bytes >> 2;
+            for (size_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        }
+    }
+}
+void launch_batched_copy(const CopyChunk* chunks, int chunk_count, cudaStream_t s) {
+    if (chunk_count <= 0) return;
+    const int grid = chunk_count < 1184 ? chunk_count : 1184;  // 8 CTAs per SM at most; each keeps 256 x 16 B in flight
+    batched_copy_kernel<<<grid, 256, 0, s>>>(chunks, chunk_count);
 }
 
 static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -188,6 +256,19 @@ void launch_transpose_in_all(const DeviceTypeBatch* tbs, const TransposeDesc* de
 void launch_transpose_out_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s) {
     if (work_count <= 0) return;
     transpose_out_all_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, what);
+}
+void launch_chain_rank(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, int32_t* body_counter, cudaStream_t s) {
+    if (work_count <= 0) return;
+    chain_rank_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, chain_delta, body_counter);
+}
+void launch_chain_degree(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, const int32_t* body_counter,
+                         int32_t* error_flag, cudaStream_t s) {
+    if (work_count <= 0) return;
+    chain_degree_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, chain_delta, body_counter, error_flag);
+}
+void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s) {
+    if (body_count <= 0) return;
+    reset_versions_kernel<<<blocks_for(body_count, 256), 256, 0, s>>>(velocity, body_count);
 }
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
     if (n == 0) return;

@@ -21,6 +21,18 @@ enum { kTransposeRefs = 1, kTransposePrestep = 2, kTransposeImpulses = 4 };
 void launch_transpose_in_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s);
 void launch_transpose_out_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s);
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s);
+// One chunk (<= 64 KiB, sizes multiple of 4 bytes) of a batched host<->device copy through mapped pinned memory.
+struct CopyChunk {
+    void* dst;
+    const void* src;
+    size_t bytes;
+};
+void launch_batched_copy(const CopyChunk* chunks, int chunk_count, cudaStream_t s);
+// Dataflow chain words (see kChainDegreeShift): chain array = refs array + chain_delta (in int32 elements).
+void launch_chain_rank(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, int32_t* body_counter, cudaStream_t s);
+void launch_chain_degree(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, const int32_t* body_counter,
+                         int32_t* error_flag, cudaStream_t s);
+void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s);
 void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
                       int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
                       int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s);
@@ -36,6 +48,10 @@ struct SolverLaunchers {
     // barrier_counter must be zero at launch. blocks_per_sm <= 0 selects the default.
     int (*persistent)(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                       unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
+    // Dataflow persistent kernel: like `persistent`, but kStageRegion ops run a whole substep's WarmStart + Solve passes with per-body version
+    // dependencies (chain words at refs + chain_delta) instead of a barrier per (batch, stage). error_flag is set to 4 if a dependency never arrives.
+    int (*dataflow)(const StageOp* program, int op_count, const WorkRecord* records, long long chain_delta, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
+                    unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s);
 };
 const SolverLaunchers* get_launchers_bepu_fast();
 const SolverLaunchers* get_launchers_bepu_strict();

@@ -1,6 +1,7 @@
 // Compiled twice: -DBEPU_NS=bepu_fast (default FMA contraction) and -DBEPU_NS=bepu_strict -fmad=false.
 #include "bepu_solver_kernels.cuh"
 #include "bepu_persistent.cuh"
+#include "bepu_dataflow.cuh"
 #include "bepu_layout_kernels.h"
 
 namespace BEPU_NS {
@@ -41,7 +42,7 @@ static void launch_final_pose(const BodyBuffers& B, const FrameParams* fp, cudaS
     final_pose_kernel<<<(unsigned)((B.count + 255) / 256), 256, 0, s>>>(B, fp);
 }
 
-static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent};
+static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent, &launch_dataflow};
 
 }  // namespace BEPU_NS
 

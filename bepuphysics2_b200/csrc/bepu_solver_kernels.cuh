@@ -99,13 +99,12 @@ __device__ __noinline__ void integrate_angular_gyroscopic(Q4 orientation, Sym3 l
     fallback_if_inertia_incompatible(previous, w);
 }
 
-// GatherAndIntegrate for one body slot of one lane (TypeProcessor.cs:L1298-1397). The lane integrates iff the device body
-// reference carries kRefIntegrateBit; all other lanes read the world inertia their owner constraint stored earlier in this
-// substep, which is bit-identical to what the reference's bundle-wide recompute would give them.
+// GatherAndIntegrate for one body slot of one lane (TypeProcessor.cs:L1298-1397), after the velocity has been loaded. The lane integrates iff the
+// device body reference carries kRefIntegrateBit; all other lanes read the world inertia their owner constraint stored earlier in this substep,
+// which is bit-identical to what the reference's bundle-wide recompute would give them.
 template <int STAGE, bool NeedsPose>
-BEPU_DI void gather_for_warm_start(uint32_t enc, const BodyBuffers& B, const FrameParams& fp, BodyState& b, Velocity& v) {
+BEPU_DI void warm_start_body(uint32_t enc, const BodyBuffers& B, const FrameParams& fp, BodyState& b, Velocity& v) {
     const uint32_t idx = enc & kRefIndexMask;
-    load_velocity(B.velocity, idx, v);
     if (enc & kRefIntegrateBit) {
         Inertia local;
         load_inertia(B.inertia_local, idx, local);
@@ -148,6 +147,11 @@ BEPU_DI void gather_for_warm_start(uint32_t enc, const BodyBuffers& B, const Fra
             else integrate_angular_gyroscopic(q, local.t, v.ang, fp.dt);
         }
     }
+}
+template <int STAGE, bool NeedsPose>
+BEPU_DI void gather_for_warm_start(uint32_t enc, const BodyBuffers& B, const FrameParams& fp, BodyState& b, Velocity& v) {
+    load_velocity(B.velocity, enc & kRefIndexMask, v);
+    warm_start_body<STAGE, NeedsPose>(enc, B, fp, b, v);
 }
 
 // ---- uniform call shapes over contact and joint types ------------------------------------------------------------------

@@ -157,7 +157,7 @@ struct bepucuda_ctx {
     bool constraints_open = false, constraints_ready = false, data_dirty = false;
     std::vector<SourceTypeBatch> sources;
     ChunkArena raw_arena, pinned_arena;
-    DeviceBuffer record_table, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
+    DeviceBuffer chain32, body_counter, record_table, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
     std::vector<DeviceTypeBatch> tbs;
     std::vector<TransposeDesc> tdescs;
     std::vector<WorkItem> work;                 // grouped by device batch, then the incremental list
@@ -177,6 +177,15 @@ struct bepucuda_ctx {
 
     bepucuda_timings timings{};
     int64_t h2d_accum = 0;
+    struct HostRange { char* host; size_t bytes; char* dev; };
+    std::vector<HostRange> host_ranges;    // page-locked + device-mapped host memory registered through bepucuda_host_register
+    std::vector<CopyChunk> pending_h2d;    // batched copies waiting for the next flush
+    DeviceBuffer chunk_table;
+    struct ChunkStage { void* host = nullptr; size_t capacity = 0; cudaEvent_t done = nullptr; };
+    ChunkStage chunk_stage[4];             // pinned ring for chunk tables (a table must outlive its H2D copy)
+    int chunk_stage_next = 0;
+    uint32_t pass_counter = 0;      // dataflow mode: WarmStart/Solve passes since the body versions were reset
+    bool versions_dirty = true;     // velocity-record padding words do not hold valid versions
     cudaEvent_t user_events[16] = {};
     std::vector<cudaEvent_t> profile_events;
 };
@@ -203,10 +212,52 @@ void open_upload_window(bepucuda_ctx* ctx) {
     }
 }
 
+// Device alias of a host pointer if [ptr, ptr + bytes) lies inside a registered (mapped) range, else nullptr.
+char* map_host(bepucuda_ctx* ctx, const void* ptr, size_t bytes) {
+    const char* p = (const char*)ptr;
+    for (auto& r : ctx->host_ranges)
+        if (p >= r.host && p + bytes <= r.host + r.bytes) return r.dev + (p - r.host);
+    return nullptr;
+}
+void queue_chunks(std::vector<CopyChunk>& list, void* dst, const void* src, size_t bytes) {
+    const size_t kChunk = (size_t)64 << 10;
+    for (size_t off = 0; off < bytes; off += kChunk) list.push_back({(char*)dst + off, (const char*)src + off, std::min(kChunk, bytes - off)});
+}
+// Runs the queued chunks as one kernel. The chunk table travels through the pinned staging arena (recycled at begin_constraints / per flush).
+int flush_chunks(bepucuda_ctx* ctx, std::vector<CopyChunk>& list) {
+    if (list.empty()) return BEPUCUDA_OK;
+    const size_t bytes = list.size() * sizeof(CopyChunk);
+    CK(ctx->chunk_table.reserve(bytes));
+    auto& st = ctx->chunk_stage[ctx->chunk_stage_next];
+    ctx->chunk_stage_next = (ctx->chunk_stage_next + 1) & 3;
+    if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    CK(cudaEventSynchronize(st.done));  // its previous use (4 flushes ago) is long finished
+    if (st.capacity < bytes) {
+        if (st.host) cudaFreeHost(st.host);
+        st.host = nullptr;
+        st.capacity = 0;
+        CK(cudaMallocHost(&st.host, bytes * 2));
+        st.capacity = bytes * 2;
+    }
+    std::memcpy(st.host, list.data(), bytes);
+    // The device-side table is reused by every flush: stream order keeps the previous batched copy ahead of this overwrite.
+    CK(cudaMemcpyAsync(ctx->chunk_table.ptr, st.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    launch_batched_copy(ctx->chunk_table.as<CopyChunk>(), (int)list.size(), ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(st.done, ctx->stream));
+    list.clear();
+    return BEPUCUDA_OK;
+}
+
 // H2D copy of one host buffer into the raw arena. Small buffers are packed through pinned staging so that hundreds of
 // tiny type batches do not each pay a pageable-memory DMA setup; large ones go directly (fast when the host registered them).
 int copy_in(bepucuda_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes == 0) return BEPUCUDA_OK;
+    if (char* alias = map_host(ctx, src, bytes)) {
+        queue_chunks(ctx->pending_h2d, dst, alias, bytes);  // read straight from the mapped host buffer by the batched copy kernel at the next flush
+        ctx->h2d_accum += (int64_t)bytes;
+        return BEPUCUDA_OK;
+    }
     if (bytes < ((size_t)256 << 10)) {
         cudaError_t e = cudaSuccess;
         void* stage = ctx->pinned_arena.alloc(bytes, &e);
@@ -262,6 +313,10 @@ void build_program(bepucuda_ctx* ctx) {
             if (kin > 0) ctx->program.push_back({kStageKinematic, 0, kin, 0});
         } else if (ctx->integ.integrate_velocity_for_kinematics && kin > 0) {
             ctx->program.push_back({kStageKinematicFirst, 0, kin, 0});
+        }
+        if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
+            if (ctx->all_work_count > 0) ctx->program.push_back({kStageRegion, 0, ctx->all_work_count, (ctx->iterations[s] << 1) | (s == 0 ? 1 : 0)});
+            continue;
         }
         for (auto& bw : ctx->batch_work)
             if (bw.second > 0) ctx->program.push_back({s == 0 ? kStageWarmStartFirst : kStageWarmStart, bw.first, bw.second, 0});
@@ -361,7 +416,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
     DeviceBuffer* bufs[] = {&ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
-                            &ctx->sync_mask, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
+                            &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev};
     for (auto b : bufs) b->release();
     ctx->raw_arena.release();
@@ -369,6 +424,10 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->frame_params_host) cudaFreeHost(ctx->frame_params_host);
     for (auto ev : ctx->user_events)
         if (ev) cudaEventDestroy(ev);
+    for (auto& st : ctx->chunk_stage) {
+        if (st.host) cudaFreeHost(st.host);
+        if (st.done) cudaEventDestroy(st.done);
+    }
     for (auto ev : ctx->profile_events) cudaEventDestroy(ev);
     cudaEvent_t evs[] = {ctx->ev_solve_begin, ctx->ev_solve_end, ctx->ev_up_begin, ctx->ev_up_end, ctx->ev_down_begin, ctx->ev_down_end};
     for (auto ev : evs)
@@ -383,12 +442,19 @@ const char* bepucuda_last_error(bepucuda_ctx* ctx) { return ctx ? ctx->error.c_s
 int32_t bepucuda_host_register(bepucuda_ctx* ctx, void* ptr, int64_t bytes) {
     if (!ctx || !ptr || bytes <= 0) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "host_register: bad arguments");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    void* dev = nullptr;
+    CK(cudaHostGetDevicePointer(&dev, ptr, 0));
+    ctx->host_ranges.push_back({(char*)ptr, (size_t)bytes, (char*)dev});
     return BEPUCUDA_OK;
 }
 int32_t bepucuda_host_unregister(bepucuda_ctx* ctx, void* ptr) {
     if (!ctx || !ptr) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "host_unregister: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaHostUnregister(ptr));
+    for (size_t i = 0; i < ctx->host_ranges.size(); ++i)
+        if (ctx->host_ranges[i].host == (char*)ptr) { ctx->host_ranges.erase(ctx->host_ranges.begin() + i); break; }
     return BEPUCUDA_OK;
 }
 
@@ -457,6 +523,8 @@ int32_t bepucuda_upload_bodies(bepucuda_ctx* ctx, const void* body_dynamics, int
         CK(cudaMemcpyAsync(ctx->raw_bodies.ptr, body_dynamics, n * 128, cudaMemcpyHostToDevice, ctx->stream));
         ctx->h2d_accum += (int64_t)n * 128;
         launch_split_bodies(ctx->raw_bodies.ptr, body_count, ctx->B, ctx->stream);
+        ctx->pass_counter = 0;       // split_bodies zeroes the padding words = version 0 everywhere
+        ctx->versions_dirty = false;
         CK(cudaGetLastError());
     }
     return BEPUCUDA_OK;
@@ -658,6 +726,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
         impulse_floats += (size_t)ctx->tbs[i].bundle_count * t->impulse_rows * 32;
     }
     CK(ctx->refs32.reserve(refs_floats * 4 + 1024));  // slack: solver warps always read two body-reference rows
+    CK(ctx->chain32.reserve(refs_floats * 4 + 1024));
     CK(ctx->prestep32.reserve(prestep_floats * 4 + 4));
     CK(ctx->impulses32.reserve(impulse_floats * 4 + 4));
     CK(ctx->map_table.reserve(maps.size() * 4 + 4));
@@ -724,6 +793,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     if (!ctx->kinematics.empty()) CK(cudaMemcpyAsync(ctx->kinematics_dev.ptr, ctx->kinematics.data(), ctx->kinematics.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 
     // ---- transposition into AOSOA-32 + ownership analysis ----
+    { int rc = flush_chunks(ctx, ctx->pending_h2d); if (rc != BEPUCUDA_OK) return rc; }
     launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, W,
                             kTransposeRefs | kTransposePrestep | kTransposeImpulses, ctx->stream);
     const size_t nb = (size_t)std::max(ctx->body_count, 1);
@@ -741,12 +811,25 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
                      ctx->body_count, ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (unsigned long long*)ctx->sync_mask.ptr, ctx->constrained.as<uint8_t>(),
                      ctx->kinematics_dev.as<int32_t>(), (int)ctx->kinematics.size(), ctx->error_dev.as<int32_t>(), ctx->tdesc_table.as<TransposeDesc>(), W,
                      ctx->source_bundle_flags.as<int32_t>(), ctx->stream);
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
+        // rank of each constraint among its bodies' constraints: one small launch per device batch, in order
+        CK(ctx->body_counter.reserve(nb * 4));
+        CK(cudaMemsetAsync(ctx->body_counter.ptr, 0, nb * 4, ctx->stream));
+        const long long chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
+        for (auto& bw : ctx->batch_work)
+            launch_chain_rank(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>() + bw.first, bw.second, ctx->bodies_per_type.as<int32_t>(), chain_delta,
+                              ctx->body_counter.as<int32_t>(), ctx->stream);
+        launch_chain_degree(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), chain_delta,
+                            ctx->body_counter.as<int32_t>(), ctx->error_dev.as<int32_t>(), ctx->stream);
+        ctx->versions_dirty = true;
+    }
     CK(cudaGetLastError());
     int32_t err = 0;
     CK(cudaMemcpyAsync(&err, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // also guarantees the std::vector sources of the copies above were consumed
     if (err == 1) return fail(ctx, BEPUCUDA_ERR_BATCH_INVARIANT, "end_constraints: a synchronized batch references the same dynamic body more than once");
     if (err == 2) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "end_constraints: body reference out of range");
+    if (err == 3) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "end_constraints: a body has more than 65535 constraints (dataflow mode limit)");
 
     ctx->timings.constraint_count = constraint_count;
     ctx->timings.device_batch_count = (int)batch_tbs.size();
@@ -764,9 +847,16 @@ int32_t bepucuda_update_type_batch(bepucuda_ctx* ctx, int32_t batch_index, int32
     open_upload_window(ctx);
     for (auto& s : ctx->sources)
         if (s.batch_index == batch_index && s.type_batch_index == type_batch_index) {
-            // Direct copies only: the pinned staging arena is recycled per begin_constraints, not per frame.
-            CK(cudaMemcpyAsync(s.raw_prestep, prestep, s.prestep_bytes, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(s.raw_impulses, accumulated_impulses, s.impulse_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            char* alias_p = map_host(ctx, prestep, s.prestep_bytes);
+            char* alias_i = map_host(ctx, accumulated_impulses, s.impulse_bytes);
+            if (alias_p && alias_i) {
+                queue_chunks(ctx->pending_h2d, s.raw_prestep, alias_p, s.prestep_bytes);
+                queue_chunks(ctx->pending_h2d, s.raw_impulses, alias_i, s.impulse_bytes);
+            } else {
+                // Direct copies only: the pinned staging arena is recycled per begin_constraints, not per frame.
+                CK(cudaMemcpyAsync(s.raw_prestep, prestep, s.prestep_bytes, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(s.raw_impulses, accumulated_impulses, s.impulse_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            }
             ctx->h2d_accum += (int64_t)(s.prestep_bytes + s.impulse_bytes);
             s.host_impulses = accumulated_impulses;
             ctx->data_dirty = true;
@@ -787,6 +877,7 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
         if (rc != BEPUCUDA_OK) return rc;
     }
     if (ctx->data_dirty) {
+        { int rc = flush_chunks(ctx, ctx->pending_h2d); if (rc != BEPUCUDA_OK) return rc; }
         launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
                                 kTransposePrestep | kTransposeImpulses, ctx->stream);
         ctx->data_dirty = false;
@@ -801,6 +892,12 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     // frame parameters (previous frame's copy has completed by stream order only after its graph; wait for it before reusing the pinned struct)
     CK(cudaEventSynchronize(ctx->ev_solve_end));
     compute_frame_params(ctx, dt, ctx->frame_params_host);
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && ctx->versions_dirty) {
+        launch_reset_versions(ctx->velocity.as<float4>(), ctx->body_count, ctx->stream);
+        ctx->pass_counter = 0;
+        ctx->versions_dirty = false;
+    }
+    ctx->frame_params_host->pass_base = ctx->pass_counter;
     CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
 
     CK(cudaEventRecord(ctx->ev_solve_begin, ctx->stream));
@@ -811,6 +908,14 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
                                             ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->cfg.reserved[0], ctx->stream);
         if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "persistent kernel launch");
         launches = 1;
+    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
+        CK(cudaMemsetAsync(ctx->barrier_dev.ptr, 0, sizeof(unsigned int), ctx->stream));
+        const long long chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
+        int rc = ctx->launchers->dataflow(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->record_table.as<WorkRecord>(), chain_delta, ctx->kinematics_dev.as<int32_t>(),
+                                          ctx->B, ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->error_dev.as<int32_t>(), ctx->cfg.reserved[0], ctx->stream);
+        if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "dataflow kernel launch");
+        launches = 1;
+        for (int it : ctx->iterations) ctx->pass_counter += (uint32_t)it + 1u;
     } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_GRAPH) {
         if (!ctx->graph_valid) {
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -849,11 +954,20 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     return BEPUCUDA_OK;
 }
 
+static int check_device_error_flag(bepucuda_ctx* ctx) {
+    if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_DATAFLOW) return BEPUCUDA_OK;
+    int32_t err = 0;
+    CK(cudaMemcpyAsync(&err, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (err == 4) return fail(ctx, BEPUCUDA_ERR_CUDA, "dataflow solve: a body version dependency never arrived (spin limit hit); results are invalid");
+    return BEPUCUDA_OK;
+}
+
 int32_t bepucuda_synchronize(bepucuda_ctx* ctx) {
     if (!ctx) return BEPUCUDA_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    return BEPUCUDA_OK;
+    return check_device_error_flag(ctx);
 }
 
 int32_t bepucuda_download_bodies(bepucuda_ctx* ctx, void* out, int32_t body_count) {
@@ -878,10 +992,13 @@ int32_t bepucuda_download_impulses(bepucuda_ctx* ctx) {
                              kTransposeImpulses, ctx->stream);
     CK(cudaGetLastError());
     int64_t bytes = 0;
+    std::vector<CopyChunk> d2h;
     for (auto& s : ctx->sources) {
-        CK(cudaMemcpyAsync(s.host_impulses, s.raw_impulses, s.impulse_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (char* alias = map_host(ctx, s.host_impulses, s.impulse_bytes)) queue_chunks(d2h, alias, s.raw_impulses, s.impulse_bytes);
+        else CK(cudaMemcpyAsync(s.host_impulses, s.raw_impulses, s.impulse_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         bytes += (int64_t)s.impulse_bytes;
     }
+    { int rc = flush_chunks(ctx, d2h); if (rc != BEPUCUDA_OK) return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->timings.d2h_bytes += bytes;
     return BEPUCUDA_OK;
@@ -907,6 +1024,7 @@ int32_t bepucuda_get_timings(bepucuda_ctx* ctx, bepucuda_timings* out) {
     if (!ctx || !out) return BEPUCUDA_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    { int rc = check_device_error_flag(ctx); if (rc != BEPUCUDA_OK) return rc; }
     if (ctx->have_solve) cudaEventElapsedTime(&ctx->timings.solve_ms, ctx->ev_solve_begin, ctx->ev_solve_end);
     if (ctx->have_up && !ctx->up_open) cudaEventElapsedTime(&ctx->timings.upload_ms, ctx->ev_up_begin, ctx->ev_up_end);
     if (ctx->have_down) cudaEventElapsedTime(&ctx->timings.download_ms, ctx->ev_down_begin, ctx->ev_down_end);
@@ -932,6 +1050,7 @@ int32_t bepucuda_event_elapsed_ms(bepucuda_ctx* ctx, int32_t a, int32_t b, float
 int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_profile* out) {
     if (!ctx || !out || !(dt > 0)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "profile_stages: bad arguments");
     if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages before end_constraints");
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages: not available in dataflow mode (no per-stage launches)");
     CK(cudaSetDevice(ctx->device));
     std::memset(out, 0, sizeof(*out));
     if (ctx->data_dirty) {

@@ -21,7 +21,8 @@ namespace {
 
 constexpr uint32_t kKinematicMask = 1u << 30;  // Bodies_GatherScatter.cs:L109-110
 
-template <class T> struct AlignedBuffer {  // BufferPool hands out 128-B aligned blocks (BufferPool.cs:L42)
+template <class T> struct AlignedBuffer {  // BufferPool hands out 128-B aligned blocks carved from large pages (BufferPool.cs:L42); page-granular here so
+                                          // that every buffer can be page-locked on its own (cudaHostRegister pins whole pages)
     T* data = nullptr;
     size_t capacity = 0;
     ~AlignedBuffer() { std::free(data); }
@@ -29,8 +30,8 @@ template <class T> struct AlignedBuffer {  // BufferPool hands out 128-B aligned
         if (count <= capacity) return;
         size_t cap = std::max<size_t>(count, capacity * 2);
         cap = std::max<size_t>(cap, 64);
-        size_t bytes = ((cap * sizeof(T) + 127) / 128) * 128;
-        T* n = (T*)std::aligned_alloc(128, bytes);
+        size_t bytes = ((cap * sizeof(T) + 4095) / 4096) * 4096;
+        T* n = (T*)std::aligned_alloc(4096, bytes);
         if (!n) throw std::bad_alloc();
         std::memset(n, 0, bytes);
         if (data) std::memcpy(n, data, used * sizeof(T));

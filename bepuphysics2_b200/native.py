@@ -86,7 +86,7 @@ class StageProfile(C.Structure):
         return {n: {"ms": self.ms[i], "launches": self.launches[i], "algorithmic_bytes": self.algorithmic_bytes[i]} for i, n in enumerate(self.STAGE_NAMES) if self.launches[i]}
 
 
-EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM = 0, 1, 2
+EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW = 0, 1, 2, 3
 
 # Every symbol include/bepucuda.h declares (checked by the CPU test-suite).
 C_ABI_SYMBOLS = [

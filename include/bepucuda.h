@@ -45,7 +45,8 @@ typedef struct bepucuda_ctx bepucuda_ctx;
 enum bepucuda_execution_mode {
     BEPUCUDA_EXEC_GRAPH = 0,      /* one kernel per (batch, stage), whole frame captured in a CUDA graph */
     BEPUCUDA_EXEC_PERSISTENT = 1, /* one cooperative kernel per frame, grid barrier per (batch, stage) */
-    BEPUCUDA_EXEC_STREAM = 2      /* plain stream launches, no graph (debug / profiling with ncu) */
+    BEPUCUDA_EXEC_STREAM = 2,     /* plain stream launches, no graph (debug / profiling with ncu) */
+    BEPUCUDA_EXEC_DATAFLOW = 3    /* one cooperative kernel per frame; per-body version dependencies instead of a barrier per (batch, stage) */
 };
 
 typedef struct bepucuda_config {

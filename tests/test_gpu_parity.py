@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from bepuphysics2_b200 import scenes
-from bepuphysics2_b200.native import EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
+from bepuphysics2_b200.native import EXEC_DATAFLOW, EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -28,7 +28,7 @@ def test_box_stack_config1_bit_exact(libs):
     assert got["timings"]["device_batch_count"] == 2
 
 
-@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM])
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
 def test_box_stack_substepped_all_execution_modes(libs, mode):
     _parity(scenes.box_stacks(8, 12), mode=mode, substeps=4, velocity_iterations=2, frames=3)
 
@@ -103,3 +103,67 @@ def test_ragdolls_persistent_fast_within_tolerance(libs):
     """Fast build on joints: relative RMS error <= 1e-3, max abs error <= 2e-2 after one frame (measured ~3e-5 / 1e-3; the twist/servo angle
     measurements go through acos near 1, which amplifies rounding: see tools/fast_error_stats.py)."""
     _parity(scenes.ragdolls(60, seed=5), exact=False, mode=EXEC_PERSISTENT, rel_rms=1e-3, max_abs=2e-2, substeps=1, velocity_iterations=4)
+
+
+@pytest.mark.parametrize("scene_name", ["pile", "nonconvex", "ragdolls", "fallback", "mixed_bodies"])
+def test_dataflow_mode_bit_exact(libs, scene_name):
+    """Per-body version dependencies instead of a barrier per (batch, stage): same Gauss-Seidel order per body, so bit-identical results."""
+    if scene_name == "pile":
+        _parity(scenes.shape_pile(5000, seed=11), mode=EXEC_DATAFLOW, substeps=4, velocity_iterations=2, frames=3)
+    elif scene_name == "nonconvex":
+        _parity(scenes.shape_pile(2000, seed=7, nonconvex_fraction=0.5), mode=EXEC_DATAFLOW, substeps=3, velocity_iterations=[1, 2, 3], frames=2)
+    elif scene_name == "ragdolls":
+        _parity(scenes.ragdolls(60, seed=5), mode=EXEC_DATAFLOW, substeps=2, velocity_iterations=3, frames=3)
+    elif scene_name == "fallback":
+        _parity(scenes.fallback_stress(600, hubs=3, seed=5), mode=EXEC_DATAFLOW, fallback_batch_threshold=8, substeps=2, velocity_iterations=2, frames=2)
+    else:
+        scene = scenes.box_stacks(4, 4)
+        extra = scenes.make_bodies(np.array([[100, 5, 0], [120, 5, 0]], dtype=np.float32), linear=np.array([[1, 2, 3], [0, 0, 0]], dtype=np.float32),
+                                   angular=np.array([[0.5, 0.1, -0.3], [0, 1, 0]], dtype=np.float32), inverse_mass=np.array([1, 0], dtype=np.float32),
+                                   inverse_inertia=np.array([[2, 0, 2, 0, 0, 2], [0, 0, 0, 0, 0, 0]], dtype=np.float32))
+        scene["bodies"] = np.concatenate([scene["bodies"], extra])
+        scene["bodies"][0, 8:11] = (0.2, 0.0, 0.1)
+        integ = util.bp.IntegratorDesc.default()
+        integ.angular_integration_mode = 1
+        _parity(scene, mode=EXEC_DATAFLOW, substeps=3, velocity_iterations=2, integrator=integ, frames=2)
+
+
+def test_dataflow_device_resident_frames_keep_versions(libs):
+    """Several solves without re-uploading bodies: the version counters keep running across frames."""
+    import bepuphysics2_b200 as bp
+
+    scene = scenes.shape_pile(2000, seed=13)
+    a = util.make_sim(scene, substeps=2, velocity_iterations=2)
+    b = util.make_sim(scene, substeps=2, velocity_iterations=2)
+    ref = util.run_oracle(a, DT, frames=4)
+    ts = bp.CudaTimestepper(b, strict_fp=True, execution_mode=EXEC_DATAFLOW)
+    ts.describe()
+    for _ in range(3):
+        ts.solve_device_only(DT)
+    ts.solve(DT, download=True)
+    ts.download_prestep()
+    ts.close()
+    util.compare(ref, util.snapshot(b), exact=True)
+
+
+def test_registered_host_buffers_refresh_flow_bit_exact(libs):
+    """The per-frame flow of a host application: page-locked (registered) buffers, refresh (bodies + prestep + impulses re-uploaded through the batched
+    zero-copy kernel), solve, download into the same buffers. Several frames, strict build, against the oracle."""
+    import bepuphysics2_b200 as bp
+
+    scene = scenes.shape_pile(4000, seed=21)
+    a = util.make_sim(scene, substeps=3, velocity_iterations=2)
+    b = util.make_sim(scene, substeps=3, velocity_iterations=2)
+    ref = util.run_oracle(a, DT, frames=3)
+    ts = bp.CudaTimestepper(b, strict_fp=True)
+    ts.register_host_buffers()
+    ts.describe()
+    for f in range(3):
+        if f > 0:
+            ts.refresh()
+        ts.solve(DT, download=True)
+        ts.download_prestep()
+    t = ts.timings()
+    ts.close()
+    assert t.h2d_bytes > 0 and t.d2h_bytes > 0
+    util.compare(ref, util.snapshot(b), exact=True)

@@ -119,6 +119,7 @@ BEPU_DI void run_bundle_dataflow(const WorkRecord* __restrict__ record, int lane
     case ID: run_lane_dataflow<T, STAGE>(rec, lane, chain_delta, B, fp, pass_index, error_flag); break;
         BEPU_CONTACT_TYPES(BEPU_CASE)
         BEPU_JOINT_TYPES(BEPU_CASE)
+        BEPU_JOINT_TYPES_MORE(BEPU_CASE)
 #undef BEPU_CASE
         default: break;
     }

@@ -8,7 +8,7 @@
 // part of the access pattern and is written by other warps of the same launch sequence, so it never goes through L1.
 #pragma once
 #include "bepu_contacts.cuh"
-#include "bepu_joints.cuh"
+#include "bepu_joints_more.cuh"
 #include "bepu_device_types.h"
 
 namespace BEPU_NS {
@@ -238,6 +238,7 @@ BEPU_DI void run_bundle(const WorkRecord& rec, int lane, uint32_t enc0, uint32_t
     case ID: run_lane<T, STAGE>(refs, p, a, enc0, enc1, B, fp); break;
         BEPU_CONTACT_TYPES(BEPU_CASE)
         BEPU_JOINT_TYPES(BEPU_CASE)
+        BEPU_JOINT_TYPES_MORE(BEPU_CASE)
 #undef BEPU_CASE
         default: break;
     }

@@ -501,6 +501,140 @@ def ragdolls(count=10_000, seed=5, contacts_per_body=2.0, motor="motor", spacing
             "description": "%d ragdolls (%d bodies, %d joints) + kinematic tube, %d constraints total" % (count, total_dyn, 58 * count, total)}
 
 
+# (type id, bodies per constraint) of every joint / motor / servo / limit type of DefaultTypes.cs beyond the ragdoll set.
+JOINT_ZOO_TYPES = {23: 2, 24: 2, 28: 2, 31: 2, 32: 4, 33: 2, 34: 2, 35: 2, 36: 3, 37: 2, 38: 2, 39: 2, 40: 2, 41: 2, 42: 1, 43: 1, 44: 1, 45: 1, 52: 2, 53: 2, 54: 2, 55: 2}
+
+
+def joint_zoo(body_count=2000, per_type=200, seed=5, kinematic_fraction=0.05, types=None):
+    """Random bodies on a jittered grid, connected by `per_type` constraints of each type in JOINT_ZOO_TYPES (or `types`) with randomised
+    but physically sensible prestep data (Weld, AngularHinge, AngularSwivelHinge, TwistMotor, AngularAxisMotor, AngularAxisGearMotor,
+    BallSocketServo/Motor, DistanceServo/Limit, PointOnLineServo, LinearAxisServo/Motor/Limit, CenterDistance constraint/limit, the four
+    one-body servos/motors, AreaConstraint (3 bodies) and VolumeConstraint (4 bodies)). A fraction of the bodies is kinematic; no constraint
+    gets more than one kinematic body and one-body constraints only go on dynamic bodies."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = body_count
+    side = int(math.ceil(n ** (1.0 / 3.0)))
+    idx = np.arange(n)
+    pos = np.stack([idx % side, (idx // side) % side, idx // (side * side)], axis=1).astype(np.float32) * np.float32(1.5)
+    pos += rng.uniform(-0.3, 0.3, size=(n, 3)).astype(np.float32)
+    inv_inertia = _shape_inverse_inertias()[rng.integers(0, 5, size=n)]
+    inv_mass = rng.uniform(0.5, 2.0, size=n).astype(np.float32)
+    kinematic = rng.random(n) < kinematic_fraction
+    inv_mass[kinematic] = 0
+    inv_inertia[kinematic] = 0
+    bodies = make_bodies(pos, orientation=_random_unit_quaternions(rng, n), linear=rng.uniform(-0.5, 0.5, size=(n, 3)).astype(np.float32),
+                         angular=rng.uniform(-0.5, 0.5, size=(n, 3)).astype(np.float32), inverse_mass=inv_mass, inverse_inertia=inv_inertia)
+    dynamic = np.flatnonzero(~kinematic).astype(np.int32)
+    fmax = np.float32(np.finfo(np.float32).max)
+
+    def f32(x):
+        return np.asarray(x, dtype=np.float32)
+
+    def offsets(m):
+        return rng.uniform(-0.5, 0.5, size=(m, 3)).astype(np.float32)
+
+    def axes(m):
+        a = rng.standard_normal((m, 3)).astype(np.float32)
+        return (a / np.linalg.norm(a, axis=1, keepdims=True)).astype(np.float32)
+
+    def scalars(m, lo, hi):
+        return rng.uniform(lo, hi, size=(m, 1)).astype(np.float32)
+
+    def springs(m):
+        return np.concatenate([scalars(m, 5, 30) * TWO_PI, scalars(m, 0.3, 1.5) * np.float32(2)], axis=1).astype(np.float32)
+
+    def servos(m):  # MaximumSpeed, BaseSpeed, MaximumForce; a third of them unlimited like ServoSettings.Default
+        s = np.concatenate([scalars(m, 0.5, 5), scalars(m, 0, 0.5), scalars(m, 10, 1000)], axis=1)
+        unlimited = rng.random(m) < 0.33
+        s[unlimited] = (fmax, 0, fmax)
+        return s.astype(np.float32)
+
+    def motors(m):  # MaximumForce, Damping (MotorSettings softness)
+        s = np.concatenate([scalars(m, 10, 1000), scalars(m, 0.1, 100)], axis=1)
+        s[rng.random(m) < 0.33, 0] = fmax
+        return s.astype(np.float32)
+
+    def pick(m, count):
+        """`count` distinct nearby bodies per constraint (consecutive grid indices from a random start), at most one kinematic: the first is dynamic."""
+        first = dynamic[rng.integers(0, dynamic.shape[0], size=m)]
+        cols = [first]
+        for k in range(1, count):
+            cand = (first + k * (1 + rng.integers(0, 3, size=m))) % n
+            # replace kinematic partners of slots >= 2 (and duplicates) by the next dynamic body
+            for _ in range(8):
+                bad = np.zeros(m, dtype=bool)
+                for c in cols:
+                    bad |= cand == c
+                if k >= 2:
+                    bad |= kinematic[cand]
+                if not bad.any():
+                    break
+                cand = np.where(bad, (cand + 1) % n, cand)
+            cols.append(cand.astype(np.int32))
+        return np.stack(cols, axis=1).astype(np.int32)
+
+    constraints = []
+    chosen = JOINT_ZOO_TYPES if types is None else {t: JOINT_ZOO_TYPES[t] for t in types}
+    for type_id, nb in chosen.items():
+        m = per_type
+        h = pick(m, nb)
+        if nb >= 2:  # at most one kinematic body: slot 1 may be kinematic, slots 0 and >= 2 are dynamic
+            assert not kinematic[h[:, 0]].any() and not kinematic[h[:, 2:]].any()
+        p0 = pos[h[:, 0]]
+        if type_id in (23, 24):
+            pre = np.concatenate([axes(m), axes(m), springs(m)], axis=1)
+        elif type_id == 28:
+            pre = np.concatenate([axes(m), axes(m), scalars(m, -2, 2), motors(m)], axis=1)
+        elif type_id == 31:
+            pre = np.concatenate([offsets(m) * 2, _random_unit_quaternions(rng, m), springs(m)], axis=1)
+        elif type_id == 32:
+            ab, ac, ad = pos[h[:, 1]] - p0, pos[h[:, 2]] - p0, pos[h[:, 3]] - p0
+            volume = np.einsum("ij,ij->i", np.cross(ab, ac), ad)[:, None]
+            pre = np.concatenate([volume * scalars(m, 0.8, 1.2), springs(m)], axis=1)
+        elif type_id == 33:
+            pre = np.concatenate([offsets(m), offsets(m), scalars(m, 0.5, 3), servos(m), springs(m)], axis=1)
+        elif type_id == 34:
+            lo = scalars(m, 0.2, 1.5)
+            pre = np.concatenate([offsets(m), offsets(m), lo, lo + scalars(m, 0.5, 2), springs(m)], axis=1)
+        elif type_id == 35:
+            pre = np.concatenate([scalars(m, 0.5, 3), springs(m)], axis=1)
+        elif type_id == 36:
+            area = np.linalg.norm(np.cross(pos[h[:, 1]] - p0, pos[h[:, 2]] - p0), axis=1)[:, None]
+            pre = np.concatenate([area * scalars(m, 0.8, 1.2), springs(m)], axis=1)
+        elif type_id == 37:
+            pre = np.concatenate([offsets(m), offsets(m), axes(m), servos(m), springs(m)], axis=1)
+        elif type_id == 38:
+            pre = np.concatenate([offsets(m), offsets(m), axes(m), scalars(m, -1, 1), servos(m), springs(m)], axis=1)
+        elif type_id == 39:
+            pre = np.concatenate([offsets(m), offsets(m), axes(m), scalars(m, -2, 2), motors(m)], axis=1)
+        elif type_id == 40:
+            pre = np.concatenate([offsets(m), offsets(m), axes(m), scalars(m, -1.5, 0), scalars(m, 0, 1.5), springs(m)], axis=1)
+        elif type_id == 41:
+            pre = np.concatenate([axes(m), scalars(m, -2, 2), motors(m)], axis=1)
+        elif type_id == 42:
+            pre = np.concatenate([_random_unit_quaternions(rng, m), springs(m), servos(m)], axis=1)
+        elif type_id == 43:
+            pre = np.concatenate([offsets(m) * 4, motors(m)], axis=1)
+        elif type_id == 44:
+            pre = np.concatenate([offsets(m), p0 + offsets(m) * 2, springs(m), servos(m)], axis=1)
+        elif type_id == 45:
+            pre = np.concatenate([offsets(m), offsets(m) * 4, motors(m)], axis=1)
+        elif type_id == 52:
+            pre = np.concatenate([offsets(m), offsets(m) * 4, motors(m)], axis=1)
+        elif type_id == 53:
+            pre = np.concatenate([offsets(m), offsets(m), springs(m), servos(m)], axis=1)
+        elif type_id == 54:
+            pre = np.concatenate([axes(m), scalars(m, 0.5, 3), motors(m)], axis=1)
+        elif type_id == 55:
+            lo = scalars(m, 0.2, 1.5)
+            pre = np.concatenate([lo, lo + scalars(m, 0.5, 2), springs(m)], axis=1)
+        else:
+            raise ValueError("joint_zoo has no generator for type %d" % type_id)
+        constraints.append((type_id, h, np.ascontiguousarray(f32(pre))))
+    total = sum(c[1].shape[0] for c in constraints)
+    return {"bodies": bodies, "constraints": constraints, "description": "joint zoo: %d bodies, %d constraints of %d types" % (n, total, len(constraints))}
+
+
 def build(scene, simulation):
     """Adds a scene to a host Simulation (Bodies.Add, then Solver.Add per constraint in list order)."""
     simulation.add_bodies(scene["bodies"])

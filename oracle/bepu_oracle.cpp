@@ -14,6 +14,7 @@
 
 #include "bepu_contacts.h"
 #include "bepu_joints.h"
+#include "bepu_joints_more.h"
 
 namespace bepu_oracle {
 
@@ -61,6 +62,21 @@ template <class F, class T> struct AdaptJ1 {
     }
 };
 
+// three / four body constraints (AreaConstraint, VolumeConstraint) only touch positions, inverse masses and linear velocities
+template <class F, class T> struct AdaptJN {
+    static void ws(const BodyIn<F>* b, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) {
+        V3<F> pos[T::kBodies];
+        F im[T::kBodies];
+        for (int i = 0; i < T::kBodies; ++i) { pos[i] = b[i].pos; im[i] = b[i].inertia.inv_mass; }
+        T::warm_start(pos, im, p, a, v);
+    }
+    static void sv(const BodyIn<F>* b, float dt, float idt, const Rows<F>& p, const Rows<F>& a, Velocity<F>* v) {
+        V3<F> pos[T::kBodies];
+        F im[T::kBodies];
+        for (int i = 0; i < T::kBodies; ++i) { pos[i] = b[i].pos; im[i] = b[i].inertia.inv_mass; }
+        T::solve(pos, im, dt, idt, p, a, v);
+    }
+};
 template <class F> struct Registry {
     typedef F Lane;
     TypeOps<F> ops[64];
@@ -80,6 +96,10 @@ template <class F> struct Registry {
         ops[id].bodies = 1; ops[id].prestep_rows = T::kPrestepRows; ops[id].impulse_rows = T::kImpulseRows;
         ops[id].warm_start = &AdaptJ1<F, T>::ws; ops[id].solve = &AdaptJ1<F, T>::sv; ops[id].incremental = nullptr;
     }
+    template <class T> void jointN(int id) {
+        ops[id].bodies = T::kBodies; ops[id].prestep_rows = T::kPrestepRows; ops[id].impulse_rows = T::kImpulseRows;
+        ops[id].warm_start = &AdaptJN<F, T>::ws; ops[id].solve = &AdaptJN<F, T>::sv; ops[id].incremental = nullptr;
+    }
     Registry() {
         // BatchTypeId constants: Contact/ContactConvexTypes.cs, ContactNonconvexTypes.cs and each joint file.
         contact1<ConvexOneBody<F, 1>>(0); contact1<ConvexOneBody<F, 2>>(1); contact1<ConvexOneBody<F, 3>>(2); contact1<ConvexOneBody<F, 4>>(3);
@@ -87,6 +107,7 @@ template <class F> struct Registry {
         contact1<NonconvexOneBody<F, 2>>(8); contact1<NonconvexOneBody<F, 3>>(9); contact1<NonconvexOneBody<F, 4>>(10);
         contact2<NonconvexTwoBody<F, 2>>(15); contact2<NonconvexTwoBody<F, 3>>(16); contact2<NonconvexTwoBody<F, 4>>(17);
         register_joints(*this);
+        register_joints_more(*this);
     }
 };
 template <class F> static const Registry<F>& registry() {

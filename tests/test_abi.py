@@ -27,7 +27,11 @@ def test_type_registry_matches_oracle_and_reference_sizes(libs):
     # (bodies, prestep floats, impulse floats) from the reference's struct definitions
     expected = {0: (1, 11, 4), 1: (1, 15, 5), 2: (1, 19, 6), 3: (1, 23, 7), 4: (2, 14, 4), 5: (2, 18, 5), 6: (2, 22, 6), 7: (2, 26, 7),
                 8: (1, 18, 6), 9: (1, 25, 9), 10: (1, 32, 12), 15: (2, 21, 6), 16: (2, 28, 9), 17: (2, 35, 12),
-                22: (2, 8, 3), 25: (2, 9, 1), 26: (2, 14, 1), 27: (2, 12, 1), 29: (2, 9, 3), 30: (2, 5, 3), 46: (2, 14, 4), 47: (2, 14, 5)}
+                22: (2, 8, 3), 25: (2, 9, 1), 26: (2, 14, 1), 27: (2, 12, 1), 29: (2, 9, 3), 30: (2, 5, 3), 46: (2, 14, 4), 47: (2, 14, 5),
+                23: (2, 8, 2), 24: (2, 8, 1), 28: (2, 9, 1), 31: (2, 9, 6), 32: (4, 3, 1), 33: (2, 12, 1), 34: (2, 10, 1), 35: (2, 3, 1), 36: (3, 3, 1),
+                37: (2, 14, 2), 38: (2, 15, 1), 39: (2, 12, 1), 40: (2, 13, 1), 41: (2, 6, 1), 42: (1, 9, 3), 43: (1, 5, 3), 44: (1, 11, 3), 45: (1, 8, 3),
+                52: (2, 8, 3), 53: (2, 11, 3), 54: (2, 6, 1), 55: (2, 4, 1)}
+    assert sorted(t for t in range(64) if bp.type_info(t) is not None) == sorted(expected), "every registered type has a pinned layout"
     for type_id in range(64):
         ours, theirs = bp.type_info(type_id), ob.type_info(type_id)
         assert ours == theirs, "type %d: device registry %s vs oracle %s" % (type_id, ours, theirs)

@@ -167,3 +167,31 @@ def test_registered_host_buffers_refresh_flow_bit_exact(libs):
     ts.close()
     assert t.h2d_bytes > 0 and t.d2h_bytes > 0
     util.compare(ref, util.snapshot(b), exact=True)
+
+
+@pytest.mark.parametrize("type_id", sorted(scenes.JOINT_ZOO_TYPES))
+def test_each_remaining_joint_type_bit_exact(libs, type_id):
+    """One scene per constraint type of DefaultTypes.cs beyond the ragdoll set (1, 2, 3 and 4 body types), substepped, several frames so that
+    warm starting sees non-zero accumulated impulses."""
+    got = _parity(scenes.joint_zoo(300, 150, seed=20 + type_id, types=[type_id]), substeps=3, velocity_iterations=2, frames=3)
+    assert got["timings"]["constraint_count"] == 150
+
+
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
+def test_joint_zoo_all_types_together_all_execution_modes(libs, mode):
+    """All 22 remaining types in one scene (many batches, kinematic partners, 3- and 4-body constraints) in every execution mode."""
+    _parity(scenes.joint_zoo(1500, 120, seed=6), mode=mode, substeps=2, velocity_iterations=2, frames=2)
+
+
+def test_joint_zoo_with_fallback_batch_and_momentum_conserving_integration(libs):
+    """Low fallback threshold pushes multi-body joints into the sequential fallback batch; ConserveMomentum exercises the bundle-wide
+    first-substep quirk with 1-, 3- and 4-body bundles."""
+    integ = util.bp.IntegratorDesc.default()
+    integ.angular_integration_mode = 1
+    got = _parity(scenes.joint_zoo(250, 60, seed=9), fallback_batch_threshold=4, substeps=2, velocity_iterations=2, frames=2, integrator=integ)
+    assert got["timings"]["fallback_level_count"] > 0
+
+
+def test_joint_zoo_fast_build_within_tolerance(libs):
+    """Fast (FMA, approximate div/sqrt) build on the full zoo after one frame: relative RMS error <= 1e-3, max abs error <= 5e-2."""
+    _parity(scenes.joint_zoo(1500, 120, seed=6), exact=False, rel_rms=1e-3, max_abs=5e-2, substeps=2, velocity_iterations=2)

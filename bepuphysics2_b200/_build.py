@@ -45,20 +45,21 @@ def build(force=False, verbose=False, variant=None, defines=()):
     os.makedirs(BUILD, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "bepucuda.h"))
-    units = [
-        ("solver_fast.o", "bepu_solver_kernels.cu", ["-DBEPU_NS=bepu_fast", "-prec-div=false", "-prec-sqrt=false"]),
-        ("solver_strict.o", "bepu_solver_kernels.cu", ["-DBEPU_NS=bepu_strict", "-fmad=false"]),
-        ("layout.o", "bepu_layout_kernels.cu", []),
-        ("api.o", "bepucuda_api.cu", []),
-    ]
+    flavours = [("fast", ["-DBEPU_NS=bepu_fast", "-prec-div=false", "-prec-sqrt=false"]), ("strict", ["-DBEPU_NS=bepu_strict", "-fmad=false"])]
+    # (object, source, extra flags); the heaviest units (dataflow, persistent) first so the pool starts them early
+    units = [("solver_%s_%d.o" % (name, unit), "bepu_solver_kernels.cu", flags + ["-DBEPU_UNIT=%d" % unit]) for unit in (5, 4, 1, 0, 2, 3) for name, flags in flavours]
+    units += [("layout.o", "bepu_layout_kernels.cu", []), ("api.o", "bepucuda_api.cu", [])]
     jobs = []
     for obj, src, extra in units:
         o = os.path.join(BUILD, obj)
         s = os.path.join(CSRC, src)
+        frozen = os.path.exists(o) and any(obj.endswith("_%s.o" % u) for u in os.environ.get("BEPUCUDA_FREEZE_UNITS", "").split(",") if u)
+        if frozen:
+            continue  # development shortcut: keep a stale object of a unit that is not being worked on (never set for release builds)
         if force or _newer(o, [s] + headers):
             jobs.append([NVCC] + NVCC_FLAGS + extra + list(defines) + ["-c", s, "-o", o])
     if jobs:
-        with ThreadPoolExecutor(max_workers=4) as ex:
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as ex:
             for out in ex.map(_run, jobs):
                 if verbose and out.strip():
                     print(out)

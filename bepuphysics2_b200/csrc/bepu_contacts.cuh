@@ -13,13 +13,45 @@ namespace BEPU_NS {
 
 constexpr int kLanes = 32;
 
-// Prestep rows are read once per stage: load through L2 only (ld.global.cg). Also keeps the persistent kernel coherent
-// across grid barriers, where an L1 line filled before IncrementallyUpdateForSubstep rewrote a depth row would be stale.
-BEPU_DI float ldrow(const float* p, int r) { return __ldcg(p + r * kLanes); }
-BEPU_DI V3 ldrow3(const float* p, int r) { return {ldrow(p, r), ldrow(p, r + 1), ldrow(p, r + 2)}; }
-BEPU_DI Q4 ldrow4(const float* p, int r) { return {ldrow(p, r), ldrow(p, r + 1), ldrow(p, r + 2), ldrow(p, r + 3)}; }
-BEPU_DI float ldacc(const float* a, int r) { return a[r * kLanes]; }
-BEPU_DI void stacc(float* a, int r, float v) { a[r * kLanes] = v; }
+// Row accessors. A constraint function sees its prestep rows through `P` and its accumulated impulses through `A`:
+//   GlobalRows / GlobalAcc : straight from the AOSOA-32 arrays in HBM. Prestep rows are read once per stage: load through L2 only
+//                            (ld.global.cg), which also keeps the persistent kernel coherent across grid barriers, where an L1 line filled
+//                            before IncrementallyUpdateForSubstep rewrote a depth row would be stale.
+//   StagedRows / StagedAcc : the bundle's prestep + impulse block was bulk-copied (cp.async.bulk, one transaction per block) into this
+//                            warp's shared-memory slab; reads are conflict-free LDS (lane stride 4 B, row stride 128 B), impulse writes go
+//                            straight back to HBM.
+struct GlobalRows { const float* ptr; };
+struct GlobalAcc { float* ptr; };
+struct StagedRows { uint32_t addr, bar; };            // shared-space byte address of this lane's element of row 0; the (single-use) mbarrier the bulk copies complete on
+struct StagedAcc { uint32_t addr; float* ptr; };      // read staged copy, write global
+BEPU_DI float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// Blocks until the rows behind an accessor may be read: the staged block lands asynchronously (phase 0 of the slab's single-use mbarrier).
+BEPU_DI void rows_ready(GlobalRows) {}
+BEPU_DI void rows_ready(StagedRows p) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(p.bar)
+        : "memory");
+}
+BEPU_DI float ldrow(const float* p, int r) { return __ldcg(p + r * kLanes); }  // raw pointer form (IncrementallyUpdateForSubstep rewrites rows in place)
+BEPU_DI float ldrow(GlobalRows p, int r) { return __ldcg(p.ptr + r * kLanes); }
+BEPU_DI float ldrow(StagedRows p, int r) { return lds_f32(p.addr + r * (kLanes * 4)); }
+template <class PR> BEPU_DI V3 ldrow3(PR p, int r) { return {ldrow(p, r), ldrow(p, r + 1), ldrow(p, r + 2)}; }
+template <class PR> BEPU_DI Q4 ldrow4(PR p, int r) { return {ldrow(p, r), ldrow(p, r + 1), ldrow(p, r + 2), ldrow(p, r + 3)}; }
+BEPU_DI float ldacc(GlobalAcc a, int r) { return a.ptr[r * kLanes]; }
+BEPU_DI void stacc(GlobalAcc a, int r, float v) { a.ptr[r * kLanes] = v; }
+BEPU_DI float ldacc(StagedAcc a, int r) { return lds_f32(a.addr + r * (kLanes * 4)); }
+BEPU_DI void stacc(StagedAcc a, int r, float v) { __stcs(a.ptr + r * kLanes, v); }  // streaming store: read again only after the whole set went by
 
 // ---- two-body penetration limit: PenetrationLimit.cs ----
 BEPU_DI void penetration_apply(const Inertia& iA, const Inertia& iB, V3 normal, V3 angularA, V3 angularB, float impulse, Velocity& vA, Velocity& vB) {  // L45-65
@@ -208,7 +240,7 @@ template <int N> struct ConvexTwoBody {
     static constexpr bool kIncremental = true;
     static constexpr bool kNeedsPose = false;
 
-    BEPU_DI static void warm_start(const Inertia& iA, const Inertia& iB, const float* p, const float* a, Velocity& vA, Velocity& vB) {  // e.g. L1473-1486
+    template <class PR, class AR> BEPU_DI static void warm_start(const Inertia& iA, const Inertia& iB, PR p, AR a, Velocity& vA, Velocity& vB) {  // e.g. L1473-1486
         V3 normal = ldrow3(p, L::kNormal), offsetB = ldrow3(p, L::kOffsetB);
         V3 x, z;
         build_orthonormal_basis(normal, x, z);
@@ -224,7 +256,7 @@ template <int N> struct ConvexTwoBody {
         for (int i = 0; i < N; ++i) penetration_warm_start(iA, iB, normal, offs[i], offs[i] - offsetB, ldacc(a, 2 + i), vA, vB);
         twist_apply(normal, iA, iB, ldacc(a, N + 2), vA, vB);
     }
-    BEPU_DI static void solve(const Inertia& iA, const Inertia& iB, float dt, float inverseDt, const float* p, float* a, Velocity& vA, Velocity& vB) {  // e.g. L1488-1513
+    template <class PR, class AR> BEPU_DI static void solve(const Inertia& iA, const Inertia& iB, float dt, float inverseDt, PR p, AR a, Velocity& vA, Velocity& vB) {  // e.g. L1488-1513
         V3 normal = ldrow3(p, L::kNormal), offsetB = ldrow3(p, L::kOffsetB);
         float friction = ldrow(p, L::kFriction), maxRecovery = ldrow(p, L::kMaxRecovery);
         Springiness sp = compute_springiness(ldrow(p, L::kAngularFrequency), ldrow(p, L::kTwiceDampingRatio), dt);
@@ -276,7 +308,7 @@ template <int N> struct ConvexOneBody {
     static constexpr bool kIncremental = true;
     static constexpr bool kNeedsPose = false;
 
-    BEPU_DI static void warm_start(const Inertia& iA, const float* p, const float* a, Velocity& vA) {  // e.g. L303-309
+    template <class PR, class AR> BEPU_DI static void warm_start(const Inertia& iA, PR p, AR a, Velocity& vA) {  // e.g. L303-309
         V3 normal = ldrow3(p, L::kNormal);
         V3 x, z;
         build_orthonormal_basis(normal, x, z);
@@ -291,7 +323,7 @@ template <int N> struct ConvexOneBody {
         for (int i = 0; i < N; ++i) penetration1_apply(iA, normal, cross(offs[i], normal), ldacc(a, 2 + i), vA);
         twist1_apply(normal, iA, ldacc(a, N + 2), vA);
     }
-    BEPU_DI static void solve(const Inertia& iA, float dt, float inverseDt, const float* p, float* a, Velocity& vA) {  // e.g. L311-328
+    template <class PR, class AR> BEPU_DI static void solve(const Inertia& iA, float dt, float inverseDt, PR p, AR a, Velocity& vA) {  // e.g. L311-328
         V3 normal = ldrow3(p, L::kNormal);
         float friction = ldrow(p, L::kFriction), maxRecovery = ldrow(p, L::kMaxRecovery);
         Springiness sp = compute_springiness(ldrow(p, L::kAngularFrequency), ldrow(p, L::kTwiceDampingRatio), dt);
@@ -349,7 +381,7 @@ template <int N> struct NonconvexTwoBody {
     static constexpr int kImpulseRows = L::kImpulseRows;
     static constexpr bool kIncremental = true;
     static constexpr bool kNeedsPose = false;
-    BEPU_DI static void warm_start(const Inertia& iA, const Inertia& iB, const float* p, const float* a, Velocity& vA, Velocity& vB) {  // L246-261
+    template <class PR, class AR> BEPU_DI static void warm_start(const Inertia& iA, const Inertia& iB, PR p, AR a, Velocity& vA, Velocity& vB) {  // L246-261
         V3 offsetB = ldrow3(p, L::kOffsetB);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -362,7 +394,7 @@ template <int N> struct NonconvexTwoBody {
             penetration_warm_start(iA, iB, normal, offset, contactOffsetB, ldacc(a, 3 * i + 2), vA, vB);
         }
     }
-    BEPU_DI static void solve(const Inertia& iA, const Inertia& iB, float dt, float inverseDt, const float* p, float* a, Velocity& vA, Velocity& vB) {  // L263-283
+    template <class PR, class AR> BEPU_DI static void solve(const Inertia& iA, const Inertia& iB, float dt, float inverseDt, PR p, AR a, Velocity& vA, Velocity& vB) {  // L263-283
         V3 offsetB = ldrow3(p, L::kOffsetB);
         float friction = ldrow(p, 0), maxRecovery = ldrow(p, 3);
         Springiness sp = compute_springiness(ldrow(p, 1), ldrow(p, 2), dt);
@@ -399,7 +431,7 @@ template <int N> struct NonconvexOneBody {
     static constexpr int kImpulseRows = L::kImpulseRows;
     static constexpr bool kIncremental = true;
     static constexpr bool kNeedsPose = false;
-    BEPU_DI static void warm_start(const Inertia& iA, const float* p, const float* a, Velocity& vA) {  // L186-199
+    template <class PR, class AR> BEPU_DI static void warm_start(const Inertia& iA, PR p, AR a, Velocity& vA) {  // L186-199
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int c = L::kContacts + 7 * i;
@@ -410,7 +442,7 @@ template <int N> struct NonconvexOneBody {
             penetration1_apply(iA, normal, cross(offset, normal), ldacc(a, 3 * i + 2), vA);
         }
     }
-    BEPU_DI static void solve(const Inertia& iA, float dt, float inverseDt, const float* p, float* a, Velocity& vA) {  // L201-219
+    template <class PR, class AR> BEPU_DI static void solve(const Inertia& iA, float dt, float inverseDt, PR p, AR a, Velocity& vA) {  // L201-219
         float friction = ldrow(p, 0), maxRecovery = ldrow(p, 3);
         Springiness sp = compute_springiness(ldrow(p, 1), ldrow(p, 2), dt);
 #pragma unroll

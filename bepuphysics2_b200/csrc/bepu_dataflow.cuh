@@ -34,8 +34,8 @@ template <class T, int STAGE>
 __device__ __noinline__ void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_delta, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, int32_t* error_flag) {
     constexpr int NB = T::kBodies;
     const int32_t* refs = rec.refs + lane;
-    float* p = rec.prestep + lane;
-    float* a = rec.impulses + lane;
+    const GlobalRows p{rec.prestep + lane};
+    const GlobalAcc a{rec.impulses + lane};
     uint32_t enc[NB], expect[NB];
     bool dynamic[NB], ready[NB];
 #pragma unroll
@@ -125,7 +125,7 @@ BEPU_DI void run_bundle_dataflow(const WorkRecord* __restrict__ record, int lane
     }
 }
 
-__global__ void __launch_bounds__(kPersistentThreads, 2)
+static __global__ void __launch_bounds__(kPersistentThreads, 2)
 dataflow_solve_kernel(const StageOp* __restrict__ program, int op_count, const WorkRecord* __restrict__ records, long long chain_delta, const int32_t* __restrict__ kinematics,
                       BodyBuffers B, const FrameParams* __restrict__ fpp, unsigned int* barrier_counter, int32_t* error_flag) {
     const FrameParams fp = *fpp;

@@ -68,11 +68,11 @@ BEPU_DI void ball_socket_apply(Velocity& vA, Velocity& vB, V3 offsetA, V3 offset
 struct BallSocket {
     static constexpr int kBodies = 2, kPrestepRows = 8, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 offsetA = transform(ldrow3(p, 0), b[0].q), offsetB = transform(ldrow3(p, 3), b[1].q);
         ball_socket_apply(v[0], v[1], offsetA, offsetB, b[0].inertia, b[1].inertia, V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 offsetA = transform(ldrow3(p, 0), b[0].q), offsetB = transform(ldrow3(p, 3), b[1].q);
         Springiness sp = compute_springiness(ldrow(p, 6), ldrow(p, 7), dt);
         // ComputeEffectiveMass, BallSocketShared.cs:L10-26
@@ -102,19 +102,19 @@ struct BallSocket {
 struct SwingLimit {
     static constexpr int kBodies = 2, kPrestepRows = 9, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static V3 jacobian(const float* p, Q4 qA, Q4 qB, V3& axisA, V3& axisB) {
+    template <class PR> BEPU_DI static V3 jacobian(PR p, Q4 qA, Q4 qB, V3& axisA, V3& axisB) {
         axisA = transform(ldrow3(p, 0), qA);
         axisB = transform(ldrow3(p, 3), qB);
         V3 j = cross(axisA, axisB);
         V3 fallback = find_perpendicular(axisA);
         return dot(j, j) < 1e-7f ? fallback : j;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 axisA, axisB;
         V3 j = jacobian(p, b[0].q, b[1].q, axisA, axisB);
         angular1_apply(transform(j, b[0].inertia.t), transform(j, b[1].inertia.t), ldacc(a, 0), v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         V3 axisA, axisB;
         V3 j = jacobian(p, b[0].q, b[1].q, axisA, axisB);
         V3 i2vA = transform(j, b[0].inertia.t), ni2vB = transform(j, b[1].inertia.t);
@@ -189,7 +189,7 @@ BEPU_DI TwistEffectiveMass twist_effective_mass(float dt, float angularFrequency
 struct TwistLimit {
     static constexpr int kBodies = 2, kPrestepRows = 12, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static V3 jacobian(const float* p, Q4 qA, Q4 qB, float& error) {
+    template <class PR> BEPU_DI static V3 jacobian(PR p, Q4 qA, Q4 qB, float& error) {
         V3 basisBX, basisBZ;
         M33 basisA;
         V3 j = twist_jacobian_full(qA, qB, ldrow4(p, 0), ldrow4(p, 4), basisBX, basisBZ, basisA);
@@ -200,12 +200,12 @@ struct TwistLimit {
         error = useMin ? -minError : maxError;
         return useMin ? -j : j;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         float error;
         V3 j = jacobian(p, b[0].q, b[1].q, error);
         angular1_apply(transform(j, b[0].inertia.t), transform(j, b[1].inertia.t), ldacc(a, 0), v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         float error;
         V3 j = jacobian(p, b[0].q, b[1].q, error);
         TwistEffectiveMass m = twist_effective_mass(dt, ldrow(p, 10), ldrow(p, 11), b[0].inertia.t, b[1].inertia.t, j);
@@ -225,11 +225,11 @@ struct TwistLimit {
 struct TwistServo {
     static constexpr int kBodies = 2, kPrestepRows = 14, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 j = twist_jacobian_only(b[0].q, b[1].q, ldrow4(p, 0), ldrow4(p, 4));
         angular1_apply(transform(j, b[0].inertia.t), transform(j, b[1].inertia.t), ldacc(a, 0), v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         V3 basisBX, basisBZ;
         M33 basisA;
         V3 j = twist_jacobian_full(b[0].q, b[1].q, ldrow4(p, 0), ldrow4(p, 4), basisBX, basisBZ, basisA);
@@ -255,10 +255,10 @@ struct TwistServo {
 struct AngularMotor {
     static constexpr int kBodies = 2, kPrestepRows = 5, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float*, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR, AR a, Velocity* v) {
         angular3_apply(v[0].ang, v[1].ang, b[0].inertia.t, b[1].inertia.t, V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         MotorSoftness ms = motor_softness(ldrow(p, 3), ldrow(p, 4), dt);
         Sym3 unsoftenedEffectiveMass = invert(b[0].inertia.t + b[1].inertia.t);
         V3 biasVelocity = transform(ldrow3(p, 0), b[0].q);
@@ -277,10 +277,10 @@ struct AngularMotor {
 struct AngularServo {
     static constexpr int kBodies = 2, kPrestepRows = 9, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float*, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR, AR a, Velocity* v) {
         angular3_apply(v[0].ang, v[1].ang, b[0].inertia.t, b[1].inertia.t, V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         Q4 targetOrientationB = concatenate(ldrow4(p, 0), b[0].q);
         Q4 errorRotation = concatenate(conjugate(targetOrientationB), b[1].q);
         V3 errorAxis;
@@ -346,7 +346,7 @@ struct Hinge {
         vB.lin = vB.lin - ballSocket * iB.inv_mass;
         vB.ang = vB.ang + transform(cross(ballSocket, offsetB) - hingeAngularImpulseA, iB.t);
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         M33 mA = matrix_from_quaternion(b[0].q);
         V3 offsetA = transform(ldrow3(p, 0), mA);
         V3 offsetB = transform(ldrow3(p, 6), b[1].q);
@@ -355,7 +355,7 @@ struct Hinge {
         M23 hingeJacobian{transform(localAX, mA), transform(localAY, mA)};
         apply(offsetA, offsetB, hingeJacobian, b[0].inertia, b[1].inertia, V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)}, V2{ldacc(a, 3), ldacc(a, 4)}, v[0], v[1]);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         const Inertia& iA = b[0].inertia;
         const Inertia& iB = b[1].inertia;
         M33 mA = matrix_from_quaternion(b[0].q), mB = matrix_from_quaternion(b[1].q);
@@ -441,7 +441,7 @@ struct SwivelHinge {
         vB.lin = vB.lin - ballSocketCSI * iB.inv_mass;
         vB.ang = vB.ang + transform(cross(ballSocketCSI, offsetB) - swivelHingeAngularImpulseA, iB.t);
     }
-    BEPU_DI static V3 jacobian(const float* p, Q4 qA, Q4 qB, V3& swivelAxis, V3& hingeAxis, V3& offsetA, V3& offsetB) {  // L86-101
+    template <class PR> BEPU_DI static V3 jacobian(PR p, Q4 qA, Q4 qB, V3& swivelAxis, V3& hingeAxis, V3& offsetA, V3& offsetB) {  // L86-101
         M33 mA = matrix_from_quaternion(qA), mB = matrix_from_quaternion(qB);
         offsetA = transform(ldrow3(p, 0), mA);
         swivelAxis = transform(ldrow3(p, 3), mA);
@@ -450,12 +450,12 @@ struct SwivelHinge {
         V3 j = cross(swivelAxis, hingeAxis);
         return length_squared(j) < 1e-3f ? hingeAxis : j;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 swivelAxis, hingeAxis, offsetA, offsetB;
         V3 j = jacobian(p, b[0].q, b[1].q, swivelAxis, hingeAxis, offsetA, offsetB);
         apply(offsetA, offsetB, j, b[0].inertia, b[1].inertia, V4{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2), ldacc(a, 3)}, v[0], v[1]);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         const Inertia& iA = b[0].inertia;
         const Inertia& iB = b[1].inertia;
         V3 swivelAxis, hingeAxis, offsetA, offsetB;

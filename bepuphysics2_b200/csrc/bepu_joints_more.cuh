@@ -117,11 +117,11 @@ struct Weld {
         vB.lin = vB.lin - offsetCSI * iB.inv_mass;
         vB.ang = vB.ang - transform(orientationCSI, iB.t);
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 offset = transform(ldrow3(p, 0), b[0].q);
         apply(b[0].inertia, b[1].inertia, offset, V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)}, V3{ldacc(a, 3), ldacc(a, 4), ldacc(a, 5)}, v[0], v[1]);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         const Inertia& iA = b[0].inertia;
         const Inertia& iB = b[1].inertia;
         V3 offset = transform(ldrow3(p, 0), b[0].q);
@@ -184,12 +184,12 @@ struct AngularHinge {
         hingeAxisA = transform(localHingeAxisA, mA);
         return M23{transform(localAX, mA), transform(localAY, mA)};
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 hingeAxisA;
         M23 jacobianA = jacobians(ldrow3(p, 0), b[0].q, hingeAxisA);
         apply(multiply(jacobianA, b[0].inertia.t), multiply(jacobianA, b[1].inertia.t), V2{ldacc(a, 0), ldacc(a, 1)}, v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 hingeAxisA;
         M23 jacobianA = jacobians(ldrow3(p, 0), b[0].q, hingeAxisA);
         V3 hingeAxisB = transform(ldrow3(p, 3), b[1].q);
@@ -219,19 +219,19 @@ struct AngularHinge {
 struct AngularSwivelHinge {
     static constexpr int kBodies = 2, kPrestepRows = 8, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static V3 jacobian(const float* p, Q4 qA, Q4 qB, V3& swivelAxis, V3& hingeAxis) {  // L82-94
+    template <class PR> BEPU_DI static V3 jacobian(PR p, Q4 qA, Q4 qB, V3& swivelAxis, V3& hingeAxis) {  // L82-94
         swivelAxis = transform(ldrow3(p, 0), qA);
         hingeAxis = transform(ldrow3(p, 3), qB);
         V3 j = cross(swivelAxis, hingeAxis);
         V3 fallbackJacobian = find_perpendicular(swivelAxis);
         return dot(j, j) < 1e-3f ? fallbackJacobian : j;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 swivelAxis, hingeAxis;
         V3 j = jacobian(p, b[0].q, b[1].q, swivelAxis, hingeAxis);
         angular1_apply(transform(j, b[0].inertia.t), transform(j, b[1].inertia.t), ldacc(a, 0), v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 swivelAxis, hingeAxis;
         V3 j = jacobian(p, b[0].q, b[1].q, swivelAxis, hingeAxis);
         V3 i2vA = transform(j, b[0].inertia.t), ni2vB = transform(j, b[1].inertia.t);
@@ -261,11 +261,11 @@ struct TwistMotor {
         j = j * (1.0f / len);
         return len < 1e-10f ? axisA : j;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 j = jacobian(b[0].q, b[1].q, ldrow3(p, 0), ldrow3(p, 3));
         angular1_apply(transform(j, b[0].inertia.t), transform(j, b[1].inertia.t), ldacc(a, 0), v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 j = jacobian(b[0].q, b[1].q, ldrow3(p, 0), ldrow3(p, 3));
         V3 i2vA = transform(j, b[0].inertia.t), ni2vB = transform(j, b[1].inertia.t);  // TwistServo.cs:L133-144
         float unsoftenedInverseEffectiveMass = dot(i2vA, j) + dot(ni2vB, j);
@@ -289,11 +289,11 @@ struct TwistMotor {
 struct AngularAxisMotor {
     static constexpr int kBodies = 2, kPrestepRows = 6, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 axis = transform(ldrow3(p, 0), b[0].q);
         angular1_apply(transform(axis, b[0].inertia.t), transform(axis, b[1].inertia.t), ldacc(a, 0), v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 jA = transform(ldrow3(p, 0), b[0].q);
         V3 jIA = transform(jA, b[0].inertia.t);
         float contributionA = dot(jA, jIA);
@@ -314,12 +314,12 @@ struct AngularAxisMotor {
 struct AngularAxisGearMotor {
     static constexpr int kBodies = 2, kPrestepRows = 6, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 axis = transform(ldrow3(p, 0), b[0].q);
         V3 jA = axis * ldrow(p, 3);
         angular1_apply(transform(jA, b[0].inertia.t), transform(axis, b[1].inertia.t), ldacc(a, 0), v[0].ang, v[1].ang);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 axis = transform(ldrow3(p, 0), b[0].q);
         V3 jA = axis * ldrow(p, 3);
         V3 i2vA = transform(jA, b[0].inertia.t);
@@ -361,11 +361,11 @@ BEPU_DI void ball_socket_solve_clamped(Velocity& vA, Velocity& vB, V3 offsetA, V
 struct BallSocketMotor {
     static constexpr int kBodies = 2, kPrestepRows = 8, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 targetOffsetB = transform(ldrow3(p, 0), b[1].q);
         ball_socket_apply(v[0], v[1], (b[1].pos - b[0].pos) + targetOffsetB, targetOffsetB, b[0].inertia, b[1].inertia, V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 targetOffsetB = transform(ldrow3(p, 0), b[1].q);
         V3 offsetA = (b[1].pos - b[0].pos) + targetOffsetB;
         MotorSoftness m = motor_softness(ldrow(p, 6), ldrow(p, 7), dt);
@@ -380,11 +380,11 @@ struct BallSocketMotor {
 struct BallSocketServo {
     static constexpr int kBodies = 2, kPrestepRows = 11, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         V3 offsetA = transform(ldrow3(p, 0), b[0].q), offsetB = transform(ldrow3(p, 3), b[1].q);
         ball_socket_apply(v[0], v[1], offsetA, offsetB, b[0].inertia, b[1].inertia, V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         V3 offsetA = transform(ldrow3(p, 0), b[0].q), offsetB = transform(ldrow3(p, 3), b[1].q);
         Springiness sp = compute_springiness(ldrow(p, 6), ldrow(p, 7), dt);
         Sym3 effectiveMass = ball_socket_effective_mass(b[0].inertia, b[1].inertia, offsetA, offsetB, sp.effective_mass_cfm_scale);
@@ -403,7 +403,7 @@ struct DistanceServo {
     static constexpr int kBodies = 2, kPrestepRows = 12, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
     struct Frame { V3 anchorOffsetA, anchorOffsetB, direction, angularJA, angularJB; float distance; };
-    BEPU_DI static Frame frame(const BodyState* b, const float* p) {  // GetDistance L109-117 + ComputeJacobian L119-130
+    template <class PR> BEPU_DI static Frame frame(const BodyState* b, PR p) {  // GetDistance L109-117 + ComputeJacobian L119-130
         Frame f;
         f.anchorOffsetA = transform(ldrow3(p, 0), b[0].q);
         f.anchorOffsetB = transform(ldrow3(p, 3), b[1].q);
@@ -422,11 +422,11 @@ struct DistanceServo {
         vB.lin = vB.lin - direction * (csi * imB);
         vB.ang = ai2vB * csi + vB.ang;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         Frame f = frame(b, p);
         apply(b[0].inertia.inv_mass, b[1].inertia.inv_mass, f.direction, transform(f.angularJA, b[0].inertia.t), transform(f.angularJB, b[1].inertia.t), ldacc(a, 0), v[0], v[1]);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         Frame f = frame(b, p);
         V3 ai2vA = transform(f.angularJA, b[0].inertia.t), ai2vB = transform(f.angularJB, b[1].inertia.t);  // ComputeTransforms L132-158
         float angularContributionA = dot(f.angularJA, ai2vA), angularContributionB = dot(f.angularJB, ai2vB);
@@ -452,7 +452,7 @@ struct DistanceLimit {
     static constexpr int kBodies = 2, kPrestepRows = 10, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
     struct Frame { V3 direction, angularJA, angularJB; float distance; bool useMinimum; };
-    BEPU_DI static Frame frame(const BodyState* b, const float* p) {  // L116-139
+    template <class PR> BEPU_DI static Frame frame(const BodyState* b, PR p) {  // L116-139
         Frame f;
         V3 offsetA = transform(ldrow3(p, 0), b[0].q), offsetB = transform(ldrow3(p, 3), b[1].q);
         V3 anchorOffset = (offsetB - offsetA) + (b[1].pos - b[0].pos);
@@ -472,11 +472,11 @@ struct DistanceLimit {
         vA.ang = vA.ang + transform(angularJA * csi, iA.t);
         vB.ang = vB.ang + transform(angularJB * csi, iB.t);
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         Frame f = frame(b, p);
         apply(f.direction, f.angularJA, f.angularJB, b[0].inertia, b[1].inertia, ldacc(a, 0), v[0], v[1]);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         Frame f = frame(b, p);
         float linearCSVA = dot(v[0].lin, f.direction), negatedLinearCSVB = dot(v[1].lin, f.direction);
         float angularCSVA = dot(v[0].ang, f.angularJA), angularCSVB = dot(v[1].ang, f.angularJB);
@@ -512,7 +512,7 @@ struct PointOnLineServo {
         vB.lin = vB.lin - negatedLinearChangeB;
         vB.ang = angularChangeB + vB.ang;
     }
-    BEPU_DI static Frame frame(const BodyState* b, const float* p) {  // L103-126
+    template <class PR> BEPU_DI static Frame frame(const BodyState* b, PR p) {  // L103-126
         Frame f;
         V3 localDirection = ldrow3(p, 6);
         V3 localTangentX, localTangentY;
@@ -533,11 +533,11 @@ struct PointOnLineServo {
         f.angularJB.y = cross(f.linearJacobian.y, offsetB);
         return f;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         Frame f = frame(b, p);
         apply(v[0], v[1], f, b[0].inertia, b[1].inertia, V2{ldacc(a, 0), ldacc(a, 1)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         Frame f = frame(b, p);
         Sym2 linearContribution = sandwich_scale(f.linearJacobian, b[0].inertia.inv_mass + b[1].inertia.inv_mass);
         Sym2 inverseEffectiveMass = matrix_sandwich(f.angularJA, b[0].inertia.t) + matrix_sandwich(f.angularJB, b[1].inertia.t);
@@ -570,7 +570,7 @@ BEPU_DI void linear_axis_apply(V3 linearJA, V3 ai2vA, V3 ai2vB, const Inertia& i
     vA.ang = vA.ang + ai2vA * csi;
     vB.ang = vB.ang + ai2vB * csi;
 }
-BEPU_DI LinearAxisFrame linear_axis_frame(const BodyState* b, const float* p) {  // LinearAxisServo.cs:L182-197
+template <class PR> BEPU_DI LinearAxisFrame linear_axis_frame(const BodyState* b, PR p) {  // LinearAxisServo.cs:L182-197
     LinearAxisFrame f;
     M33 mA = matrix_from_quaternion(b[0].q);
     f.normal = transform(ldrow3(p, 6), mA);
@@ -590,15 +590,15 @@ BEPU_DI float linear_axis_effective_mass(const LinearAxisFrame& f, const Inertia
     return cfm / (iA.inv_mass + iB.inv_mass + angularContributionA + angularContributionB);
 }
 BEPU_DI float linear_axis_csv(const Velocity* v, const LinearAxisFrame& f) { return dot(v[0].lin - v[1].lin, f.normal) + dot(v[0].ang, f.angularJA) + dot(v[1].ang, f.angularJB); }
-BEPU_DI void linear_axis_warm_start(const LinearAxisFrame& f, const BodyState* b, const float* a, Velocity* v) {
+template <class AR> BEPU_DI void linear_axis_warm_start(const LinearAxisFrame& f, const BodyState* b, AR a, Velocity* v) {
     linear_axis_apply(f.normal, transform(f.angularJA, b[0].inertia.t), transform(f.angularJB, b[1].inertia.t), b[0].inertia, b[1].inertia, ldacc(a, 0), v[0], v[1]);
 }
 // prestep: LocalOffsetA xyz, LocalOffsetB xyz, LocalPlaneNormal xyz, TargetOffset, MaximumSpeed, BaseSpeed, MaximumForce, AngularFrequency, TwiceDampingRatio | impulse: 1
 struct LinearAxisServo {
     static constexpr int kBodies = 2, kPrestepRows = 15, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) { linear_axis_warm_start(linear_axis_frame(b, p), b, a, v); }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) { linear_axis_warm_start(linear_axis_frame(b, p), b, a, v); }
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         LinearAxisFrame f = linear_axis_frame(b, p);
         Springiness sp = compute_springiness(ldrow(p, 13), ldrow(p, 14), dt);
         V3 ai2vA, ai2vB;
@@ -617,8 +617,8 @@ struct LinearAxisServo {
 struct LinearAxisMotor {
     static constexpr int kBodies = 2, kPrestepRows = 12, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) { linear_axis_warm_start(linear_axis_frame(b, p), b, a, v); }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) { linear_axis_warm_start(linear_axis_frame(b, p), b, a, v); }
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         LinearAxisFrame f = linear_axis_frame(b, p);
         MotorSoftness m = motor_softness(ldrow(p, 10), ldrow(p, 11), dt);
         V3 ai2vA, ai2vB;
@@ -635,7 +635,7 @@ struct LinearAxisMotor {
 struct LinearAxisLimit {
     static constexpr int kBodies = 2, kPrestepRows = 13, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static LinearAxisFrame frame(const BodyState* b, const float* p, float& error) {  // LinearAxisLimit.cs:L92-119
+    template <class PR> BEPU_DI static LinearAxisFrame frame(const BodyState* b, PR p, float& error) {  // LinearAxisLimit.cs:L92-119
         LinearAxisFrame f;
         M33 mA = matrix_from_quaternion(b[0].q);
         f.normal = transform(ldrow3(p, 6), mA);
@@ -653,11 +653,11 @@ struct LinearAxisLimit {
         f.angularJB = cross(f.normal, offsetB);
         return f;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         float error;
         linear_axis_warm_start(frame(b, p, error), b, a, v);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         float error;
         LinearAxisFrame f = frame(b, p, error);
         Springiness sp = compute_springiness(ldrow(p, 11), ldrow(p, 12), dt);
@@ -682,7 +682,7 @@ BEPU_DI void center_distance_apply(V3 jacobianA, float imA, float imB, float imp
 struct CenterDistanceConstraint {
     static constexpr int kBodies = 2, kPrestepRows = 3, kImpulseRows = 1;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float*, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR, AR a, Velocity* v) {
         V3 ab = b[1].pos - b[0].pos;
         float lengthSquared = length_squared(ab);
         float inverseDistance = 1.0f / sqrtf(lengthSquared);
@@ -690,7 +690,7 @@ struct CenterDistanceConstraint {
         if (lengthSquared < 1e-10f) jacobianA = V3{1.0f, 0.0f, 0.0f};
         center_distance_apply(jacobianA, b[0].inertia.inv_mass, b[1].inertia.inv_mass, ldacc(a, 0), v[0], v[1]);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 ab = b[1].pos - b[0].pos;
         float distance = length(ab);
         float inverseDistance = 1.0f / distance;
@@ -720,13 +720,13 @@ struct CenterDistanceLimit {
         useMinimum = fabsf(distance - minimumDistance) < fabsf(distance - maximumDistance);
         return useMinimum ? -jacobianA : jacobianA;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         float distance;
         bool useMinimum;
         V3 jacobianA = jacobian(ldrow(p, 0), ldrow(p, 1), b[0].pos, b[1].pos, distance, useMinimum);
         center_distance_apply(jacobianA, b[0].inertia.inv_mass, b[1].inertia.inv_mass, ldacc(a, 0), v[0], v[1]);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         float distance;
         bool useMinimum;
         const float minimumDistance = ldrow(p, 0), maximumDistance = ldrow(p, 1);
@@ -750,10 +750,10 @@ struct CenterDistanceLimit {
 struct OneBodyAngularServo {
     static constexpr int kBodies = 1, kPrestepRows = 9, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float*, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR, AR a, Velocity* v) {
         v[0].ang = v[0].ang + transform(V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)}, b[0].inertia.t);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         Q4 errorRotation = concatenate(conjugate(b[0].q), ldrow4(p, 0));
         V3 errorAxis;
         float errorLength;
@@ -776,10 +776,10 @@ struct OneBodyAngularServo {
 struct OneBodyAngularMotor {
     static constexpr int kBodies = 1, kPrestepRows = 5, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float*, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR, AR a, Velocity* v) {
         v[0].ang = v[0].ang + transform(V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)}, b[0].inertia.t);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         MotorSoftness m = motor_softness(ldrow(p, 3), ldrow(p, 4), dt);
         Sym3 unsoftenedEffectiveMass = invert(b[0].inertia.t);
         V3 csi = transform(ldrow3(p, 0) - v[0].ang, unsoftenedEffectiveMass);
@@ -806,10 +806,10 @@ BEPU_DI Sym3 one_body_linear_effective_mass(V3 offset, const Inertia& inertia) {
 struct OneBodyLinearServo {
     static constexpr int kBodies = 1, kPrestepRows = 11, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         one_body_linear_apply(transform(ldrow3(p, 0), b[0].q), b[0].inertia, v[0], V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
         V3 offset = transform(ldrow3(p, 0), b[0].q);
         Springiness sp = compute_springiness(ldrow(p, 6), ldrow(p, 7), dt);
         V3 worldGrabPoint = offset + b[0].pos;
@@ -831,10 +831,10 @@ struct OneBodyLinearServo {
 struct OneBodyLinearMotor {
     static constexpr int kBodies = 1, kPrestepRows = 8, kImpulseRows = 3;
     static constexpr bool kIncremental = false, kNeedsPose = true;
-    BEPU_DI static void warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
         one_body_linear_apply(transform(ldrow3(p, 0), b[0].q), b[0].inertia, v[0], V3{ldacc(a, 0), ldacc(a, 1), ldacc(a, 2)});
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         V3 offset = transform(ldrow3(p, 0), b[0].q);
         MotorSoftness m = motor_softness(ldrow(p, 6), ldrow(p, 7), dt);
         V3 csv = (ldrow3(p, 3) - cross(v[0].ang, offset)) - v[0].lin;
@@ -877,11 +877,11 @@ struct AreaConstraint {
         j.inverseJacobianLength = 1.0f / sqrtf(jacobianLengthSquared);
         return j;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float*, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR, AR a, Velocity* v) {
         Jacobian j = jacobian(b);
         apply(b, j, j.inverseJacobianLength * ldacc(a, 0), v);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         Jacobian j = jacobian(b);
         float inverseJacobianLengthSquared = j.inverseJacobianLength * j.inverseJacobianLength;
         float inverseEffectiveMass = fmax_ps(
@@ -930,11 +930,11 @@ struct VolumeConstraint {
         j.inverseJacobianLength = 1.0f / sqrtf(jacobianLengthSquared);
         return j;
     }
-    BEPU_DI static void warm_start(const BodyState* b, const float*, const float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void warm_start(const BodyState* b, PR, AR a, Velocity* v) {
         Jacobian j = jacobian(b);
         apply(b, j, j.inverseJacobianLength * ldacc(a, 0), v);
     }
-    BEPU_DI static void solve(const BodyState* b, float dt, float, const float* p, float* a, Velocity* v) {
+    template <class PR, class AR> BEPU_DI static void solve(const BodyState* b, float dt, float, PR p, AR a, Velocity* v) {
         Jacobian j = jacobian(b);
         float inverseJacobianLengthSquared = j.inverseJacobianLength * j.inverseJacobianLength;
         float inverseEffectiveMass = fmax_ps(1e-14f, inverseJacobianLengthSquared * (j.contributionA * b[0].inertia.inv_mass + j.contributionB * b[1].inertia.inv_mass +

@@ -39,7 +39,7 @@ BEPU_DI void run_constraint_op(const StageOp& op, const WorkRecord* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(kPersistentThreads, 2)
+static __global__ void __launch_bounds__(kPersistentThreads, 2)
 persistent_solve_kernel(const StageOp* __restrict__ program, int op_count, const WorkRecord* __restrict__ records, const int32_t* __restrict__ kinematics, BodyBuffers B,
                         const FrameParams* __restrict__ fpp, unsigned int* barrier_counter) {
     const FrameParams fp = *fpp;

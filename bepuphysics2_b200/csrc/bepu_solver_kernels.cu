@@ -1,13 +1,33 @@
-// Compiled twice: -DBEPU_NS=bepu_fast (default FMA contraction) and -DBEPU_NS=bepu_strict -fmad=false.
+// Compiled per numerics flavour (-DBEPU_NS=bepu_fast with FMA contraction / -DBEPU_NS=bepu_strict -fmad=false) and per unit (-DBEPU_UNIT=n),
+// so that the big per-type switch of each kernel gets its own translation unit and the build parallelises:
+//   0 WarmStartFirst stage   1 WarmStart stage   2 Solve stage   3 Incremental stage + kinematic + final pose + launcher table
+//   4 persistent kernel      5 dataflow kernel
 #include "bepu_solver_kernels.cuh"
+#if BEPU_UNIT == 4
 #include "bepu_persistent.cuh"
+#elif BEPU_UNIT == 5
 #include "bepu_dataflow.cuh"
+#endif
 #include "bepu_layout_kernels.h"
 
 namespace BEPU_NS {
 
+void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
+void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
+void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
+int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
+                           unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
+int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, long long chain_delta, const int32_t* kinematics, const BodyBuffers& B,
+                         const FrameParams* fp, unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s);
+
+#if BEPU_UNIT <= 3
 template <int STAGE>
 static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+    static bool carveout_set = false;
+    if (!carveout_set) {  // the staged stages keep one 6 KB slab per resident warp in shared memory
+        cudaFuncSetAttribute(constraint_stage_kernel<STAGE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
     const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(blocks);
@@ -21,12 +41,27 @@ static void launch_stage_t(const WorkRecord* records, int work_count, const Body
     cfg.numAttrs = pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE>, records, work_count, B, fp);
 }
+#endif
+
+#if BEPU_UNIT == 0
+void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+    launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, pdl, s);
+}
+#elif BEPU_UNIT == 1
+void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+    launch_stage_t<kStageWarmStart>(records, work_count, B, fp, pdl, s);
+}
+#elif BEPU_UNIT == 2
+void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+    launch_stage_t<kStageSolve>(records, work_count, B, fp, pdl, s);
+}
+#elif BEPU_UNIT == 3
 static void launch_constraint_stage(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
     if (work_count <= 0) return;
     switch (stage) {
-        case kStageWarmStartFirst: launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, pdl, s); break;
-        case kStageWarmStart: launch_stage_t<kStageWarmStart>(records, work_count, B, fp, pdl, s); break;
-        case kStageSolve: launch_stage_t<kStageSolve>(records, work_count, B, fp, pdl, s); break;
+        case kStageWarmStartFirst: launch_stage_warm_start_first(records, work_count, B, fp, pdl, s); break;
+        case kStageWarmStart: launch_stage_warm_start(records, work_count, B, fp, pdl, s); break;
+        case kStageSolve: launch_stage_solve(records, work_count, B, fp, pdl, s); break;
         case kStageIncremental: launch_stage_t<kStageIncremental>(records, work_count, B, fp, pdl, s); break;
         default: break;
     }
@@ -41,13 +76,27 @@ static void launch_final_pose(const BodyBuffers& B, const FrameParams* fp, cudaS
     if (B.count <= 0) return;
     final_pose_kernel<<<(unsigned)((B.count + 255) / 256), 256, 0, s>>>(B, fp);
 }
-
-static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent, &launch_dataflow};
+static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent_unit, &launch_dataflow_unit};
+#elif BEPU_UNIT == 4
+int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
+                           unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s) {
+    return launch_persistent(program, op_count, records, kinematics, B, fp, barrier_counter, blocks_per_sm, s);
+}
+#elif BEPU_UNIT == 5
+int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, long long chain_delta, const int32_t* kinematics, const BodyBuffers& B,
+                         const FrameParams* fp, unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s) {
+    return launch_dataflow(program, op_count, records, chain_delta, kinematics, B, fp, barrier_counter, error_flag, blocks_per_sm, s);
+}
+#else
+#error "BEPU_UNIT must be 0..5"
+#endif
 
 }  // namespace BEPU_NS
 
+#if BEPU_UNIT == 3
 namespace bepucuda {
 #define BEPU_CAT2(a, b) a##b
 #define BEPU_CAT(a, b) BEPU_CAT2(a, b)
 const SolverLaunchers* BEPU_CAT(get_launchers_, BEPU_NS)() { return &BEPU_NS::kLaunchers; }
 }  // namespace bepucuda
+#endif

@@ -17,16 +17,26 @@ using namespace bepucuda;
 
 // ---- body records: one 32-byte record = one DRAM sector = ONE 256-bit load/store (LDG.E.256 / STG.E.256, new on sm_100) ----------------
 struct F8 { float a, b, c, d, e, f, g, h; };
+// Body records: one 256-bit access per 32-B record. In the per-stage kernels the records are marked evict-last in L2 (and never allocate in
+// L1) so that the body arrays stay L2-resident while the constraint rows stream past them (those are fetched evict-first, see the bulk copies);
+// the persistent / dataflow kernels, which rely on L2 as the coherence point across grid barriers inside one launch, keep plain ld/st.cg.
+#if defined(BEPU_UNIT) && BEPU_UNIT <= 3
+#define BEPU_BODY_LD "ld.global.L1::no_allocate.L2::evict_last.v8.f32"
+#define BEPU_BODY_ST "st.global.L1::no_allocate.L2::evict_last.v8.f32"
+#else
+#define BEPU_BODY_LD "ld.global.cg.v8.f32"
+#define BEPU_BODY_ST "st.global.cg.v8.f32"
+#endif
 BEPU_DI F8 ld256(const float4* p) {
     F8 r;
-    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile(BEPU_BODY_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.a), "=f"(r.b), "=f"(r.c), "=f"(r.d), "=f"(r.e), "=f"(r.f), "=f"(r.g), "=f"(r.h)
                  : "l"(p)
                  : "memory");
     return r;
 }
 BEPU_DI void st256(float4* p, float a, float b, float c, float d, float e, float f, float g, float h) {
-    asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+    asm volatile(BEPU_BODY_ST " [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
 }
 BEPU_DI void load_velocity(const float4* vel, uint32_t i, Velocity& v) {
     const F8 r = ld256(vel + 2 * (size_t)i);
@@ -69,7 +79,7 @@ BEPU_DI void fallback_if_inertia_incompatible(V3 previous, V3& w) {  // L180-190
 }
 // The two momentum-conserving modes are rare (AngularIntegrationMode.Nonconserving is the default everywhere in the
 // reference's demos/benchmarks); keeping them out of line keeps their registers out of the hot WarmStart path.
-__device__ __noinline__ void integrate_angular_conserve_momentum(Q4 previousOrientation, Sym3 localInverseInertia, Sym3 worldInverseInertia, V3& w) {  // L192-206
+static __device__ __noinline__ void integrate_angular_conserve_momentum(Q4 previousOrientation, Sym3 localInverseInertia, Sym3 worldInverseInertia, V3& w) {  // L192-206
     M33 prevR = matrix_from_quaternion(previousOrientation);
     V3 localPrevW = transform_by_transposed(w, prevR);
     Sym3 localInertiaTensor = invert(localInverseInertia);
@@ -78,7 +88,7 @@ __device__ __noinline__ void integrate_angular_conserve_momentum(Q4 previousOrie
     w = transform(angularMomentum, worldInverseInertia);
     fallback_if_inertia_incompatible(previous, w);
 }
-__device__ __noinline__ void integrate_angular_gyroscopic(Q4 orientation, Sym3 localInverseInertia, V3& w, float dt) {  // L208-253
+static __device__ __noinline__ void integrate_angular_gyroscopic(Q4 orientation, Sym3 localInverseInertia, V3& w, float dt) {  // L208-253
     M33 R = matrix_from_quaternion(orientation);
     V3 localW = transform_by_transposed(w, R);
     Sym3 I = invert(localInverseInertia);
@@ -155,12 +165,12 @@ BEPU_DI void gather_for_warm_start(uint32_t enc, const BodyBuffers& B, const Fra
 }
 
 // ---- uniform call shapes over contact and joint types ------------------------------------------------------------------
-template <class T> BEPU_DI void call_warm_start(const BodyState* b, const float* p, const float* a, Velocity* v) {
+template <class T, class PR, class AR> BEPU_DI void call_warm_start(const BodyState* b, PR p, AR a, Velocity* v) {
     if constexpr (T::kNeedsPose) T::warm_start(b, p, a, v);
     else if constexpr (T::kBodies == 2) T::warm_start(b[0].inertia, b[1].inertia, p, a, v[0], v[1]);
     else T::warm_start(b[0].inertia, p, a, v[0]);
 }
-template <class T> BEPU_DI void call_solve(const BodyState* b, float dt, float inverseDt, const float* p, float* a, Velocity* v) {
+template <class T, class PR, class AR> BEPU_DI void call_solve(const BodyState* b, float dt, float inverseDt, PR p, AR a, Velocity* v) {
     if constexpr (T::kNeedsPose) T::solve(b, dt, inverseDt, p, a, v);
     else if constexpr (T::kBodies == 2) T::solve(b[0].inertia, b[1].inertia, dt, inverseDt, p, a, v[0], v[1]);
     else T::solve(b[0].inertia, dt, inverseDt, p, a, v[0]);
@@ -172,9 +182,11 @@ template <class T> BEPU_DI void call_incremental(float dt, const Velocity* v, fl
     }
 }
 
-// One constraint lane of one stage. refs/p/a address this lane in row 0 of the bundle; enc0/enc1 are the (possibly prefetched) first two body references.
-template <class T, int STAGE>
-BEPU_DI void run_lane(const int32_t* refs, float* p, float* a, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+// One constraint lane of one stage. refs addresses this lane in row 0 of the bundle's body references; enc0/enc1 are the (possibly prefetched)
+// first two body references; p / a are the row accessors (global or staged); p_rw is the lane's raw prestep pointer for the in-place
+// IncrementallyUpdateForSubstep.
+template <class T, int STAGE, class PR, class AR>
+BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
     constexpr int NB = T::kBodies;
     uint32_t enc[NB];
     enc[0] = enc0;
@@ -187,7 +199,7 @@ BEPU_DI void run_lane(const int32_t* refs, float* p, float* a, uint32_t enc0, ui
     if constexpr (STAGE == kStageIncremental) {
 #pragma unroll
         for (int s = 0; s < NB; ++s) load_velocity(B.velocity, enc[s] & kRefIndexMask, v[s]);
-        call_incremental<T>(fp.dt, v, p);
+        call_incremental<T>(fp.dt, v, p_rw);
     } else if constexpr (STAGE == kStageSolve) {
 #pragma unroll
         for (int s = 0; s < NB; ++s) {
@@ -196,6 +208,7 @@ BEPU_DI void run_lane(const int32_t* refs, float* p, float* a, uint32_t enc0, ui
             load_inertia(B.inertia_world, idx, b[s].inertia);
             if (T::kNeedsPose) load_pose(B.pose, idx, b[s].pos, b[s].q);
         }
+        rows_ready(p);
         call_solve<T>(b, fp.dt, fp.inverse_dt, p, a, v);
 #pragma unroll
         for (int s = 0; s < NB; ++s)
@@ -203,6 +216,7 @@ BEPU_DI void run_lane(const int32_t* refs, float* p, float* a, uint32_t enc0, ui
     } else {
 #pragma unroll
         for (int s = 0; s < NB; ++s) gather_for_warm_start<STAGE, T::kNeedsPose>(enc[s], B, fp, b[s], v[s]);
+        rows_ready(p);
         call_warm_start<T>(b, p, a, v);
 #pragma unroll
         for (int s = 0; s < NB; ++s)
@@ -210,8 +224,20 @@ BEPU_DI void run_lane(const int32_t* refs, float* p, float* a, uint32_t enc0, ui
     }
 }
 
+// Work records and body references are loaded with `asm volatile` so that the loads are ISSUED where the source places them (a whole pipeline
+// stage before their first use); plain __ldg loads get sunk next to the first use by the compiler and the warp then eats the full latency there.
+BEPU_DI int4 ldg_nc_v4(const void* p) {
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+BEPU_DI uint32_t ldg_nc_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 BEPU_DI WorkRecord load_record(const WorkRecord* r) {
-    const int4 lo = __ldg(reinterpret_cast<const int4*>(r)), hi = __ldg(reinterpret_cast<const int4*>(r) + 1);
+    const int4 lo = ldg_nc_v4(r), hi = ldg_nc_v4(reinterpret_cast<const int4*>(r) + 1);
     WorkRecord w;
     w.refs = reinterpret_cast<int32_t*>((unsigned long long)(unsigned int)lo.x | ((unsigned long long)(unsigned int)lo.y << 32));
     w.prestep = reinterpret_cast<float*>((unsigned long long)(unsigned int)lo.z | ((unsigned long long)(unsigned int)lo.w << 32));
@@ -228,14 +254,13 @@ BEPU_DI WorkRecord load_record(const WorkRecord* r) {
     X(8, NonconvexOneBody<2>) X(9, NonconvexOneBody<3>) X(10, NonconvexOneBody<4>)                                                \
     X(15, NonconvexTwoBody<2>) X(16, NonconvexTwoBody<3>) X(17, NonconvexTwoBody<4>)
 
-template <int STAGE>
-BEPU_DI void run_bundle(const WorkRecord& rec, int lane, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+template <int STAGE, class PR, class AR>
+BEPU_DI void run_bundle_rows(const WorkRecord& rec, int lane, PR p, AR a, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
     const int32_t* refs = rec.refs + lane;
-    float* p = rec.prestep + lane;
-    float* a = rec.impulses + lane;
+    float* p_rw = rec.prestep + lane;
     switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \
-    case ID: run_lane<T, STAGE>(refs, p, a, enc0, enc1, B, fp); break;
+    case ID: run_lane<T, STAGE>(refs, p, a, p_rw, enc0, enc1, B, fp); break;
         BEPU_CONTACT_TYPES(BEPU_CASE)
         BEPU_JOINT_TYPES(BEPU_CASE)
         BEPU_JOINT_TYPES_MORE(BEPU_CASE)
@@ -243,36 +268,102 @@ BEPU_DI void run_bundle(const WorkRecord& rec, int lane, uint32_t enc0, uint32_t
         default: break;
     }
 }
+// Rows straight from HBM (persistent / dataflow kernels, and the incremental stage everywhere).
+template <int STAGE>
+BEPU_DI void run_bundle(const WorkRecord& rec, int lane, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+    run_bundle_rows<STAGE>(rec, lane, GlobalRows{rec.prestep + lane}, GlobalAcc{rec.impulses + lane}, enc0, enc1, B, fp);
+}
 // The reference arena is padded, so reading a second body-reference row is always in bounds (one-body types ignore it).
 template <int STAGE> BEPU_DI void run_bundle(const WorkRecord& rec, int lane, const BodyBuffers& B, const FrameParams& fp) {
-    const uint32_t enc0 = (uint32_t)__ldg(rec.refs + lane), enc1 = (uint32_t)__ldg(rec.refs + kLanes + lane);
+    const uint32_t enc0 = ldg_nc_u32(rec.refs + lane), enc1 = ldg_nc_u32(rec.refs + kLanes + lane);
     run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
 }
 
+// ---- bulk staging of one bundle's prestep + accumulated impulse block into shared memory (cp.async.bulk + mbarrier) ----------------
+// Block sizes per type id (rows of 128 B); 0 for ids without a type.
+struct StageRowCounts { uint8_t prestep[64], impulses[64]; };
+__host__ __device__ constexpr StageRowCounts make_stage_row_counts() {
+    StageRowCounts c{};
+#define BEPU_ROWS(ID, T) c.prestep[ID] = (uint8_t)T::kPrestepRows; c.impulses[ID] = (uint8_t)T::kImpulseRows;
+    BEPU_CONTACT_TYPES(BEPU_ROWS)
+    BEPU_JOINT_TYPES(BEPU_ROWS)
+    BEPU_JOINT_TYPES_MORE(BEPU_ROWS)
+#undef BEPU_ROWS
+    return c;
+}
+__constant__ StageRowCounts kStageRowCounts = make_stage_row_counts();
+constexpr int kStageSlabRows = 48;  // >= max(prestep rows + impulse rows) over all types (Contact4Nonconvex: 35 + 12)
+constexpr int kStageSlabBytes = kStageSlabRows * kLanes * 4;
+
+BEPU_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BEPU_DI void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+BEPU_DI void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+// Constraint rows are touched once per stage and the whole set is far larger than what is reused before the next stage: fetch them evict-first.
+BEPU_DI uint64_t l2_evict_first_policy() {
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+BEPU_DI void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar),
+                 "l"(policy)
+                 : "memory");
+}
 // ---- kernels ------------------------------------------------------------------------------------------------------------
 constexpr int kStageBlockThreads = 64;
 #ifndef BEPU_STAGE_MIN_BLOCKS
 #define BEPU_STAGE_MIN_BLOCKS 1
 #endif
 
+// One (batch, stage): one warp per bundle. In the WarmStart / Solve stages the bundle's whole prestep + accumulated-impulse block (contiguous in
+// the AOSOA-32 layout) is fetched with ONE cp.async.bulk transaction pair into the warp's shared-memory slab while the lanes gather their
+// body records, instead of ~30 dependent row loads spread through the constraint math.
 template <int STAGE>
 __global__ void __launch_bounds__(kStageBlockThreads, BEPU_STAGE_MIN_BLOCKS) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp) {
     // Programmatic dependent launch: let the NEXT stage's grid become resident right away, and do everything that does not depend on
     // the previous stage (work record, body references, frame scalars: all immutable during a solve) before waiting for it.
     asm volatile("griddepcontrol.launch_dependents;");
+    constexpr bool kStaged = STAGE != kStageIncremental;
+    constexpr int kWarps = kStageBlockThreads / 32;
+    __shared__ __align__(128) float slab[kStaged ? kWarps * kStageSlabRows * kLanes : 1];
+    __shared__ __align__(8) unsigned long long bars[kWarps];
+    const int warp_in_block = threadIdx.x >> 5;
     const int warp = (blockIdx.x * kStageBlockThreads + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     WorkRecord rec{};
     uint32_t enc0 = (uint32_t)kRefEmpty, enc1 = 0;
     const bool active = warp < work_count;
+    const uint32_t slab_addr = kStaged ? smem_u32(slab) + warp_in_block * kStageSlabBytes : 0;
+    const uint32_t bar = smem_u32(&bars[warp_in_block]);
     if (active) {
         rec = load_record(records + warp);
-        enc0 = (uint32_t)__ldg(rec.refs + lane);
-        enc1 = (uint32_t)__ldg(rec.refs + kLanes + lane);
+        if (kStaged && lane == 0) mbar_init(bar, 1);
+        enc0 = ldg_nc_u32(rec.refs + lane);
+        enc1 = ldg_nc_u32(rec.refs + kLanes + lane);
     }
     const FrameParams fp = *fpp;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (active) run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
+    if (!active) return;
+    if constexpr (kStaged) {
+        // The bulk transactions are issued only after the wait: depth rows are rewritten by IncrementallyUpdateForSubstep and accumulated impulses by
+        // this batch's previous stage, and with programmatic dependent launch several earlier grids may still be in flight before it.
+        const uint32_t prestep_bytes = kStageRowCounts.prestep[rec.type_id] * (kLanes * 4);
+        const uint32_t impulse_bytes = kStageRowCounts.impulses[rec.type_id] * (kLanes * 4);
+        if (lane == 0) {
+            const uint64_t policy = l2_evict_first_policy();
+            mbar_expect_tx(bar, prestep_bytes + impulse_bytes);
+            bulk_copy_g2s(slab_addr, rec.prestep, prestep_bytes, bar, policy);
+            bulk_copy_g2s(slab_addr + prestep_bytes, rec.impulses, impulse_bytes, bar, policy);
+        }
+        __syncwarp();
+        run_bundle_rows<STAGE>(rec, lane, StagedRows{slab_addr + lane * 4, bar}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp);
+    } else {
+        run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
+    }
 }
 
 // IntegrateKinematicVelocities / IntegrateKinematicPosesAndVelocities (PoseIntegrator.cs:L451-487, L493-535)
@@ -338,7 +429,7 @@ BEPU_DI void run_final_pose(int i, const BodyBuffers& B, const FrameParams& fp) 
     store_pose(B.pose, i, pos, q);
     if (integrateVelocity) store_velocity(B.velocity, i, v);
 }
-__global__ void final_pose_kernel(BodyBuffers B, const FrameParams* __restrict__ fpp) {
+static __global__ void final_pose_kernel(BodyBuffers B, const FrameParams* __restrict__ fpp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B.count) return;
     const FrameParams fp = *fpp;

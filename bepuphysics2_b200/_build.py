@@ -49,6 +49,9 @@ def build(force=False, verbose=False, variant=None, defines=()):
     # (object, source, extra flags); the heaviest units (dataflow, persistent) first so the pool starts them early
     units = [("solver_%s_%d.o" % (name, unit), "bepu_solver_kernels.cu", flags + ["-DBEPU_UNIT=%d" % unit]) for unit in (5, 4, 1, 0, 2, 3) for name, flags in flavours]
     units += [("layout.o", "bepu_layout_kernels.cu", []), ("api.o", "bepucuda_api.cu", [])]
+    all_sources = [os.path.join(CSRC, f) for f in ("bepu_solver_kernels.cu", "bepu_layout_kernels.cu", "bepucuda_api.cu")] + headers
+    if not force and not defines and os.path.exists(LIB_CUDA) and not _newer(LIB_CUDA, all_sources):
+        units = []  # the shared library is newer than every source: nothing to compile (object files need not travel with a snapshot)
     jobs = []
     for obj, src, extra in units:
         o = os.path.join(BUILD, obj)
@@ -64,7 +67,7 @@ def build(force=False, verbose=False, variant=None, defines=()):
                 if verbose and out.strip():
                     print(out)
     objs = [os.path.join(BUILD, u[0]) for u in units]
-    if force or _newer(LIB_CUDA, objs):
+    if units and (force or _newer(LIB_CUDA, objs)):
         _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB_CUDA] + objs)
     if variant:
         return LIB_CUDA, LIB_HOST

@@ -66,16 +66,56 @@ def build_sim(args, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle (clocks event) reasons sampled DURING the timed region: NVML every 5 ms from a thread (nvidia_ml_py), falling back to
+    `nvidia-smi -lms 100` (B200_PROFILING.md recipe) when NVML is unavailable."""
 
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device_index):
         self.device_index = device_index
-        self.samples = []
+        self.samples = []  # (sm_mhz, sm_max_mhz, set(reasons))
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device when possible
+            handle = None
+            try:
+                import torch
+
+                bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+                dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+                dev = torch.cuda.get_device_properties(device_index).pci_device_id
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.nvml, self.handle = pynvml, handle
+        except Exception:
+            self.nvml = None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mask = reasons_fn(self.handle)
+                self.samples.append((float(sm), float(smax), {k for k, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -85,31 +125,32 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 7:
-                self.samples.append(parts)
+                try:
+                    self.samples.append((float(parts[0]), float(parts[1]), {n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")}))
+                except ValueError:
+                    pass
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(s[0]))
-                smax.append(float(s[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0}
+        reasons = set()
+        for s in self.samples:
+            reasons |= s[2]
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(reasons), "samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def load_traffic(bodies, kernel):
@@ -343,7 +384,9 @@ def main():
         if traffic_row:
             traffic = traffic_row["dram_bytes_per_launch"]
             roof_extra["traffic_source"] = traffic_row["source"]
-            roof_extra["algorithmic_bytes_per_launch"] = roof_bytes / launches
+            roof_extra["traffic_launch"] = traffic_row["launch"]
+            roof_extra["traffic_launch_algorithmic_bytes"] = traffic_row["algorithmic_bytes_per_launch"]
+            roof_extra["mean_algorithmic_bytes_per_launch"] = roof_bytes / launches
         line = {
             "metric": "constraint-iterations/sec (solver+integrator)", "value": value, "unit": "constraint-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

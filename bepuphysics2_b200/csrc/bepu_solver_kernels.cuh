@@ -314,7 +314,10 @@ BEPU_DI void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32
                  : "memory");
 }
 // ---- kernels ------------------------------------------------------------------------------------------------------------
-constexpr int kStageBlockThreads = 64;
+#ifndef BEPU_STAGE_BLOCK_THREADS
+#define BEPU_STAGE_BLOCK_THREADS 64
+#endif
+constexpr int kStageBlockThreads = BEPU_STAGE_BLOCK_THREADS;
 #ifndef BEPU_STAGE_MIN_BLOCKS
 #define BEPU_STAGE_MIN_BLOCKS 1
 #endif

@@ -21,11 +21,15 @@ int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord*
                          const FrameParams* fp, unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s);
 
 #if BEPU_UNIT <= 3
-template <int STAGE>
-static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+#ifndef BEPU_DEEP_MINB
+#define BEPU_DEEP_MINB 12
+#endif
+constexpr int kDeepBatchBundles = 2400;  // more bundles than the uncapped build keeps resident at once (148 SMs x 16 warps)
+template <int STAGE, int MINB>
+static void launch_stage_variant(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
     static bool carveout_set = false;
     if (!carveout_set) {  // the staged stages keep one 6 KB slab per resident warp in shared memory
-        cudaFuncSetAttribute(constraint_stage_kernel<STAGE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(constraint_stage_kernel<STAGE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carveout_set = true;
     }
     const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
@@ -39,7 +43,12 @@ static void launch_stage_t(const WorkRecord* records, int work_count, const Body
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE>, records, work_count, B, fp);
+    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, work_count, B, fp);
+}
+template <int STAGE>
+static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+    if (STAGE != kStageIncremental && work_count >= kDeepBatchBundles) launch_stage_variant<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, pdl, s);
+    else launch_stage_variant<STAGE, 1>(records, work_count, B, fp, pdl, s);
 }
 #endif
 

@@ -318,15 +318,15 @@ BEPU_DI void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32
 #define BEPU_STAGE_BLOCK_THREADS 64
 #endif
 constexpr int kStageBlockThreads = BEPU_STAGE_BLOCK_THREADS;
-#ifndef BEPU_STAGE_MIN_BLOCKS
-#define BEPU_STAGE_MIN_BLOCKS 1
-#endif
 
 // One (batch, stage): one warp per bundle. In the WarmStart / Solve stages the bundle's whole prestep + accumulated-impulse block (contiguous in
 // the AOSOA-32 layout) is fetched with ONE cp.async.bulk transaction pair into the warp's shared-memory slab while the lanes gather their
 // body records, instead of ~30 dependent row loads spread through the constraint math.
-template <int STAGE>
-__global__ void __launch_bounds__(kStageBlockThreads, BEPU_STAGE_MIN_BLOCKS) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp) {
+// MINB = minimum resident CTAs per SM the register allocation must allow: 1 (uncapped, ~106 registers: best when a stage is less than a wave and a
+// warp's own latency is all that counts) or 12 (<= 80 registers, 24 instead of 16 warps per SM: ~4 % faster once a batch is several waves deep,
+// 3-12 % slower below one wave; the launcher picks per launch by bundle count).
+template <int STAGE, int MINB>
+__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp) {
     // Programmatic dependent launch: let the NEXT stage's grid become resident right away, and do everything that does not depend on
     // the previous stage (work record, body references, frame scalars: all immutable during a solve) before waiting for it.
     asm volatile("griddepcontrol.launch_dependents;");

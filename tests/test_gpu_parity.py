@@ -195,3 +195,16 @@ def test_joint_zoo_with_fallback_batch_and_momentum_conserving_integration(libs)
 def test_joint_zoo_fast_build_within_tolerance(libs):
     """Fast (FMA, approximate div/sqrt) build on the full zoo after one frame: relative RMS error <= 1e-3, max abs error <= 5e-2."""
     _parity(scenes.joint_zoo(1500, 120, seed=6), exact=False, rel_rms=1e-3, max_abs=5e-2, substeps=2, velocity_iterations=2)
+
+
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
+def test_edge_cases_no_constraints_single_body_and_per_substep_iteration_schedule(libs, mode):
+    """Degenerate inputs through the whole C-ABI sequence: bodies without any constraint (only IntegrateAfterSubstepping runs), a single constrained
+    body, a one-constraint scene, and a per-substep velocity-iteration schedule that contains a zero."""
+    free = {"bodies": scenes.make_bodies(np.array([[0, 5, 0], [3, 1, 2]], dtype=np.float32), linear=np.array([[1, 0, 0], [0, 2, 0]], dtype=np.float32),
+                                         angular=np.array([[0.1, 0.2, 0.3], [0, 0, 1]], dtype=np.float32), inverse_mass=np.array([1, 0.5], dtype=np.float32),
+                                         inverse_inertia=np.array([[1, 0, 1, 0, 0, 1], [2, 0, 3, 0, 0, 4]], dtype=np.float32)), "constraints": []}
+    _parity(free, mode=mode, substeps=3, velocity_iterations=2, frames=2)
+    one = scenes.joint_zoo(2, 1, seed=3, kinematic_fraction=0.0, types=[44])  # one one-body servo on one of two bodies
+    _parity(one, mode=mode, substeps=2, velocity_iterations=1, frames=2)
+    _parity(scenes.shape_pile(300, seed=2), mode=mode, substeps=3, velocity_iterations=[2, 0, 1], frames=2)

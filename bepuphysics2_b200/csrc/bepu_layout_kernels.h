@@ -38,10 +38,12 @@ void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work
                       int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s);
 
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
+constexpr int kLaunchPdl = 1, kLaunchPrefetchRows = 2;
 struct SolverLaunchers {
     // Launches one constraint stage (kStageWarmStartFirst / kStageWarmStart / kStageSolve / kStageIncremental) over `work_count` bundles.
-    // pdl: launch with programmatic stream serialization (the kernel overlaps its prologue with the previous stage's tail).
-    void (*constraint_stage)(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
+    // launch_flags: kLaunchPdl = launch with programmatic stream serialization (the kernel overlaps its prologue with the previous stage);
+    // kLaunchPrefetchRows = the kernel launched just before this one writes neither this batch's prestep nor its impulses, so the prologue may fetch them.
+    void (*constraint_stage)(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
     void (*kinematic_stage)(int stage, const int32_t* kinematics, int count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
     void (*final_pose)(const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
     // Persistent cooperative kernel: runs a whole stage program with a grid barrier between ops. Returns a cudaError_t.

@@ -12,9 +12,9 @@
 
 namespace BEPU_NS {
 
-void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
-void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
-void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s);
+void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
+void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
+void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
 int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                            unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
 int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, long long chain_delta, const int32_t* kinematics, const BodyBuffers& B,
@@ -26,7 +26,7 @@ int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord*
 #endif
 constexpr int kDeepBatchBundles = 2400;  // more bundles than the uncapped build keeps resident at once (148 SMs x 16 warps)
 template <int STAGE, int MINB>
-static void launch_stage_variant(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+static void launch_stage_variant(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     static bool carveout_set = false;
     if (!carveout_set) {  // the staged stages keep one 6 KB slab per resident warp in shared memory
         cudaFuncSetAttribute(constraint_stage_kernel<STAGE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -42,36 +42,36 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, work_count, B, fp);
+    cfg.numAttrs = (launch_flags & bepucuda::kLaunchPdl) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0);
 }
 template <int STAGE>
-static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
-    if (STAGE != kStageIncremental && work_count >= kDeepBatchBundles) launch_stage_variant<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, pdl, s);
-    else launch_stage_variant<STAGE, 1>(records, work_count, B, fp, pdl, s);
+static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    if (STAGE != kStageIncremental && work_count >= kDeepBatchBundles) launch_stage_variant<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, launch_flags, s);
+    else launch_stage_variant<STAGE, 1>(records, work_count, B, fp, launch_flags, s);
 }
 #endif
 
 #if BEPU_UNIT == 0
-void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
-    launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, pdl, s);
+void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, s);
 }
 #elif BEPU_UNIT == 1
-void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
-    launch_stage_t<kStageWarmStart>(records, work_count, B, fp, pdl, s);
+void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    launch_stage_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, s);
 }
 #elif BEPU_UNIT == 2
-void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
-    launch_stage_t<kStageSolve>(records, work_count, B, fp, pdl, s);
+void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    launch_stage_t<kStageSolve>(records, work_count, B, fp, launch_flags, s);
 }
 #elif BEPU_UNIT == 3
-static void launch_constraint_stage(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, bool pdl, cudaStream_t s) {
+static void launch_constraint_stage(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     if (work_count <= 0) return;
     switch (stage) {
-        case kStageWarmStartFirst: launch_stage_warm_start_first(records, work_count, B, fp, pdl, s); break;
-        case kStageWarmStart: launch_stage_warm_start(records, work_count, B, fp, pdl, s); break;
-        case kStageSolve: launch_stage_solve(records, work_count, B, fp, pdl, s); break;
-        case kStageIncremental: launch_stage_t<kStageIncremental>(records, work_count, B, fp, pdl, s); break;
+        case kStageWarmStartFirst: launch_stage_warm_start_first(records, work_count, B, fp, launch_flags, s); break;
+        case kStageWarmStart: launch_stage_warm_start(records, work_count, B, fp, launch_flags, s); break;
+        case kStageSolve: launch_stage_solve(records, work_count, B, fp, launch_flags, s); break;
+        case kStageIncremental: launch_stage_t<kStageIncremental>(records, work_count, B, fp, launch_flags, s); break;
         default: break;
     }
 }

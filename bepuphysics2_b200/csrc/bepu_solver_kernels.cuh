@@ -320,16 +320,18 @@ BEPU_DI void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32
 constexpr int kStageBlockThreads = BEPU_STAGE_BLOCK_THREADS;
 
 // One (batch, stage): one warp per bundle. In the WarmStart / Solve stages the bundle's whole prestep + accumulated-impulse block (contiguous in
-// the AOSOA-32 layout) is fetched with ONE cp.async.bulk transaction pair into the warp's shared-memory slab while the lanes gather their
-// body records, instead of ~30 dependent row loads spread through the constraint math.
-// MINB = minimum resident CTAs per SM the register allocation must allow: 1 (uncapped, ~106 registers: best when a stage is less than a wave and a
-// warp's own latency is all that counts) or 12 (<= 80 registers, 24 instead of 16 warps per SM: ~4 % faster once a batch is several waves deep,
-// 3-12 % slower below one wave; the launcher picks per launch by bundle count).
+// the AOSOA-32 layout) is fetched with ONE cp.async.bulk transaction pair into the warp's shared-memory slab, instead of ~30 dependent row loads
+// spread through the constraint math.
+//
+// Programmatic dependent launch, with the trigger placed AFTER this kernel's own wait: the next stage's grid can start once every CTA here has
+// passed `griddepcontrol.wait`, i.e. once the PREVIOUS stage has completed and flushed. So while a kernel runs its pre-wait prologue, everything
+// older than its immediate predecessor is final, and the prologue may read whatever that one predecessor does not write: the work record and
+// body references (immutable during a solve) always, and -- when the host says so (kStagePrefetchRows: the predecessor is neither the incremental
+// contact update, which rewrites depth rows, nor a stage of this same batch, which rewrites these impulses) -- the whole row block. That takes the
+// bulk copy's latency off the critical path; after the wait only the body gather, the math and the scatter remain.
+constexpr int kStagePrefetchRows = 1;
 template <int STAGE, int MINB>
-__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp) {
-    // Programmatic dependent launch: let the NEXT stage's grid become resident right away, and do everything that does not depend on
-    // the previous stage (work record, body references, frame scalars: all immutable during a solve) before waiting for it.
-    asm volatile("griddepcontrol.launch_dependents;");
+__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags) {
     constexpr bool kStaged = STAGE != kStageIncremental;
     constexpr int kWarps = kStageBlockThreads / 32;
     __shared__ __align__(128) float slab[kStaged ? kWarps * kStageSlabRows * kLanes : 1];
@@ -342,21 +344,32 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
     const bool active = warp < work_count;
     const uint32_t slab_addr = kStaged ? smem_u32(slab) + warp_in_block * kStageSlabBytes : 0;
     const uint32_t bar = smem_u32(&bars[warp_in_block]);
+    const bool early_rows = kStaged && (flags & kStagePrefetchRows);
+    uint32_t prestep_bytes = 0, impulse_bytes = 0;
     if (active) {
         rec = load_record(records + warp);
-        if (kStaged && lane == 0) mbar_init(bar, 1);
+        if constexpr (kStaged) {
+            prestep_bytes = kStageRowCounts.prestep[rec.type_id] * (kLanes * 4);
+            impulse_bytes = kStageRowCounts.impulses[rec.type_id] * (kLanes * 4);
+            if (lane == 0) {
+                mbar_init(bar, 1);
+                if (early_rows) {
+                    const uint64_t policy = l2_evict_first_policy();
+                    mbar_expect_tx(bar, prestep_bytes + impulse_bytes);
+                    bulk_copy_g2s(slab_addr, rec.prestep, prestep_bytes, bar, policy);
+                    bulk_copy_g2s(slab_addr + prestep_bytes, rec.impulses, impulse_bytes, bar, policy);
+                }
+            }
+        }
         enc0 = ldg_nc_u32(rec.refs + lane);
         enc1 = ldg_nc_u32(rec.refs + kLanes + lane);
     }
     const FrameParams fp = *fpp;
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     if (!active) return;
     if constexpr (kStaged) {
-        // The bulk transactions are issued only after the wait: depth rows are rewritten by IncrementallyUpdateForSubstep and accumulated impulses by
-        // this batch's previous stage, and with programmatic dependent launch several earlier grids may still be in flight before it.
-        const uint32_t prestep_bytes = kStageRowCounts.prestep[rec.type_id] * (kLanes * 4);
-        const uint32_t impulse_bytes = kStageRowCounts.impulses[rec.type_id] * (kLanes * 4);
-        if (lane == 0) {
+        if (!early_rows && lane == 0) {
             const uint64_t policy = l2_evict_first_policy();
             mbar_expect_tx(bar, prestep_bytes + impulse_bytes);
             bulk_copy_g2s(slab_addr, rec.prestep, prestep_bytes, bar, policy);

@@ -286,16 +286,26 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
     const FrameParams* fp = ctx->frame_params_dev.as<FrameParams>();
     const int32_t* kin = ctx->kinematics_dev.as<int32_t>();
     int64_t n = 0;
+    const bool pdl = ctx->cfg.reserved[1] == 0;
+    // Row prefetch in the PDL prologue (see constraint_stage_kernel): allowed when the kernel launched immediately before neither rewrites this
+    // batch's prestep rows (the incremental contact update does) nor its impulses (a stage of the same batch does: single-batch scenes).
+    const StageOp* previous = nullptr;  // last launched op
     for (const StageOp& op : ctx->program) {
         switch (op.stage) {
             case kStageWarmStartFirst: case kStageWarmStart: case kStageSolve: case kStageIncremental:
-                if (op.work_count > 0) { ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, ctx->cfg.reserved[1] == 0, s); ++n; }
+                if (op.work_count > 0) {
+                    bool prefetch = op.stage != kStageIncremental && previous != nullptr && previous->stage != kStageIncremental;
+                    if (prefetch && previous->stage <= kStageSolve && previous->work_begin == op.work_begin) prefetch = false;
+                    ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0), s);
+                    previous = &op;
+                    ++n;
+                }
                 break;
             case kStageKinematicFirst: case kStageKinematic:
-                if (op.work_count > 0) { ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, s); ++n; }
+                if (op.work_count > 0) { ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, s); previous = &op; ++n; }
                 break;
             case kStageFinalPose:
-                if (ctx->B.count > 0) { ctx->launchers->final_pose(ctx->B, fp, s); ++n; }
+                if (ctx->B.count > 0) { ctx->launchers->final_pose(ctx->B, fp, s); previous = &op; ++n; }
                 break;
         }
     }
@@ -1076,7 +1086,7 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
         const bool has_work = op.stage == kStageFinalPose ? ctx->B.count > 0 : op.work_count > 0;
         if (!has_work) continue;
         CK(cudaEventRecord(ctx->profile_events[2 * i], ctx->stream));
-        if (op.stage <= kStageIncremental) ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, false, ctx->stream);
+        if (op.stage <= kStageIncremental) ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, 0, ctx->stream);
         else if (op.stage <= kStageKinematic) ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, ctx->stream);
         else ctx->launchers->final_pose(ctx->B, fp, ctx->stream);
         CK(cudaEventRecord(ctx->profile_events[2 * i + 1], ctx->stream));

@@ -64,3 +64,21 @@ def test_product_sources_never_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inc")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text.lower(), "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/bepucuda.h is the drop-in boundary: it has to compile as C99 (what a P/Invoke / cgo / ctypes binding generator consumes) and as
+    C++11, with no CUDA or torch types in any signature."""
+    import subprocess
+
+    header = open(os.path.join(ROOT, "include", "bepucuda.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    code = re.sub(r"bepucuda|BEPUCUDA|void\* cuda_stream", "", code)  # the one stream handle crosses as an opaque void*
+    for forbidden in ("cuda", "torch", "at::", "std::", "#include <cuda"):
+        assert forbidden not in code, "%r appears in the public header's code" % forbidden
+    c = tmp_path / "use.c"
+    c.write_text('#include "bepucuda.h"\nint main(void) { bepucuda_config cfg; bepucuda_timings t; (void)cfg; (void)t; return bepucuda_type_info(0, 0, 0, 0) == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(c)], check=True)
+    cpp = tmp_path / "use.cpp"
+    cpp.write_text('#include "bepucuda.h"\nint main() { return 0; }\n')
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(cpp)], check=True)

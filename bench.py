@@ -407,8 +407,10 @@ def main():
             line["large_scene"] = large
         if not args.no_cpu_baseline:
             cb = cpu_reference_run(args, steps=3, warmup=1, threads=args.cpu_threads)
+            c1 = cpu_reference_run(args, steps=1, warmup=0, threads=1)  # the reference's own benchmarks run single-threaded (ShapePileBenchmark.cs:L228)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "constraint-iterations/s", "cores": cb["cores"], "kind": "port",
-                                    "sample": "3 full frames of the same workload after 1 warm-up (C++ restatement of the reference solver, AVX2 8-wide + OpenMP over bundles; %.1f ms/frame)" % cb["ms_per_step"]}
+                                    "sample": "3 full frames of the same workload after 1 warm-up (C++ restatement of the reference solver, AVX2 8-wide + OpenMP over bundles; %.1f ms/frame)" % cb["ms_per_step"],
+                                    "single_thread": {"value": c1["value"], "ms_per_step": c1["ms_per_step"], "sample": "1 frame, 1 thread, same code"}}
         print(json.dumps(line))
     if ts is not None:
         ts.close()

@@ -24,6 +24,17 @@ namespace BepuCuda
         public int DeviceBatchCount, FallbackLevelCount;
     }
 
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct StageProfile
+    {
+        public fixed float Ms[8];
+        public fixed long Launches[8];
+        public fixed long AlgorithmicBytes[8];
+    }
+
+    [UnmanagedFunctionPointer(CallingConvention.Cdecl)]
+    public unsafe delegate int ExchangeFn(void* user, void* delta, long count, void* cudaStream);
+
     public static unsafe class Native
     {
         const string Lib = "bepucuda";
@@ -45,6 +56,11 @@ namespace BepuCuda
         [DllImport(Lib)] public static extern int bepucuda_synchronize(IntPtr ctx);
         [DllImport(Lib)] public static extern int bepucuda_download_bodies(IntPtr ctx, void* bodyDynamicsOut, int bodyCount);
         [DllImport(Lib)] public static extern int bepucuda_download_impulses(IntPtr ctx);
+        [DllImport(Lib)] public static extern int bepucuda_download_prestep(IntPtr ctx, int batchIndex, int typeBatchIndex, float* prestepOut);
         [DllImport(Lib)] public static extern int bepucuda_get_timings(IntPtr ctx, Timings* timings);
+        [DllImport(Lib)] public static extern int bepucuda_event_record(IntPtr ctx, int slot);
+        [DllImport(Lib)] public static extern int bepucuda_event_elapsed_ms(IntPtr ctx, int slotBegin, int slotEnd, float* ms);
+        [DllImport(Lib)] public static extern int bepucuda_profile_stages(IntPtr ctx, float dt, StageProfile* profile);
+        [DllImport(Lib)] public static extern int bepucuda_set_boundary_bodies(IntPtr ctx, int* bodyIndices, int count, ExchangeFn exchange, void* user);
     }
 }

@@ -82,3 +82,16 @@ def test_public_header_is_plain_c(tmp_path):
     cpp = tmp_path / "use.cpp"
     cpp.write_text('#include "bepucuda.h"\nint main() { return 0; }\n')
     subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), str(cpp)], check=True)
+
+
+def test_csharp_binding_declares_every_entry_point():
+    """integration/csharp/BepuCuda.cs (the P/Invoke stub INTEGRATION.md hands to a bepuphysics2 maintainer; not compilable here) must not drift from
+    the header: one [DllImport] per exported function, same argument count."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bepucuda.h")).read(), flags=re.S)
+    cs = open(os.path.join(ROOT, "integration", "csharp", "BepuCuda.cs")).read()
+    declared = {m.group(1): m.group(2) for m in re.finditer(r"\b(bepucuda_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", header) if m.group(1) != "bepucuda_exchange_fn"}
+    bound = {m.group(1): m.group(2) for m in re.finditer(r"extern\s+\w+\s+(bepucuda_[a-z_0-9]+)\s*\(([^)]*)\)", cs)}
+    assert sorted(declared) == sorted(bound)
+    count = lambda args: 0 if args.strip() in ("", "void") else args.count(",") + 1
+    for name in declared:
+        assert count(declared[name]) == count(bound[name]), "%s: %d C parameters vs %d in the C# binding" % (name, count(declared[name]), count(bound[name]))

@@ -29,6 +29,8 @@ BEPU_DI void grid_barrier(unsigned int* counter, unsigned int target) {
 
 BEPU_DI bool is_constraint_stage(int stage) { return stage <= kStageIncremental; }
 
+// The kernel itself is only compiled in its own unit (bepu_dataflow.cuh includes this header for the barrier helpers).
+#if !defined(BEPU_UNIT) || BEPU_UNIT == 4
 template <int STAGE>
 BEPU_DI void run_constraint_op(const StageOp& op, const WorkRecord* __restrict__ records, bool prefetched, const WorkRecord& rec0, uint32_t enc0, uint32_t enc1, int first_item, int stride,
                                int lane, const BodyBuffers& B, const FrameParams& fp) {
@@ -109,5 +111,7 @@ static int launch_persistent(const StageOp* program, int op_count, const WorkRec
     void* args[] = {(void*)&program, (void*)&op_count, (void*)&records, (void*)&kinematics, (void*)&Bc, (void*)&fp, (void*)&barrier_counter};
     return (int)cudaLaunchCooperativeKernel((const void*)persistent_solve_kernel, dim3(grid), dim3(kPersistentThreads), args, 0, s);
 }
+
+#endif
 
 }  // namespace BEPU_NS

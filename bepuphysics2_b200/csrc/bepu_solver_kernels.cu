@@ -43,15 +43,7 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (launch_flags & bepucuda::kLaunchPdl) ? 1 : 0;
-    static int lookahead = 0;  // warps of this kernel resident at once
-    if (lookahead == 0) {
-        int device = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&device);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, constraint_stage_kernel<STAGE, MINB>, kStageBlockThreads, 0);
-        lookahead = sms * (per_sm > 0 ? per_sm : 1) * (kStageBlockThreads / 32);
-    }
-    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0, lookahead);
+    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0);
 }
 template <int STAGE>
 static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {

@@ -329,17 +329,9 @@ constexpr int kStageBlockThreads = BEPU_STAGE_BLOCK_THREADS;
 // body references (immutable during a solve) always, and -- when the host says so (kStagePrefetchRows: the predecessor is neither the incremental
 // contact update, which rewrites depth rows, nor a stage of this same batch, which rewrites these impulses) -- the whole row block. That takes the
 // bulk copy's latency off the critical path; after the wait only the body gather, the math and the scatter remain.
-//
-// Deep batches (MINB > 1: several waves of CTAs per launch) additionally run a helper prefetch chain for the CTAs that will occupy this slot later
-// (`lookahead` = warps resident at once; CTAs are dispatched in index order as slots free up): the work record of warp w + 3·lookahead is pulled into
-// L2, the record of w + 2·lookahead (an L2 hit thanks to the warp that ran one lookahead earlier) yields the address of its body references, which
-// are pulled into L2, and the references of w + lookahead (again an L2 hit) yield the body records that warp will gather, which are pulled into L2.
-// A later warp then finds its three dependent loads (record → references → body records) in L2 instead of paying three DRAM round trips.
 constexpr int kStagePrefetchRows = 1;
-BEPU_DI void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int STAGE, int MINB>
-__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags,
-                                                                                     int lookahead) {
+__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags) {
     constexpr bool kStaged = STAGE != kStageIncremental;
     constexpr int kWarps = kStageBlockThreads / 32;
     __shared__ __align__(128) float slab[kStaged ? kWarps * kStageSlabRows * kLanes : 1];
@@ -372,18 +364,6 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
         enc0 = ldg_nc_u32(rec.refs + lane);
         enc1 = ldg_nc_u32(rec.refs + kLanes + lane);
     }
-    // helper chain for later warps (deep batches only); the loads are consumed after this warp's own work
-    constexpr bool kHelper = MINB > 1 && STAGE != kStageIncremental;
-    const int32_t* refs_ahead1 = nullptr;
-    const int32_t* refs_ahead2 = nullptr;
-    if constexpr (kHelper) {
-        if (active) {
-            const long long w1 = (long long)warp + lookahead, w2 = w1 + lookahead, w3 = w2 + lookahead;
-            if (w3 < work_count && lane == 0) prefetch_l2_line(records + w3);
-            if (w2 < work_count) refs_ahead2 = load_record(records + w2).refs;
-            if (w1 < work_count) refs_ahead1 = load_record(records + w1).refs;
-        }
-    }
     const FrameParams fp = *fpp;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
@@ -397,23 +377,6 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
         }
         __syncwarp();
         run_bundle_rows<STAGE>(rec, lane, StagedRows{slab_addr + lane * 4, bar}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp);
-        if constexpr (kHelper) {
-            if (refs_ahead2 != nullptr && lane < 2) prefetch_l2_line(refs_ahead2 + lane * kLanes);  // first two body-reference rows of w + 2·lookahead
-            if (refs_ahead1 != nullptr) {
-                const uint32_t a0 = ldg_nc_u32(refs_ahead1 + lane), a1 = ldg_nc_u32(refs_ahead1 + kLanes + lane);
-                if ((int32_t)a0 != kRefEmpty) {
-                    const size_t i0 = a0 & kRefIndexMask;
-                    prefetch_l2_line(B.velocity + 2 * i0);
-                    prefetch_l2_line(B.inertia_world + 2 * i0);
-                    // the second reference row belongs to the next bundle for one-body types: a harmless extra prefetch of a real body
-                    if ((int32_t)a1 != kRefEmpty && (a1 & kRefIndexMask) < (uint32_t)B.count) {
-                        const size_t i1 = a1 & kRefIndexMask;
-                        prefetch_l2_line(B.velocity + 2 * i1);
-                        prefetch_l2_line(B.inertia_world + 2 * i1);
-                    }
-                }
-            }
-        }
     } else {
         run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
     }

@@ -281,7 +281,10 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line; NCCL's version/debug banner goes to stderr
+        # stdout carries exactly one JSON line: NCCL_DEBUG=VERSION (set on the GPU boxes) prints a banner to stdout, WARN does not; other levels go to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     mode = {"graph": EXEC_GRAPH, "persistent": EXEC_PERSISTENT, "stream": EXEC_STREAM, "dataflow": EXEC_DATAFLOW}[args.mode]
 

@@ -635,6 +635,18 @@ def joint_zoo(body_count=2000, per_type=200, seed=5, kinematic_fraction=0.05, ty
     return {"bodies": bodies, "constraints": constraints, "description": "joint zoo: %d bodies, %d constraints of %d types" % (n, total, len(constraints))}
 
 
+def merge(*parts):
+    """Concatenates scenes into one (body handles of later parts are shifted): independent islands in one simulation, so one solve exercises every
+    constraint type, kinematic partners and unconstrained bodies together."""
+    bodies, constraints, offset = [], [], 0
+    for part in parts:
+        bodies.append(part["bodies"])
+        for type_id, handles, prestep in part["constraints"]:
+            constraints.append((type_id, (handles + offset).astype(np.int32), prestep))
+        offset += part["bodies"].shape[0]
+    return {"bodies": np.concatenate(bodies), "constraints": constraints, "description": " + ".join(p.get("description", "?") for p in parts)}
+
+
 def build(scene, simulation):
     """Adds a scene to a host Simulation (Bodies.Add, then Solver.Add per constraint in list order)."""
     simulation.add_bodies(scene["bodies"])

@@ -208,3 +208,24 @@ def test_edge_cases_no_constraints_single_body_and_per_substep_iteration_schedul
     one = scenes.joint_zoo(2, 1, seed=3, kinematic_fraction=0.0, types=[44])  # one one-body servo on one of two bodies
     _parity(one, mode=mode, substeps=2, velocity_iterations=1, frames=2)
     _parity(scenes.shape_pile(300, seed=2), mode=mode, substeps=3, velocity_iterations=[2, 0, 1], frames=2)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_mixed_scenes_bit_exact(libs, seed):
+    """Seeded random combinations: a pile (convex + nonconvex contacts), ragdolls, the joint zoo and free bodies merged into one simulation; random
+    substep count, per-substep iteration schedule, host bundle width, fallback threshold, angular integration mode and execution mode."""
+    rng = np.random.default_rng(1000 + seed)
+    parts = [scenes.shape_pile(int(rng.integers(200, 900)), seed=int(rng.integers(1, 99)), nonconvex_fraction=float(rng.choice([0.0, 0.4]))),
+             scenes.ragdolls(int(rng.integers(3, 12)), seed=int(rng.integers(1, 99)), motor=str(rng.choice(["motor", "servo"]))),
+             scenes.joint_zoo(int(rng.integers(150, 400)), int(rng.integers(8, 30)), seed=int(rng.integers(1, 99))),
+             {"bodies": scenes.make_bodies(rng.uniform(-5, 5, size=(5, 3)).astype(np.float32) + 200, linear=rng.uniform(-1, 1, size=(5, 3)).astype(np.float32),
+                                           angular=rng.uniform(-1, 1, size=(5, 3)).astype(np.float32), inverse_mass=np.ones(5, dtype=np.float32),
+                                           inverse_inertia=np.tile(np.array([[1, 0, 2, 0, 0, 3]], dtype=np.float32), (5, 1))), "constraints": []}]
+    scene = scenes.merge(*parts)
+    substeps = int(rng.integers(1, 5))
+    iterations = [int(x) for x in rng.integers(1, 4, size=substeps)]
+    integ = util.bp.IntegratorDesc.default()
+    integ.angular_integration_mode = int(rng.integers(0, 3))
+    integ.allow_substeps_for_unconstrained = int(rng.integers(0, 2))
+    _parity(scene, mode=int(rng.choice([EXEC_GRAPH, EXEC_STREAM, EXEC_PERSISTENT, EXEC_DATAFLOW])), bundle_width=int(rng.choice([4, 8, 16])),
+            fallback_batch_threshold=int(rng.choice([6, 64])), substeps=substeps, velocity_iterations=iterations, integrator=integ, frames=2)

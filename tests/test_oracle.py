@@ -124,3 +124,15 @@ def test_fallback_batch_runs_sequentially(libs):
     a = util.run_oracle(util.make_sim(scene, fallback_batch_threshold=4, substeps=2, velocity_iterations=2), DT, threads=1)
     b = util.run_oracle(util.make_sim(scene, fallback_batch_threshold=4, substeps=2, velocity_iterations=2), DT, threads=4)
     util.compare(a, b, exact=True)
+
+
+def test_merged_scene_islands_evolve_independently(libs):
+    """scenes.merge puts independent islands into one simulation; each island must evolve exactly as it does alone (batching interleaves them, the
+    arithmetic per constraint and per body does not change)."""
+    pile, dolls = scenes.shape_pile(400, seed=3), scenes.ragdolls(5, seed=4)
+    alone_a = util.run_oracle(util.make_sim(pile, substeps=2, velocity_iterations=2), DT, frames=2)["bodies"]
+    alone_b = util.run_oracle(util.make_sim(dolls, substeps=2, velocity_iterations=2), DT, frames=2)["bodies"]
+    both = util.run_oracle(util.make_sim(scenes.merge(pile, dolls), substeps=2, velocity_iterations=2), DT, frames=2)["bodies"]
+    n = alone_a.shape[0]
+    assert np.array_equal(both[:n, util.MOTION], alone_a[:, util.MOTION])
+    assert np.array_equal(both[n:, util.MOTION], alone_b[:, util.MOTION])

@@ -274,18 +274,117 @@ void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
     if (n == 0) return;
     fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, v);
 }
-void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
-                      int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
-                      int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s) {
-    if (work_count > 0) {
+void launch_ownership_pass1(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
+                            int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, int32_t* error_flag, cudaStream_t s) {
+    if (work_count > 0)
         ownership_pass1_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, sync_batch_count, body_count, first_batch,
                                                                                          sync_refcount, sync_mask, error_flag);
+}
+void launch_ownership_rest(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int body_count, const int32_t* first_batch,
+                           const int32_t* sync_refcount, const unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
+                           int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s) {
+    if (work_count > 0) {
         ownership_pass2_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, body_count, first_batch, constrained);
         bundle_flags_pass_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, source_bundle_flags, 0);
         bundle_flags_pass_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, source_bundle_flags, 1);
     }
     if (body_count > 0) check_invariant_kernel<<<blocks_for(body_count, 256), 256, 0, s>>>(body_count, sync_refcount, sync_mask, error_flag);
     if (kinematic_count > 0) mark_kinematics_kernel<<<blocks_for(kinematic_count, 128), 128, 0, s>>>(kinematics, kinematic_count, body_count, constrained, error_flag);
+}
+
+// ---- sharded batches: exchange of the body records one rank wrote in a stage (see bepucuda_set_boundary_bodies) --------------------------------
+// staging = three planes of 8 words per body: velocity | world inertia | pose. A written record carries 1 in a padding word (velocity word 3,
+// inertia / pose word 7); everything else is zero, so an integer sum over ranks reproduces the one writer's bits.
+__global__ void collect_stage_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
+                                     int stage, BodyBuffers B, int32_t* staging) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int nb = bodies_per_type[tb.type_id];
+    const size_t n = (size_t)B.count;
+    for (int s = 0; s < nb; ++s) {
+        const int32_t enc = tb.refs[((size_t)w.bundle * nb + s) * 32 + lane];
+        if (enc < 0 || (enc & kRefKinematicBit)) continue;
+        const size_t idx = (size_t)(enc & kRefIndexMask);
+        int4* out = reinterpret_cast<int4*>(staging);
+        const int4* vel = reinterpret_cast<const int4*>(B.velocity) + 2 * idx;
+        int4 lo = vel[0], hi = vel[1];
+        lo.w = 1;
+        hi.w = 0;
+        out[2 * idx] = lo;
+        out[2 * idx + 1] = hi;
+        if (stage != kStageSolve && ((uint32_t)enc & kRefIntegrateBit)) {
+            const int4* in = reinterpret_cast<const int4*>(B.inertia_world) + 2 * idx;
+            lo = in[0];
+            hi = in[1];
+            hi.w = 1;
+            out[2 * (n + idx)] = lo;
+            out[2 * (n + idx) + 1] = hi;
+            if (stage == kStageWarmStart) {
+                const int4* po = reinterpret_cast<const int4*>(B.pose) + 2 * idx;
+                lo = po[0];
+                hi = po[1];
+                hi.w = 1;
+                out[2 * (2 * n + idx)] = lo;
+                out[2 * (2 * n + idx) + 1] = hi;
+            }
+        }
+    }
+}
+__global__ void apply_stage_kernel(const int32_t* __restrict__ staging, int planes, BodyBuffers B) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)B.count;
+    if (i >= n) return;
+    const int4* in = reinterpret_cast<const int4*>(staging);
+    int4 lo = in[2 * i], hi = in[2 * i + 1];
+    if (lo.w != 0) {
+        lo.w = 0;
+        int4* vel = reinterpret_cast<int4*>(B.velocity) + 2 * i;
+        vel[0] = lo;
+        vel[1] = hi;
+    }
+    if (planes >= 2) {
+        lo = in[2 * (n + i)];
+        hi = in[2 * (n + i) + 1];
+        if (hi.w != 0) {
+            hi.w = 0;
+            int4* iw = reinterpret_cast<int4*>(B.inertia_world) + 2 * i;
+            iw[0] = lo;
+            iw[1] = hi;
+        }
+    }
+    if (planes >= 3) {
+        lo = in[2 * (2 * n + i)];
+        hi = in[2 * (2 * n + i) + 1];
+        if (hi.w != 0) {
+            hi.w = 0;
+            int4* po = reinterpret_cast<int4*>(B.pose) + 2 * i;
+            po[0] = lo;
+            po[1] = hi;
+        }
+    }
+}
+__global__ void widen_u8_kernel(const uint8_t* __restrict__ in, int32_t* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] ? 1 : 0;
+}
+__global__ void narrow_i32_kernel(const int32_t* __restrict__ in, uint8_t* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] != 0 ? 1 : 0;
+}
+void launch_collect_stage(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int stage, const BodyBuffers& B, int32_t* staging,
+                          cudaStream_t s) {
+    if (work_count > 0) collect_stage_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, stage, B, staging);
+}
+void launch_apply_stage(const int32_t* staging, int planes, const BodyBuffers& B, cudaStream_t s) {
+    if (B.count > 0) apply_stage_kernel<<<blocks_for((size_t)B.count, 256), 256, 0, s>>>(staging, planes, B);
+}
+void launch_widen_u8(const uint8_t* in, int32_t* out, size_t n, cudaStream_t s) {
+    if (n) widen_u8_kernel<<<blocks_for(n, 256), 256, 0, s>>>(in, out, n);
+}
+void launch_narrow_i32(const int32_t* in, uint8_t* out, size_t n, cudaStream_t s) {
+    if (n) narrow_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(in, out, n);
 }
 
 }  // namespace bepucuda

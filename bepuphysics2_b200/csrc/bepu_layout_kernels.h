@@ -33,9 +33,17 @@ void launch_chain_rank(const DeviceTypeBatch* tbs, const WorkItem* work, int wor
 void launch_chain_degree(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, const int32_t* body_counter,
                          int32_t* error_flag, cudaStream_t s);
 void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s);
-void launch_ownership(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
-                      int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
-                      int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s);
+void launch_ownership_pass1(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
+                            int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, int32_t* error_flag, cudaStream_t s);
+void launch_ownership_rest(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int body_count, const int32_t* first_batch,
+                           const int32_t* sync_refcount, const unsigned long long* sync_mask, uint8_t* constrained, const int32_t* kinematics, int kinematic_count,
+                           int32_t* error_flag, const TransposeDesc* descs, int W, int32_t* source_bundle_flags, cudaStream_t s);
+// Sharded batches (bepucuda_set_boundary_bodies): pack the body records a stage wrote / write back every valid record / mask conversions.
+void launch_collect_stage(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int stage, const BodyBuffers& B, int32_t* staging,
+                          cudaStream_t s);
+void launch_apply_stage(const int32_t* staging, int planes, const BodyBuffers& B, cudaStream_t s);
+void launch_widen_u8(const uint8_t* in, int32_t* out, size_t n, cudaStream_t s);
+void launch_narrow_i32(const int32_t* in, uint8_t* out, size_t n, cudaStream_t s);
 
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
 constexpr int kLaunchPdl = 1, kLaunchPrefetchRows = 2;

@@ -164,6 +164,10 @@ struct bepucuda_ctx {
     std::vector<int32_t> bundle_live;           // live constraints per work item (parallel to `work`)
     std::vector<WorkRecord> records;            // what the solver kernels read (parallel to `work`)
     std::vector<std::pair<int, int>> batch_work; // per device batch: (begin, count) into work
+    bool exchange_failed = false;
+    bepucuda_exchange_fn exchange = nullptr;    // sharded batches (bepucuda_set_boundary_bodies): all-reduce callback, its user pointer, staging planes
+    void* exchange_user = nullptr;
+    DeviceBuffer exchange_staging;
     int inc_work_begin = 0, inc_work_count = 0;
     int all_work_count = 0;                     // work[0 .. all_work_count) covers every bundle once
     int sync_batch_count = 0, fallback_levels = 0;
@@ -296,6 +300,23 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
                 if (op.work_count > 0) {
                     bool prefetch = op.stage != kStageIncremental && previous != nullptr && previous->stage != kStageIncremental;
                     if (prefetch && previous->stage <= kStageSolve && previous->work_begin == op.work_begin) prefetch = false;
+                    if (ctx->exchange) {
+                        // sharded batches: plain launches, then all ranks learn what this rank's constraints wrote in this stage
+                        ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, 0, s);
+                        ++n;
+                        if (op.stage != kStageIncremental) {
+                            const int planes = op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2);
+                            const size_t words = (size_t)ctx->body_count * 8 * planes;
+                            cudaMemsetAsync(ctx->exchange_staging.ptr, 0, words * 4, s);
+                            launch_collect_stage(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>() + op.work_begin, op.work_count, ctx->bodies_per_type.as<int32_t>(), op.stage,
+                                                 ctx->B, ctx->exchange_staging.as<int32_t>(), s);
+                            if (ctx->exchange(ctx->exchange_user, ctx->exchange_staging.ptr, (int64_t)words, 0, (void*)s) != 0) ctx->exchange_failed = true;
+                            launch_apply_stage(ctx->exchange_staging.as<int32_t>(), planes, ctx->B, s);
+                            n += 2;
+                        }
+                        previous = &op;
+                        break;
+                    }
                     ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0), s);
                     previous = &op;
                     ++n;
@@ -427,7 +448,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     invalidate_graph(ctx);
     DeviceBuffer* bufs[] = {&ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
                             &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
-                            &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev};
+                            &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
     ctx->raw_arena.release();
     ctx->pinned_arena.release();
@@ -817,10 +838,26 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->error_dev.ptr, 0, 4, ctx->stream));
     CK(ctx->source_bundle_flags.reserve((size_t)std::max(total_source_bundles, 1) * 16));
     CK(cudaMemsetAsync(ctx->source_bundle_flags.ptr, 0, (size_t)std::max(total_source_bundles, 1) * 16, ctx->stream));
-    launch_ownership(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), ctx->sync_batch_count,
-                     ctx->body_count, ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (unsigned long long*)ctx->sync_mask.ptr, ctx->constrained.as<uint8_t>(),
-                     ctx->kinematics_dev.as<int32_t>(), (int)ctx->kinematics.size(), ctx->error_dev.as<int32_t>(), ctx->tdesc_table.as<TransposeDesc>(), W,
-                     ctx->source_bundle_flags.as<int32_t>(), ctx->stream);
+    launch_ownership_pass1(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), ctx->sync_batch_count,
+                           ctx->body_count, ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (unsigned long long*)ctx->sync_mask.ptr, ctx->error_dev.as<int32_t>(),
+                           ctx->stream);
+    if (ctx->exchange && nb > 0) {
+        // sharded batches: the integration owner of a body is the lowest batch referencing it on ANY rank
+        if (ctx->exchange(ctx->exchange_user, ctx->first_batch.ptr, (int64_t)ctx->body_count, 1, (void*)ctx->stream) != 0)
+            return fail(ctx, BEPUCUDA_ERR_CUDA, "end_constraints: the exchange callback failed (first-batch minimum)");
+    }
+    launch_ownership_rest(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), ctx->body_count,
+                          ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (const unsigned long long*)ctx->sync_mask.ptr, ctx->constrained.as<uint8_t>(),
+                          ctx->kinematics_dev.as<int32_t>(), (int)ctx->kinematics.size(), ctx->error_dev.as<int32_t>(), ctx->tdesc_table.as<TransposeDesc>(), W,
+                          ctx->source_bundle_flags.as<int32_t>(), ctx->stream);
+    if (ctx->exchange && nb > 0) {
+        // ... and a body is "constrained" (final pose pass) if any rank constrains it
+        CK(ctx->exchange_staging.reserve((size_t)nb * 24 * 4));
+        launch_widen_u8(ctx->constrained.as<uint8_t>(), ctx->exchange_staging.as<int32_t>(), (size_t)ctx->body_count, ctx->stream);
+        if (ctx->exchange(ctx->exchange_user, ctx->exchange_staging.ptr, (int64_t)ctx->body_count, 0, (void*)ctx->stream) != 0)
+            return fail(ctx, BEPUCUDA_ERR_CUDA, "end_constraints: the exchange callback failed (constrained mask)");
+        launch_narrow_i32(ctx->exchange_staging.as<int32_t>(), ctx->constrained.as<uint8_t>(), (size_t)ctx->body_count, ctx->stream);
+    }
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
         // rank of each constraint among its bodies' constraints: one small launch per device batch, in order
         CK(ctx->body_counter.reserve(nb * 4));
@@ -910,6 +947,11 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     ctx->frame_params_host->pass_base = ctx->pass_counter;
     CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
 
+    if (ctx->exchange) {
+        if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_STREAM) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "solve: sharded batches need BEPUCUDA_EXEC_STREAM");
+        if (ctx->integ.angular_integration_mode != 0) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "solve: sharded batches support AngularIntegrationMode.Nonconserving only");
+        ctx->exchange_failed = false;
+    }
     CK(cudaEventRecord(ctx->ev_solve_begin, ctx->stream));
     int64_t launches = 0;
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_PERSISTENT) {
@@ -942,6 +984,7 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     } else {
         issue_stage_sequence(ctx, ctx->stream, &launches);
         CK(cudaGetLastError());
+        if (ctx->exchange_failed) return fail(ctx, BEPUCUDA_ERR_CUDA, "solve: the exchange callback failed");
     }
     CK(cudaEventRecord(ctx->ev_solve_end, ctx->stream));
     ctx->have_solve = true;
@@ -1058,6 +1101,7 @@ int32_t bepucuda_event_elapsed_ms(bepucuda_ctx* ctx, int32_t a, int32_t b, float
 }
 
 int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_profile* out) {
+    if (ctx && ctx->exchange) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages: not available with sharded batches");
     if (!ctx || !out || !(dt > 0)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "profile_stages: bad arguments");
     if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages before end_constraints");
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages: not available in dataflow mode (no per-stage launches)");
@@ -1121,8 +1165,16 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
 }
 
 int32_t bepucuda_set_boundary_bodies(bepucuda_ctx* ctx, const int32_t* body_indices, int32_t count, bepucuda_exchange_fn exchange, void* user) {
-    (void)body_indices; (void)count; (void)exchange; (void)user;
-    return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "set_boundary_bodies: cross-device constraint graphs are not supported yet; shard independent islands across contexts");
+    if (!ctx || count < 0) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_boundary_bodies: bad arguments");
+    (void)body_indices;  // every body is treated as possibly shared (see the header)
+    if (ctx->constraints_open) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "set_boundary_bodies inside begin/end_constraints");
+    if (exchange && ctx->cfg.execution_mode != BEPUCUDA_EXEC_STREAM)
+        return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "set_boundary_bodies: sharded batches need a context created with BEPUCUDA_EXEC_STREAM");
+    ctx->exchange = exchange;
+    ctx->exchange_user = user;
+    // ownership and the constrained mask depend on it: the constraint description has to be (re)built
+    if (ctx->constraints_ready && !ctx->sources.empty()) ctx->constraints_ready = false;
+    return BEPUCUDA_OK;
 }
 
 }  // extern "C"

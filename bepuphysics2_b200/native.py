@@ -98,6 +98,9 @@ C_ABI_SYMBOLS = [
 ]
 
 
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
+
+
 def load_libraries():
     """Loads libbepucuda.so and libbepuhost.so from the package directory. Fails loudly if they are missing: there is no fallback."""
     global _LIBS
@@ -119,6 +122,7 @@ def load_libraries():
     cuda.bepucuda_type_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     cuda.bepucuda_get_timings.argtypes = [vp, C.POINTER(Timings)]
     cuda.bepucuda_solve.argtypes = [vp, f32]
+    cuda.bepucuda_set_boundary_bodies.argtypes = [vp, vp, i32, EXCHANGE_FN, vp]
     cuda.bepucuda_synchronize.argtypes = [vp]
     cuda.bepucuda_set_solve_description.argtypes = [vp, i32, C.POINTER(i32), i32]
     cuda.bepucuda_set_integrator.argtypes = [vp, C.POINTER(IntegratorDesc)]
@@ -319,6 +323,27 @@ class CudaTimestepper:
         """Page-locks the simulation's buffers (a C# host would register its BufferPool blocks once)."""
         self._check(self._host.bepuhost_cuda_register_buffers(self.sim._sim, self._ctx))
         self._registered = True
+
+    def set_exchange(self, callback):
+        """Sharded batches (bepucuda_set_boundary_bodies): `callback(device_pointer, word_count, op, cuda_stream) -> int` must combine `word_count` int32
+        words at `device_pointer` across all ranks in place (op 0 = sum, 1 = min) as stream-ordered work on `cuda_stream`. None switches it off.
+        Call before describe()."""
+        if callback is None:
+            self._exchange_cb = None
+            self._check(self._cuda.bepucuda_set_boundary_bodies(self._ctx, None, 0, None, None))
+            return
+
+        def trampoline(user, words, count, op, stream):
+            try:
+                return int(callback(words, count, op, stream) or 0)
+            except Exception:  # never unwind through the C frame
+                import traceback
+
+                traceback.print_exc()
+                return -1
+
+        self._exchange_cb = EXCHANGE_FN(trampoline)  # keep the thunk alive
+        self._check(self._cuda.bepucuda_set_boundary_bodies(self._ctx, None, 0, self._exchange_cb, None))
 
     def describe(self):
         """Uploads bodies + every type batch and rebuilds device topology (call after any add/remove)."""

@@ -173,11 +173,21 @@ typedef struct bepucuda_stage_profile {
 } bepucuda_stage_profile;
 int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_profile* out);
 
-/* Multi-GPU (no reference counterpart). One context per rank/GPU, one process per GPU. Marks which
- * local bodies are replicated on other ranks ("boundary bodies") and installs an exchange callback invoked on the
- * context stream after every (batch, stage) that wrote a boundary body. The callback runs host-side stream-ordered
- * work (e.g. enqueues an NCCL all-reduce of `count` floats at `delta` on `cuda_stream`); it must not block. */
-typedef int32_t (*bepucuda_exchange_fn)(void* user, void* delta, int64_t count, void* cuda_stream);
+/* Multi-GPU, one constraint graph over several contexts (replaces the reference's multithreaded batch dispatch,
+ * Solver_Solve.cs:L458-654, where workers split the constraints of a batch). Every participating context ("rank": one per GPU, normally one per
+ * process) is given the WHOLE body set and the same batch layout, but only its share of the constraints (lanes of other ranks are empty, body
+ * reference -1). Within a batch no dynamic body is referenced twice, so exactly one rank writes a given body in a given (batch, stage); after every
+ * WarmStart / Solve stage the library packs the records this rank wrote (velocity; pose and world inertia too when the lane integrated) into a
+ * zero-initialised staging buffer with a "valid" word, calls `exchange` to all-reduce it, and writes every valid record back, which keeps all
+ * ranks' body arrays bit-identical to a single-context solve. At bepucuda_end_constraints the per-body integration owner (lowest batch referencing
+ * the body) and the constrained-body mask are combined the same way.
+ *   exchange(user, device_words, count, op, cuda_stream): combine `count` int32 words at `device_words` element-wise across all ranks, in place, as
+ *   stream-ordered work on `cuda_stream` (e.g. ncclAllReduce with ncclInt32 and ncclSum for op 0 / ncclMin for op 1); return 0, or non-zero to fail
+ *   the call that invoked it. With op 0 at most one rank contributes a non-zero word, so an integer sum transports bit patterns exactly.
+ * Requirements: BEPUCUDA_EXEC_STREAM, AngularIntegrationMode.Nonconserving; call before bepucuda_begin_constraints. `body_indices` / `count` name the
+ * bodies other ranks may also reference; NULL / 0 means "all of them" (the only form implemented: the list is accepted and ignored).
+ * Passing exchange = NULL returns the context to single-rank operation. */
+typedef int32_t (*bepucuda_exchange_fn)(void* user, void* device_words, int64_t count, int32_t op, void* cuda_stream);
 int32_t bepucuda_set_boundary_bodies(bepucuda_ctx* ctx, const int32_t* body_indices, int32_t count,
                                      bepucuda_exchange_fn exchange, void* user);
 

@@ -33,7 +33,7 @@ namespace BepuCuda
     }
 
     [UnmanagedFunctionPointer(CallingConvention.Cdecl)]
-    public unsafe delegate int ExchangeFn(void* user, void* delta, long count, void* cudaStream);
+    public unsafe delegate int ExchangeFn(void* user, void* deviceWords, long count, int op, void* cudaStream);
 
     public static unsafe class Native
     {

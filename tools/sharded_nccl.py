@@ -56,8 +56,13 @@ calls = [0]
 
 def exchange(ptr, count, op, stream):
     t = torch.as_tensor(Raw(ptr, count), device="cuda")
-    with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+    if os.environ.get("SHARDED_SYNC"):
+        torch.cuda.synchronize()
         dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MIN)
+        torch.cuda.synchronize()
+    else:
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MIN)
     calls[0] += 1
     return 0
 
@@ -72,6 +77,8 @@ for f in range(args.frames):
         ts.refresh()
     ts.solve(1 / 60.0, download=True)
     ms.append(ts.timings().solve_ms)
+    if args.check:
+        ts.download_prestep()  # contact depths advance on the device (IncrementallyUpdateForSubstep); the oracle mutates them in place too
 ts.close()
 ok = True
 if args.check:
@@ -79,6 +86,10 @@ if args.check:
     want = util.run_oracle(ref, 1 / 60.0, frames=args.frames, threads=8, simd=True)["bodies"]
     cols = util.MOTION
     ok = bool(np.array_equal(want[:, cols].view(np.uint32), sim.bodies[:, cols].view(np.uint32)))
+    if not ok:
+        bad = np.flatnonzero((want[:, cols].view(np.uint32) != sim.bodies[:, cols].view(np.uint32)).any(axis=1))
+        d = np.abs(want[:, cols].astype(np.float64) - sim.bodies[:, cols].astype(np.float64))
+        print("rank %d: %d of %d bodies differ (first %s, last %s), max abs diff %.3e, slab boundary at %d" % (rank, bad.size, n, bad[:5], bad[-5:], d.max(), n // world), flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 t = torch.tensor([float(np.mean(ms[1:] if len(ms) > 1 else ms))], device="cuda")

@@ -27,10 +27,12 @@ int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord*
 constexpr int kDeepBatchBundles = 2400;  // more bundles than the uncapped build keeps resident at once (148 SMs x 16 warps)
 template <int STAGE, int MINB>
 static void launch_stage_variant(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
-    static bool carveout_set = false;
-    if (!carveout_set) {  // the staged stages keep one 6 KB slab per resident warp in shared memory
+    static bool carveout_set[64] = {};  // function attributes are per device: a process may hold contexts on several
+    int device = 0;
+    cudaGetDevice(&device);
+    if (!carveout_set[device & 63]) {  // the staged stages keep one 6 KB slab per resident warp in shared memory
         cudaFuncSetAttribute(constraint_stage_kernel<STAGE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
+        carveout_set[device & 63] = true;
     }
     const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
     cudaLaunchConfig_t cfg{};

@@ -136,3 +136,21 @@ def test_merged_scene_islands_evolve_independently(libs):
     n = alone_a.shape[0]
     assert np.array_equal(both[:n, util.MOTION], alone_a[:, util.MOTION])
     assert np.array_equal(both[n:, util.MOTION], alone_b[:, util.MOTION])
+
+
+def test_oracle_output_is_stable_across_rounds(libs):
+    """tests/golden/oracle_hashes.json (made by tests/golden/make_oracle_hashes.py) pins the checker to itself: every GPU parity test leans on the
+    oracle, so a silent change to it must fail here first."""
+    import json
+    import os
+    import sys
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import make_oracle_hashes as m
+
+    with open(os.path.join(here, "oracle_hashes.json")) as f:
+        want = json.load(f)
+    assert sorted(want) == sorted(m.CASES)
+    for name in m.CASES:
+        assert m.digest(name) == want[name], "oracle output changed for %s" % name

@@ -409,7 +409,7 @@ def main():
             if "solve_kernel_algorithmic_gbs" in large:
                 large["roofline_frac_solve_kernel"] = large["solve_kernel_algorithmic_gbs"] / peak
             line["large_scene"] = large
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             cb = cpu_reference_run(args, steps=3, warmup=1, threads=args.cpu_threads)
             c1 = cpu_reference_run(args, steps=1, warmup=0, threads=1)  # the reference's own benchmarks run single-threaded (ShapePileBenchmark.cs:L228)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "constraint-iterations/s", "cores": cb["cores"], "kind": "port",

@@ -45,10 +45,12 @@ def _bodies(count):
     return scenes.make_bodies(pos, orientation=orient, linear=lin, angular=ang, inverse_mass=np.array([1.0, 0.7, 1.3, 0.9], dtype=np.float32)[:count], inverse_inertia=inertia)
 
 
-def _run(type_id, prestep, body_count, frames=240, substeps=4):
+def _run(type_id, prestep, body_count, frames=240, substeps=4, angular_damping=0.0):
     handles = np.arange(body_count, dtype=np.int32)[None, :]
     scene = {"bodies": _bodies(body_count), "constraints": [(type_id, handles, np.asarray([prestep], dtype=np.float32))]}
-    sim = util.make_sim(scene, substeps=substeps, velocity_iterations=2, integrator=_still())
+    integ = _still()
+    integ.angular_damping = angular_damping
+    sim = util.make_sim(scene, substeps=substeps, velocity_iterations=2, integrator=integ)
     for _ in range(frames):
         util.ob.solve(sim, DT)
     b = sim.bodies.astype(np.float64)
@@ -206,3 +208,66 @@ def test_joint_zoo_scalar_and_simd_are_bit_identical(libs):
     a = util.run_oracle(util.make_sim(scene, substeps=2, velocity_iterations=2), DT, frames=2, simd=False)
     b = util.run_oracle(util.make_sim(scene, substeps=2, velocity_iterations=2), DT, frames=2, simd=True)
     util.compare(a, b, exact=True)
+
+
+# ---- the ragdoll joint set (types 22, 25-27, 29, 30, 46, 47): the same kind of independent known answers ---------------------------------------
+def _qcat64(a, b):
+    return scenes.qcat(np.asarray(a, dtype=np.float64)[None, :], np.asarray(b, dtype=np.float64)[None, :])[0].astype(np.float64)
+
+
+def _twist_angle(a, b, basis_a, basis_b):
+    """Signed twist of B's basis about the shared Z axis relative to A's, measured like TwistServoFunctions.ComputeCurrentAngle but in float64:
+    rotate B's basis so its Z meets A's Z by the shortest arc, then the angle of B's X in A's XY plane."""
+    qa, qb = _qcat64(basis_a, a["q"]), _qcat64(basis_b, b["q"])
+    ax, ay, az = _rot([1, 0, 0], qa), _rot([0, 1, 0], qa), _rot([0, 0, 1], qa)
+    bx, bz = _rot([1, 0, 0], qb), _rot([0, 0, 1], qb)
+    axis = np.cross(bz, az)
+    s, c = np.linalg.norm(axis), np.dot(bz, az)
+    if s > 1e-12:
+        k = axis / s
+        ang = math.atan2(s, c)
+        bx = bx * math.cos(ang) + np.cross(k, bx) * math.sin(ang) + k * np.dot(k, bx) * (1 - math.cos(ang))  # Rodrigues
+    return math.atan2(np.dot(bx, ay), np.dot(bx, ax))
+
+
+def test_ball_socket_hinge_and_swivel_hinge_geometry(libs):
+    oa, ob_ = [0.5, 0.1, 0], [-0.4, 0.2, 0.1]
+    a, b = _run(22, np.r_[oa, ob_, SPRING], 2)
+    assert np.linalg.norm(_anchor(a, oa) - _anchor(b, ob_)) < 2e-3
+    ha, hb = np.array([0, 1, 0.0]), np.array([1, 0, 0.0])
+    a, b = _run(47, np.r_[oa, ha, ob_, hb, SPRING], 2)
+    assert np.linalg.norm(_anchor(a, oa) - _anchor(b, ob_)) < 3e-3
+    assert np.dot(_rot(ha, a["q"]), _rot(hb, b["q"])) > 1 - 1e-4
+    a, b = _run(46, np.r_[oa, ha, ob_, hb, SPRING], 2)
+    assert np.linalg.norm(_anchor(a, oa) - _anchor(b, ob_)) < 3e-3
+    assert abs(np.dot(_rot(ha, a["q"]), _rot(hb, b["q"]))) < 3e-3
+
+
+def test_swing_limit_keeps_axes_within_the_cone(libs):
+    axis_a, axis_b = np.array([0, 1, 0.0]), np.array([1, 0, 0.0])  # the bodies of _bodies() start ~90 degrees apart in these axes
+    min_dot = math.cos(0.5)
+    # an inequality with undamped bodies just bounces off the cone; with some angular damping the pair settles inside it
+    a, b = _run(25, np.r_[axis_a, axis_b, [min_dot], SPRING], 2, angular_damping=0.5)
+    assert np.dot(_rot(axis_a, a["q"]), _rot(axis_b, b["q"])) > min_dot - 5e-3
+
+
+def test_twist_servo_and_limit_control_the_twist_angle(libs):
+    basis = scenes.basis_quaternion([0, 0, 1], [1, 0, 0])
+    # Only the twist is constrained, so the two Z axes are free to swing apart (in a ragdoll a SwingLimit holds them together) and the twist
+    # measure degenerates once they oppose each other: check while they are still roughly aligned.
+    a, b = _run(26, np.r_[basis, basis, [0.7], SPRING, SERVO], 2, frames=12)
+    assert np.dot(_rot([0, 0, 1], a["q"]), _rot([0, 0, 1], b["q"])) > 0.5
+    assert _twist_angle(a, b, basis, basis) == pytest.approx(0.7, abs=5e-3)
+    a, b = _run(27, np.r_[basis, basis, [-0.2, 0.1], SPRING], 2, frames=12)
+    assert np.dot(_rot([0, 0, 1], a["q"]), _rot([0, 0, 1], b["q"])) > 0.5
+    assert -0.2 - 5e-3 <= _twist_angle(a, b, basis, basis) <= 0.1 + 5e-3
+
+
+def test_angular_servo_and_motor(libs):
+    target = _q([0, 0, 1], 0.8)
+    a, b = _run(29, np.r_[target, SPRING, SERVO], 2)
+    want = _qcat64(target, a["q"])  # TargetRelativeRotationLocalA * orientationA
+    assert abs(abs(np.dot(want, b["q"])) - 1) < 1e-5
+    w = [0.4, -0.6, 0.2]
+    a, b = _run(30, np.r_[w, MOTOR], 2, frames=20)
+    assert np.allclose(a["w"] - b["w"], _rot(w, a["q"]), atol=2e-2)

@@ -154,3 +154,60 @@ def test_oracle_output_is_stable_across_rounds(libs):
     assert sorted(want) == sorted(m.CASES)
     for name in m.CASES:
         assert m.digest(name) == want[name], "oracle output changed for %s" % name
+
+
+def _inactive(scene):
+    """The same constraint graph with every contact far out of reach (depth -100): the constraints apply nothing, but their batches still decide
+    which lane integrates which body."""
+    out = {"bodies": scene["bodies"].copy(), "constraints": [], "description": scene.get("description", "")}
+    for type_id, handles, pre in scene["constraints"]:
+        pre = pre.copy()
+        assert type_id <= 7  # convex manifolds: depth rows are 4 i + 3
+        contacts = type_id % 4 + 1
+        for i in range(contacts):
+            pre[:, 4 * i + 3] = -100.0
+        out["constraints"].append((type_id, handles, pre))
+    return out
+
+
+@pytest.mark.parametrize("name,substeps", [("pile", 1), ("pile", 5), ("fallback", 3)])
+def test_every_body_is_integrated_exactly_once_per_substep(libs, name, substeps):
+    """The invariant of the reference's commented-out validators (Solver_Solve.cs:L1298-1361): across the batches' integration responsibilities,
+    the kinematic prepass and IntegrateAfterSubstepping, every dynamic body gets exactly one velocity integration and one pose integration per
+    substep — whatever batch it was first seen in, fallback batch included. With constraints that apply nothing, every constrained body must
+    then match the closed-form trajectory (float64); a body integrated twice or never is off by g * dt_substep."""
+    if name == "pile":
+        scene = _inactive(scenes.shape_pile(3000, seed=11))
+    else:
+        scene = _inactive(scenes.fallback_stress(1500, hubs=2, seed=11))
+    rng = np.random.default_rng(3)
+    n = scene["bodies"].shape[0]
+    dynamic = scene["bodies"][:, 22] > 0
+    scene["bodies"][:, 8:11] = np.where(dynamic[:, None], rng.normal(0, 1, (n, 3)), 0).astype(np.float32)
+    before = scene["bodies"].astype(np.float64)
+    sim = util.make_sim(scene, substeps=substeps, velocity_iterations=2)
+    assert max(tb.batch_index for tb in sim.type_batches()) >= (64 if name == "fallback" else 4)  # 64 = the sequential fallback batch
+    constrained = np.zeros(n, dtype=bool)
+    for tb in sim.type_batches():
+        refs = tb.body_references
+        constrained[(refs[refs >= 0] & 0x3FFFFFFF)] = True
+    util.ob.solve(sim, DT)
+    h = DT / substeps
+    damp = 0.97 ** h
+    v = before[:, 8:11].copy()
+    p = before[:, 4:7].copy()
+    for _ in range(substeps):
+        v = (v + np.array([0, -10.0 * h, 0])) * damp
+        p = p + v * h
+    sel = constrained & dynamic
+    assert sel.sum() > 0.9 * dynamic.sum()
+    after = sim.bodies.astype(np.float64)
+    # (a wrong integration count is off by |g| * h = 0.03 .. 0.17 in velocity)
+    assert np.abs(after[sel, 8:11] - v[sel]).max() < 2e-5
+    assert np.abs(after[sel, 4:7] - p[sel]).max() < 2e-5 * max(1.0, np.abs(p).max())
+    # unconstrained dynamic bodies take one full-length step (AllowSubstepsForUnconstrainedBodies = false, PoseIntegrator.cs:L537-693)
+    free = dynamic & ~constrained
+    if free.any():
+        vf = (before[free, 8:11] + np.array([0, -10.0 * DT, 0])) * 0.97 ** DT
+        assert np.abs(after[free, 8:11] - vf).max() < 2e-5
+        assert np.abs(after[free, 4:7] - (before[free, 4:7] + vf * DT)).max() < 2e-5 * max(1.0, np.abs(p).max())

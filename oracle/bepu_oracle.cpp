@@ -10,6 +10,8 @@
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
+#include <sched.h>
+#include <atomic>
 #endif
 
 #include "bepu_contacts.h"
@@ -619,6 +621,29 @@ static void integrate_after_substepping(Solver& s, float dt, int substepCount) {
 }
 
 // ---- the substep loop: Solver_Solve.cs:L1415-1479 ------------------------------------------------------------------
+// Multithreaded shape = the reference's SolveWorker (Solver_Solve.cs:L458-654): every worker walks the same stage list, takes its share of
+// the stage's bundles and meets the others at a spinning sync point between stages; the fallback batch runs on worker 0 (L546-583).
+struct StageBarrier {
+    std::atomic<int> arrived{0};
+    std::atomic<int> epoch{0};
+    int count = 1;
+    void wait() {
+        if (count == 1) return;
+        const int e = epoch.load(std::memory_order_acquire);
+        if (arrived.fetch_add(1, std::memory_order_acq_rel) == count - 1) {
+            arrived.store(0, std::memory_order_relaxed);
+            epoch.store(e + 1, std::memory_order_release);
+            return;
+        }
+        for (int spins = 0; epoch.load(std::memory_order_acquire) == e; ++spins) {
+            if (spins < 4096)
+                __builtin_ia32_pause();
+            else
+                sched_yield();  // oversubscribed host: let the thread we are waiting for run
+        }
+    }
+};
+
 template <class F> static void run_solve(Solver& s, float totalDt) {
     oracle_scene& sc = *s.sc;
     const int W = sc.bundle_width;
@@ -627,9 +652,19 @@ template <class F> static void run_solve(Solver& s, float totalDt) {
     float substepDt = totalDt / substepCount;
     s.cb.prepare(substepDt);
     float inverseDt = 1.0f / substepDt;
-    const int threads = sc.threads > 0 ? sc.threads : 1;
+    // team size the OpenMP runtime really grants (OMP_THREAD_LIMIT, nesting)
+    int workers = sc.threads > 0 ? sc.threads : 1;
+    if (workers > 1) {
+        int granted = 1;
+#pragma omp parallel num_threads(workers)
+        {
+#pragma omp single
+            granted = omp_get_num_threads();
+        }
+        workers = granted;
+    }
 
-    // flattened (typeBatch, bundle) work lists per batch for the parallel driver
+    // flattened (typeBatch, bundle) work lists per batch
     struct Work { int t, bundle; };
     std::vector<std::vector<Work>> work(sc.batch_count);
     for (int b = 0; b < sc.batch_count; ++b)
@@ -638,56 +673,78 @@ template <class F> static void run_solve(Solver& s, float totalDt) {
             for (int k = 0; k < bundles; ++k) work[b].push_back({t, k});
         }
 
-    for (int substep = 0; substep < substepCount; ++substep) {
-        if (substep > 0) {
-            for (int b = 0; b < sc.batch_count; ++b) {
-                const int n = (int)work[b].size();
-#pragma omp parallel for schedule(static) num_threads(threads)
-                for (int i = 0; i < n; ++i) {
-                    oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
-                    const TypeOps<F>& ops = reg.ops[tb.type_id];
-                    if (ops.incremental) incremental_bundle<F>(s, ops, tb, work[b][i].bundle, substepDt);
-                }
-            }
-            integrate_kinematic_poses_and_velocities(s, substepDt);
-        } else if (s.cb.integrate_kinematic_velocity) {
-            integrate_kinematic_velocities(s);
-        }
-        for (int b = 0; b < sc.batch_count; ++b) {
+    StageBarrier barrier;
+    barrier.count = workers;
+    auto worker = [&](const int worker_index) {
+        // this worker's share of batch b: a contiguous block of bundles; the sequential fallback batch belongs to worker 0
+        auto share = [&](int b, int& begin, int& end) {
             const int n = (int)work[b].size();
-            const bool sequential = b >= sc.fallback_batch_threshold || threads == 1;
-            if (sequential) {
-                for (int i = 0; i < n; ++i) {
-                    oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
-                    warm_start_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, b, b > 0 ? &s.flags[b][work[b][i].t] : nullptr, substep > 0, substepDt);
-                }
+            if (b >= sc.fallback_batch_threshold) {
+                begin = 0;
+                end = worker_index == 0 ? n : 0;
             } else {
-#pragma omp parallel for schedule(static) num_threads(threads)
-                for (int i = 0; i < n; ++i) {
+                begin = (int)((int64_t)n * worker_index / workers);
+                end = (int)((int64_t)n * (worker_index + 1) / workers);
+            }
+        };
+        int begin, end;
+        for (int substep = 0; substep < substepCount; ++substep) {
+            if (substep > 0) {
+                for (int b = 0; b < sc.batch_count; ++b) {  // contact depths only read velocities: no sync between batches
+                    const int n = (int)work[b].size();
+                    begin = (int)((int64_t)n * worker_index / workers);
+                    end = (int)((int64_t)n * (worker_index + 1) / workers);
+                    for (int i = begin; i < end; ++i) {
+                        oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
+                        const TypeOps<F>& ops = reg.ops[tb.type_id];
+                        if (ops.incremental) incremental_bundle<F>(s, ops, tb, work[b][i].bundle, substepDt);
+                    }
+                }
+                barrier.wait();
+                if (worker_index == 0) integrate_kinematic_poses_and_velocities(s, substepDt);
+                barrier.wait();
+            } else if (s.cb.integrate_kinematic_velocity) {
+                if (worker_index == 0) integrate_kinematic_velocities(s);
+                barrier.wait();
+            }
+            for (int b = 0; b < sc.batch_count; ++b) {
+                share(b, begin, end);
+                for (int i = begin; i < end; ++i) {
                     oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
                     warm_start_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, b, b > 0 ? &s.flags[b][work[b][i].t] : nullptr, substep > 0, substepDt);
                 }
+                barrier.wait();
             }
-        }
-        const int iterations = sc.velocity_iterations[substep];
-        for (int it = 0; it < iterations; ++it) {
-            for (int b = 0; b < sc.batch_count; ++b) {
-                const int n = (int)work[b].size();
-                const bool sequential = b >= sc.fallback_batch_threshold || threads == 1;
-                if (sequential) {
-                    for (int i = 0; i < n; ++i) {
+            const int iterations = sc.velocity_iterations[substep];
+            for (int it = 0; it < iterations; ++it)
+                for (int b = 0; b < sc.batch_count; ++b) {
+                    share(b, begin, end);
+                    for (int i = begin; i < end; ++i) {
                         oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
                         solve_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, substepDt, inverseDt);
                     }
-                } else {
-#pragma omp parallel for schedule(static) num_threads(threads)
-                    for (int i = 0; i < n; ++i) {
-                        oracle_type_batch& tb = sc.batches[b].type_batches[work[b][i].t];
-                        solve_bundle<F>(s, reg.ops[tb.type_id], tb, work[b][i].bundle, substepDt, inverseDt);
-                    }
+                    barrier.wait();
                 }
-            }
         }
+    };
+    if (workers == 1) {
+        worker(0);
+        return;
+    }
+    bool ran = false;
+#pragma omp parallel num_threads(workers)
+    {
+        // every member sees the same team size: either all of them walk the stage list or none does (a short team would hang the sync points)
+        if (omp_get_num_threads() == workers) {
+            worker(omp_get_thread_num());
+#pragma omp master
+            ran = true;
+        }
+    }
+    if (!ran) {
+        workers = 1;
+        barrier.count = 1;
+        worker(0);
     }
 }
 

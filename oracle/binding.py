@@ -30,7 +30,7 @@ class OracleScene(C.Structure):
 
 def build(force=False):
     lib = os.path.join(HERE, "libbepu_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("bepu_oracle.cpp", "bepu_oracle.h", "bepu_math.h", "bepu_contacts.h", "bepu_joints.h")]
+    srcs = [os.path.join(HERE, f) for f in ("bepu_oracle.cpp", "bepu_oracle.h", "bepu_math.h", "bepu_contacts.h", "bepu_joints.h", "bepu_joints_more.h")]
     if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         r = subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:

@@ -41,10 +41,12 @@ def test_ragdolls_scalar_and_simd_are_bit_identical(libs):
     util.compare(a, b, exact=True)
 
 
-def test_thread_count_does_not_change_results(libs):
-    scene = scenes.shape_pile(3000, seed=8)
-    a = util.run_oracle(util.make_sim(scene, substeps=3, velocity_iterations=2), DT, threads=1, simd=True)
-    b = util.run_oracle(util.make_sim(scene, substeps=3, velocity_iterations=2), DT, threads=4, simd=True)
+@pytest.mark.parametrize("name,threads", [("pile", 4), ("pile", 3), ("fallback", 3), ("ragdolls", 5)])
+def test_thread_count_does_not_change_results(libs, name, threads):
+    """The worker loop (one share of every batch stage per worker, spin sync between stages, fallback batch on worker 0) against one thread."""
+    scene = {"pile": lambda: scenes.shape_pile(3000, seed=8), "fallback": lambda: scenes.fallback_stress(1500, hubs=2, seed=8), "ragdolls": lambda: scenes.ragdolls(40, seed=8)}[name]()
+    a = util.run_oracle(util.make_sim(scene, substeps=3, velocity_iterations=2), DT, frames=2, threads=1, simd=True)
+    b = util.run_oracle(util.make_sim(scene, substeps=3, velocity_iterations=2), DT, frames=2, threads=threads, simd=True)
     util.compare(a, b, exact=True)
 
 

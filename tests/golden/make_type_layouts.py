@@ -6,7 +6,10 @@ For every constraint type processor the reference declares (`class XTypeProcesso
 TAccumulatedImpulses, ...> { public const int BatchTypeId = N; }`) it records the body count and the FLATTENED, ORDERED scalar field lists of the
 prestep and accumulated-impulse structs (one entry per `Vector<float>` lane row of the AOSOA layout, e.g. "Contact0.OffsetA.X"). This is the layout
 `DemoTests/ConstraintDescriptionMappingTests.cs` round-trips in the reference; tests/test_type_layouts.py pins the oracle / device registries and the
-row orders their code assumes to it. Parsing only: nothing of the reference is copied into the repository except these field names."""
+row orders their code assumes to it. It also records every type's body access filters (the `Access*` generic arguments of the processor
+declaration: WarmStart filters per body, then Solve filters per body) and what each filter gathers / scatters in floats
+(`Constraints/IBodyAccessFilter.cs`): the inputs of the SURVEY.md §8d algorithmic-bytes model that `roofline.achieved` is built on.
+Parsing only: nothing of the reference is copied into the repository except these field and filter names."""
 import json
 import os
 import re
@@ -75,8 +78,34 @@ def flatten(type_name, structs, prefix=""):
     return out
 
 
+def load_filters(texts):
+    """Access filter -> floats gathered (read) and velocity floats scattered (written) per body."""
+    floats = {"GatherPosition": 3, "GatherOrientation": 4, "GatherMass": 1, "GatherInertiaTensor": 6, "AccessLinearVelocity": 3, "AccessAngularVelocity": 3}
+    filters = {}
+    for text in texts:
+        for m in re.finditer(r"struct\s+(Access\w+)\s*:\s*IBodyAccessFilter\s*\{(.*?)\n\s*\}", text, flags=re.S):
+            flags = dict(re.findall(r"public\s+bool\s+(\w+)\s*=>\s*(true|false)", m.group(2)))
+            assert set(flags) == set(floats), (m.group(1), flags)
+            filters[m.group(1)] = {"read": sum(floats[k] for k, v in flags.items() if v == "true"),
+                                   "write": sum(floats[k] for k, v in flags.items() if v == "true" and k.startswith("Access"))}
+    return filters
+
+
+def contact_base_filters(texts):
+    """{One,Two}BodyContactTypeProcessor fix their filters in their own base declaration."""
+    out = {}
+    for text in texts:
+        for m in re.finditer(r"class\s+(One|Two)BodyContactTypeProcessor\s*<[^>]*>\s*:\s*\w+TypeProcessor\s*<([^>]*)>", text):
+            out[m.group(1)] = [a.strip() for a in m.group(2).split(",") if a.strip().startswith("Access")]
+    return out
+
+
 def main():
     structs, texts = load_structs()
+    top = os.path.join(ROOT, "BepuPhysics", "Constraints")
+    texts = texts + [strip_comments(open(os.path.join(top, f), encoding="utf-8-sig").read()) for f in ("IBodyAccessFilter.cs",) if os.path.join(top, f) not in SRC]
+    filters = load_filters(texts)
+    contact_filters = contact_base_filters(texts)
     bodies_of = {"OneBody": 1, "TwoBody": 2, "ThreeBody": 3, "FourBody": 4}
     types = {}
     for text in texts:
@@ -87,9 +116,16 @@ def main():
             if not idm:
                 continue
             type_id = int(idm.group(1))
-            types[type_id] = {"processor": cls, "bodies": bodies_of[nb + "Body"], "prestep_struct": prestep, "impulse_struct": impulses,
-                              "prestep_rows": flatten(prestep, structs), "impulse_rows": flatten(impulses, structs)}
-    out = {"generated_from": "BepuPhysics/Constraints/**/*.cs of the reference (bepu/bepuphysics2) by tests/golden/make_type_layouts.py", "types": {str(k): types[k] for k in sorted(types)}}
+            args = re.match(r"[^>{]*", text[m.end():]).group(0)  # the rest of the generic argument list
+            access = [a.strip() for a in args.split(",") if a.strip().startswith("Access")]
+            if not access:
+                access = contact_filters[nb]
+            n = bodies_of[nb + "Body"]
+            assert len(access) == 2 * n and all(a in filters for a in access), (cls, access)
+            types[type_id] = {"processor": cls, "bodies": n, "prestep_struct": prestep, "impulse_struct": impulses,
+                              "prestep_rows": flatten(prestep, structs), "impulse_rows": flatten(impulses, structs),
+                              "warm_start_filters": access[:n], "solve_filters": access[n:]}
+    out = {"generated_from": "BepuPhysics/Constraints/**/*.cs of the reference (bepu/bepuphysics2) by tests/golden/make_type_layouts.py", "access_filters": filters, "types": {str(k): types[k] for k in sorted(types)}}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "type_layouts.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1)

@@ -133,3 +133,34 @@ def test_penetration_recovery_is_speed_limited(libs, type_id, contacts, family, 
     util.ob.solve(sim, DT)
     assert float(sim.bodies[0, 9]) == pytest.approx(-G * DT, rel=1e-6)
     assert np.abs(_penetration_impulses(sim, contacts, family)).max() == 0.0
+
+
+@pytest.mark.parametrize("type_id,contacts,family,body_count", CONTACT_TYPES, ids=IDS)
+def test_speculative_contact_only_removes_the_velocity_that_would_penetrate(libs, type_id, contacts, family, body_count):
+    """Negative depth passes through the bias unclamped: bias = depth / dt (PenetrationLimit.cs:L124-127), so a body approaching a contact
+    that is still `gap` away is slowed towards the approach speed gap / dt that just closes the gap this step, and a slower one is left
+    alone. Each contact is a soft row (SpringSettings.cs:L37-55: softness = extra / (1 + extra) per unit effective mass, extra =
+    1 / (w dt (w dt + 2 zeta))): the converged impulses of one step are the solution of a small linear system, solved here in float64."""
+    integ = _integrator()
+    integ.gravity[1] = 0.0
+    gap = 0.01
+    sim = util.make_sim(_scene(type_id, contacts, family, body_count, friction=0.0, depth=-gap, linear=(0, -1.0, 0)), substeps=1, velocity_iterations=30, integrator=integ)
+    util.ob.solve(sim, DT)
+    # float64 fixed point of the N soft rows: (J M^-1 J^T + extra * diag(K)) lambda = bias - J v0, K_i = (J M^-1 J^T)_ii, v = v0 + M^-1 J^T lambda
+    w_dt = 2 * np.pi * 30 * DT
+    extra = 1.0 / (w_dt * (w_dt + 2.0))
+    normal = np.array([0.0, 1.0, 0.0])
+    jac = np.array([np.r_[normal, np.cross(r, normal)] for r in np.asarray(FOOTPRINTS[contacts], dtype=np.float64)])
+    inverse_mass = np.diag([1.0, 1.0, 1.0, 6.0, 6.0, 6.0])
+    v0 = np.array([0, -1.0, 0, 0, 0, 0])
+    a = jac @ inverse_mass @ jac.T
+    lam = np.linalg.solve(a + extra * np.diag(np.diag(a)), -gap / DT - jac @ v0)
+    assert (lam > 0).all()
+    expected = v0 + inverse_mass @ jac.T @ lam
+    assert sim.bodies[0, 8:11].astype(np.float64) == pytest.approx(expected[:3], abs=2e-5)
+    assert sim.bodies[0, 12:15].astype(np.float64) == pytest.approx(expected[3:], abs=2e-5)
+    assert _penetration_impulses(sim, contacts, family) == pytest.approx(lam, rel=1e-3)
+    sim = util.make_sim(_scene(type_id, contacts, family, body_count, friction=0.0, depth=-gap, linear=(0, -0.5, 0)), substeps=1, velocity_iterations=8, integrator=integ)
+    util.ob.solve(sim, DT)
+    assert float(sim.bodies[0, 9]) == pytest.approx(-0.5, rel=1e-6)
+    assert np.abs(_penetration_impulses(sim, contacts, family)).max() == 0.0

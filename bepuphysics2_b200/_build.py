@@ -6,6 +6,7 @@
 nvcc cross-compiles for sm_100a without a GPU. The solver kernels are compiled twice: once with FMA contraction
 (`bepu_fast`) and once with -fmad=false (`bepu_strict`, bit-exact against a non-contracting CPU evaluation).
 """
+import hashlib
 import os
 import subprocess
 import sys
@@ -29,6 +30,26 @@ def _newer(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+def _digest(sources, flag_sets):
+    """Content hash of everything libbepucuda.so is compiled from (sources, headers, compiler flags)."""
+    h = hashlib.sha256()
+    for flags in flag_sets:
+        h.update(("\0".join(flags) + "\n").encode())
+    for path in sorted(sources, key=os.path.basename):
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stamp_matches(stamp, digest):
+    try:
+        with open(stamp) as f:
+            return f.read().strip() == digest
+    except OSError:
+        return False
+
+
 def _run(cmd):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
@@ -50,8 +71,16 @@ def build(force=False, verbose=False, variant=None, defines=()):
     units = [("solver_%s_%d.o" % (name, unit), "bepu_solver_kernels.cu", flags + ["-DBEPU_UNIT=%d" % unit]) for unit in (5, 4, 1, 0, 2, 3) for name, flags in flavours]
     units += [("layout.o", "bepu_layout_kernels.cu", []), ("api.o", "bepucuda_api.cu", [])]
     all_sources = [os.path.join(CSRC, f) for f in ("bepu_solver_kernels.cu", "bepu_layout_kernels.cu", "bepucuda_api.cu")] + headers
-    if not force and not defines and os.path.exists(LIB_CUDA) and not _newer(LIB_CUDA, all_sources):
-        units = []  # the shared library is newer than every source: nothing to compile (object files need not travel with a snapshot)
+    # Nothing to compile when the library was built from exactly these sources (content stamp written after a build: survives a snapshot that
+    # does not keep modification times) or is newer than every source. Object files need not travel with a snapshot.
+    stamp = LIB_CUDA + ".stamp"
+    digest = _digest(all_sources, [NVCC_FLAGS] + [f for _, f in flavours] + [list(defines)])
+    fresh = os.path.exists(LIB_CUDA) and (_stamp_matches(stamp, digest) or (not os.path.exists(stamp) and not _newer(LIB_CUDA, all_sources)))
+    if not force and not defines and fresh:
+        units = []
+        if not os.path.exists(stamp):
+            with open(stamp, "w") as f:
+                f.write(digest + "\n")
     jobs = []
     for obj, src, extra in units:
         o = os.path.join(BUILD, obj)
@@ -67,8 +96,11 @@ def build(force=False, verbose=False, variant=None, defines=()):
                 if verbose and out.strip():
                     print(out)
     objs = [os.path.join(BUILD, u[0]) for u in units]
-    if units and (force or _newer(LIB_CUDA, objs)):
+    if units and (force or _newer(LIB_CUDA, objs) or not _stamp_matches(stamp, digest)):
         _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB_CUDA] + objs)
+    if units and not os.environ.get("BEPUCUDA_FREEZE_UNITS"):
+        with open(stamp, "w") as f:
+            f.write(digest + "\n")
     if variant:
         return LIB_CUDA, LIB_HOST
     host_src = os.path.join(CSRC, "host", "bepu_host.cpp")

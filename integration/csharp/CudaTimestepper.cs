@@ -13,6 +13,7 @@ public unsafe class CudaTimestepper : ITimestepper, IDisposable
     public event TimestepperStageHandler CollisionsDetected;         // ITimestepper.cs:L25
     IntPtr ctx;
     IntegratorDesc integrator;
+    ulong uploadedTopology;   // signature of the constraint graph the device currently holds (0 = none)
 
     public CudaTimestepper(Vector3 gravity, float linearDamping = 0.03f, float angularDamping = 0.03f, int device = 0, bool strict = false)
     {
@@ -46,29 +47,76 @@ public unsafe class CudaTimestepper : ITimestepper, IDisposable
         fixed (IntegratorDesc* d = &integrator) Check(Native.bepucuda_set_integrator(ctx, d));
         Check(Native.bepucuda_upload_bodies(ctx, bodies.DynamicsState.Memory, bodies.Count));                       // BodySet.cs:L33
 
+        // Frames whose constraint graph did not change (same type batches, same body references, same kinematics) only refresh what the
+        // narrow phase rewrote: the device keeps its batch analysis and the captured CUDA graph (INTEGRATION.md, performance notes).
         ref var set = ref solver.ActiveSet;
-        Check(Native.bepucuda_begin_constraints(ctx, Vector<float>.Count, set.Batches.Count));
-        for (int b = 0; b < set.Batches.Count; ++b)
+        ulong topology = TopologySignature(simulation);
+        if (topology == uploadedTopology)
         {
-            ref var batch = ref set.Batches[b];
-            for (int t = 0; t < batch.TypeBatches.Count; ++t)
+            for (int b = 0; b < set.Batches.Count; ++b)
             {
-                ref var tb = ref batch.TypeBatches[t];                                                                 // TypeBatch.cs:L10-27
-                int rc = Native.bepucuda_upload_type_batch(ctx, b, t, tb.TypeId, tb.ConstraintCount, tb.BodyReferences.Memory, tb.PrestepData.Memory, tb.AccumulatedImpulses.Memory);
-                if (rc == -4) return false;   // BEPUCUDA_ERR_UNSUPPORTED_TYPE
-                Check(rc);
+                ref var batch = ref set.Batches[b];
+                for (int t = 0; t < batch.TypeBatches.Count; ++t)
+                {
+                    ref var tb = ref batch.TypeBatches[t];
+                    Check(Native.bepucuda_update_type_batch(ctx, b, t, tb.PrestepData.Memory, tb.AccumulatedImpulses.Memory));
+                }
             }
         }
-        var kinematics = stackalloc int[Math.Max(1, solver.ConstrainedKinematicHandles.Count)];                       // Solver.cs:L68
-        for (int i = 0; i < solver.ConstrainedKinematicHandles.Count; ++i)
-            kinematics[i] = simulation.Bodies.HandleToLocation[solver.ConstrainedKinematicHandles[i]].Index;
-        Check(Native.bepucuda_set_constrained_kinematics(ctx, kinematics, solver.ConstrainedKinematicHandles.Count));
-        Check(Native.bepucuda_end_constraints(ctx));
+        else
+        {
+            uploadedTopology = 0;
+            Check(Native.bepucuda_begin_constraints(ctx, Vector<float>.Count, set.Batches.Count));
+            for (int b = 0; b < set.Batches.Count; ++b)
+            {
+                ref var batch = ref set.Batches[b];
+                for (int t = 0; t < batch.TypeBatches.Count; ++t)
+                {
+                    ref var tb = ref batch.TypeBatches[t];                                                             // TypeBatch.cs:L10-27
+                    int rc = Native.bepucuda_upload_type_batch(ctx, b, t, tb.TypeId, tb.ConstraintCount, tb.BodyReferences.Memory, tb.PrestepData.Memory, tb.AccumulatedImpulses.Memory);
+                    if (rc == -4) return false;   // BEPUCUDA_ERR_UNSUPPORTED_TYPE
+                    Check(rc);
+                }
+            }
+            var kinematics = stackalloc int[Math.Max(1, solver.ConstrainedKinematicHandles.Count)];                   // Solver.cs:L68
+            for (int i = 0; i < solver.ConstrainedKinematicHandles.Count; ++i)
+                kinematics[i] = simulation.Bodies.HandleToLocation[solver.ConstrainedKinematicHandles[i]].Index;
+            Check(Native.bepucuda_set_constrained_kinematics(ctx, kinematics, solver.ConstrainedKinematicHandles.Count));
+            Check(Native.bepucuda_end_constraints(ctx));
+            uploadedTopology = topology;
+        }
 
         Check(Native.bepucuda_solve(ctx, dt));                                                                         // Simulation.cs:L278-290
         Check(Native.bepucuda_download_bodies(ctx, bodies.DynamicsState.Memory, bodies.Count));
         Check(Native.bepucuda_download_impulses(ctx));   // narrow phase redistributes them next frame (NarrowPhaseConstraintUpdate.cs:L81-135)
         return true;
+    }
+
+    // FNV-1a over everything bepucuda_end_constraints analyses: batch / type batch shape, every body reference, the constrained kinematics.
+    // (~8 bytes per constraint body: a few hundred microseconds for 300 k contacts, against a graph re-capture per frame.)
+    static ulong TopologySignature(Simulation simulation)
+    {
+        var solver = simulation.Solver;
+        ref var set = ref solver.ActiveSet;
+        ulong h = 14695981039346656037UL;
+        void Mix(ulong v) { h = (h ^ v) * 1099511628211UL; }
+        Mix((ulong)simulation.Bodies.ActiveSet.Count); Mix((ulong)set.Batches.Count); Mix((ulong)Vector<float>.Count);
+        for (int b = 0; b < set.Batches.Count; ++b)
+        {
+            ref var batch = ref set.Batches[b];
+            Mix((ulong)batch.TypeBatches.Count);
+            for (int t = 0; t < batch.TypeBatches.Count; ++t)
+            {
+                ref var tb = ref batch.TypeBatches[t];
+                Mix((ulong)tb.TypeId); Mix((ulong)tb.ConstraintCount);
+                int bundles = (tb.ConstraintCount + Vector<int>.Count - 1) / Vector<int>.Count;
+                int words = bundles * solver.TypeProcessors[tb.TypeId].BodiesPerConstraint * Vector<int>.Count / 2;   // int32 pairs
+                var refs = (ulong*)tb.BodyReferences.Memory;
+                for (int i = 0; i < words; ++i) Mix(refs[i]);
+            }
+        }
+        for (int i = 0; i < solver.ConstrainedKinematicHandles.Count; ++i) Mix((ulong)solver.ConstrainedKinematicHandles[i].Value);
+        return h == 0 ? 1 : h;
     }
 
     void Check(int rc) { if (rc != 0) throw new InvalidOperationException(System.Runtime.InteropServices.Marshal.PtrToStringAnsi(Native.bepucuda_last_error(ctx))); }

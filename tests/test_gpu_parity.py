@@ -320,3 +320,14 @@ def test_sharded_batches_two_ranks_with_exchange_bit_exact(libs):
     # every constraint is solved by exactly one rank
     for masks in zip(*kept):
         assert (np.sum(masks, axis=0) <= 1).all()
+
+
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT])
+def test_fast_build_is_run_to_run_deterministic(libs, mode):
+    """The reference's own determinism harness (Demos/SpecializedTests/DeterminismTest.cs) repeats a simulation and demands bitwise identical
+    results. The strict build is bit-identical to the oracle, hence deterministic; this holds the default FMA build to the same standard: no
+    result may depend on which CTA of a stage runs first (scene large enough for every stage to span many CTAs, several frames)."""
+    scene = scenes.merge(scenes.shape_pile(20000, seed=5, nonconvex_fraction=0.2), scenes.ragdolls(100, seed=5))
+    runs = [util.run_gpu(util.make_sim(scene, substeps=4, velocity_iterations=2), DT, frames=3, strict=False, mode=mode) for _ in range(3)]
+    for other in runs[1:]:
+        util.compare(runs[0], other, exact=True)

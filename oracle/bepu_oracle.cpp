@@ -762,6 +762,38 @@ extern "C" int32_t oracle_type_info(int32_t type_id, int32_t* bodies, int32_t* p
     return 0;
 }
 
+// One constraint lane of one stage through the typed functions (stage 0 WarmStart, 1 Solve, 2 IncrementallyUpdateForSubstep): the hook that lets
+// the CPU suite compare a host compilation of the CUDA constraint SOURCE against this restatement (tests/test_device_source_on_host.py).
+// body_states: per body 14 floats (position 3, orientation xyzw, world inverse inertia XX YX YY ZX ZY ZZ, inverse mass); velocities: per body 6;
+// row r of the lane is prestep[r * row_stride] / impulses[r * row_stride].
+extern "C" int32_t oracle_eval_lane(int32_t type_id, int32_t stage, const float* body_states, float dt, float* prestep, float* impulses, float* velocities, int32_t row_stride) {
+    if (type_id < 0 || type_id >= 64) return -1;
+    const TypeOps<float>& o = registry<float>().ops[type_id];
+    if (!o.solve) return -1;
+    BodyIn<float> b[4];
+    Velocity<float> v[4];
+    for (int s = 0; s < o.bodies; ++s) {
+        const float* f = body_states + 14 * s;
+        b[s].pos = {f[0], f[1], f[2]};
+        b[s].q = {f[3], f[4], f[5], f[6]};
+        b[s].inertia.t = {f[7], f[8], f[9], f[10], f[11], f[12]};
+        b[s].inertia.inv_mass = f[13];
+        const float* w = velocities + 6 * s;
+        v[s].lin = {w[0], w[1], w[2]};
+        v[s].ang = {w[3], w[4], w[5]};
+    }
+    Rows<float> p{prestep, row_stride}, a{impulses, row_stride};
+    if (stage == 0) o.warm_start(b, p, a, v);
+    else if (stage == 1) o.solve(b, dt, 1.0f / dt, p, a, v);
+    else if (o.incremental) o.incremental(dt, v, p);
+    for (int s = 0; s < o.bodies; ++s) {
+        float* w = velocities + 6 * s;
+        w[0] = v[s].lin.x; w[1] = v[s].lin.y; w[2] = v[s].lin.z;
+        w[3] = v[s].ang.x; w[4] = v[s].ang.y; w[5] = v[s].ang.z;
+    }
+    return 0;
+}
+
 extern "C" int32_t oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

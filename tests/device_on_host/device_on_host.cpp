@@ -1,0 +1,91 @@
+// TEST INFRASTRUCTURE. Compiles the device constraint functions of bepuphysics2_b200/csrc/{bepu_device_math,bepu_contacts,bepu_joints,
+// bepu_joints_more}.cuh for the HOST (g++, -ffp-contract=off: the arithmetic of the strict -fmad=false CUDA build) and exposes one lane of one
+// stage per call, so that the CPU test-suite can hold the CUDA source itself -- not only the GPU binary -- to the oracle bit for bit
+// (tests/test_device_source_on_host.py). Nothing here is part of the product; the product never falls back to it.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -march=x86-64-v3 -I tests/device_on_host/stubs -I bepuphysics2_b200/csrc -shared -fPIC
+#define BEPU_NS bepu_device_on_host
+#include "bepu_joints_more.cuh"  // pulls in bepu_joints.cuh, bepu_contacts.cuh, bepu_device_math.cuh (with the stub cuda_runtime.h)
+
+namespace BEPU_NS {
+
+// The per-body-count call adaptors of csrc/bepu_solver_kernels.cuh (call_warm_start / call_solve / call_incremental), restated: that header
+// also holds the kernels proper (PTX, shared memory) and cannot be compiled for the host.
+template <class T> static void call_warm_start(const BodyState* b, GlobalRows p, GlobalAcc a, Velocity* v) {
+    if constexpr (T::kNeedsPose) T::warm_start(b, p, a, v);
+    else if constexpr (T::kBodies == 2) T::warm_start(b[0].inertia, b[1].inertia, p, a, v[0], v[1]);
+    else T::warm_start(b[0].inertia, p, a, v[0]);
+}
+template <class T> static void call_solve(const BodyState* b, float dt, float inverseDt, GlobalRows p, GlobalAcc a, Velocity* v) {
+    if constexpr (T::kNeedsPose) T::solve(b, dt, inverseDt, p, a, v);
+    else if constexpr (T::kBodies == 2) T::solve(b[0].inertia, b[1].inertia, dt, inverseDt, p, a, v[0], v[1]);
+    else T::solve(b[0].inertia, dt, inverseDt, p, a, v[0]);
+}
+template <class T> static void call_incremental(float dt, const Velocity* v, float* p) {
+    if constexpr (T::kIncremental) {
+        if constexpr (T::kBodies == 2) T::incremental_update(dt, v[0], v[1], p);
+        else T::incremental_update(dt, v[0], p);
+    }
+}
+
+// Same id -> type table as BEPU_CONTACT_TYPES in csrc/bepu_solver_kernels.cuh (the joint tables come from the joint headers themselves).
+#define DEVICE_ON_HOST_CONTACT_TYPES(X)                                                                                           \
+    X(0, ConvexOneBody<1>) X(1, ConvexOneBody<2>) X(2, ConvexOneBody<3>) X(3, ConvexOneBody<4>)                                   \
+    X(4, ConvexTwoBody<1>) X(5, ConvexTwoBody<2>) X(6, ConvexTwoBody<3>) X(7, ConvexTwoBody<4>)                                   \
+    X(8, NonconvexOneBody<2>) X(9, NonconvexOneBody<3>) X(10, NonconvexOneBody<4>)                                                \
+    X(15, NonconvexTwoBody<2>) X(16, NonconvexTwoBody<3>) X(17, NonconvexTwoBody<4>)
+
+template <class T> static int eval(int stage, const float* body_states, float dt, float* prestep, float* impulses, float* velocities) {
+    constexpr int NB = T::kBodies;
+    BodyState b[NB];
+    Velocity v[NB];
+    for (int s = 0; s < NB; ++s) {
+        const float* f = body_states + 14 * s;
+        b[s].pos = {f[0], f[1], f[2]};
+        b[s].q = {f[3], f[4], f[5], f[6]};
+        b[s].inertia.t = {f[7], f[8], f[9], f[10], f[11], f[12]};
+        b[s].inertia.inv_mass = f[13];
+        const float* w = velocities + 6 * s;
+        v[s].lin = {w[0], w[1], w[2]};
+        v[s].ang = {w[3], w[4], w[5]};
+    }
+    if (stage == 0) call_warm_start<T>(b, GlobalRows{prestep}, GlobalAcc{impulses}, v);
+    else if (stage == 1) call_solve<T>(b, dt, 1.0f / dt, GlobalRows{prestep}, GlobalAcc{impulses}, v);
+    else call_incremental<T>(dt, v, prestep);
+    for (int s = 0; s < NB; ++s) {
+        float* w = velocities + 6 * s;
+        w[0] = v[s].lin.x; w[1] = v[s].lin.y; w[2] = v[s].lin.z;
+        w[3] = v[s].ang.x; w[4] = v[s].ang.y; w[5] = v[s].ang.z;
+    }
+    return 0;
+}
+
+}  // namespace BEPU_NS
+
+using namespace BEPU_NS;
+
+// Rows are laid out like one lane of a device bundle: row r of the lane is prestep[r * 32] (kLanes), same for impulses.
+// body_states: per body 14 floats (position 3, orientation xyzw, world inverse inertia XX YX YY ZX ZY ZZ, inverse mass); velocities: per body 6.
+// stage: 0 WarmStart, 1 Solve, 2 IncrementallyUpdateForSubstep. Returns -1 for an id without a type.
+extern "C" int32_t device_on_host_eval_lane(int32_t type_id, int32_t stage, const float* body_states, float dt, float* prestep, float* impulses, float* velocities) {
+    switch (type_id) {
+#define CASE(ID, T) \
+    case ID: return eval<T>(stage, body_states, dt, prestep, impulses, velocities);
+        DEVICE_ON_HOST_CONTACT_TYPES(CASE)
+        BEPU_JOINT_TYPES(CASE)
+        BEPU_JOINT_TYPES_MORE(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+extern "C" int32_t device_on_host_type_info(int32_t type_id, int32_t* bodies, int32_t* prestep_rows, int32_t* impulse_rows, int32_t* incremental) {
+    switch (type_id) {
+#define CASE(ID, T) \
+    case ID: *bodies = T::kBodies; *prestep_rows = T::kPrestepRows; *impulse_rows = T::kImpulseRows; *incremental = T::kIncremental ? 1 : 0; return 0;
+        DEVICE_ON_HOST_CONTACT_TYPES(CASE)
+        BEPU_JOINT_TYPES(CASE)
+        BEPU_JOINT_TYPES_MORE(CASE)
+#undef CASE
+        default: return -1;
+    }
+}

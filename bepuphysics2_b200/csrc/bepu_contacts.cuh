@@ -252,14 +252,56 @@ template <int N> struct ConvexTwoBody {
         if constexpr (N == 1) centerA = offs[0]; else centerA = friction_center<N>(offs, depths);
         V3 centerB = centerA - offsetB;
         tangent_apply(tangent_jacobians(x, z, centerA, centerB), iA, iB, V2{ldacc(a, 0), ldacc(a, 1)}, vA, vB);
+#ifdef BEPU_ROLLED_CONTACTS
+        // experiment: the per-contact rows as a real loop -- rows re-read by index, same operations in the same order
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            V3 offset = ldrow3(p, 4 * i);
+            penetration_warm_start(iA, iB, normal, offset, offset - offsetB, ldacc(a, 2 + i), vA, vB);
+        }
+#else
 #pragma unroll
         for (int i = 0; i < N; ++i) penetration_warm_start(iA, iB, normal, offs[i], offs[i] - offsetB, ldacc(a, 2 + i), vA, vB);
+#endif
         twist_apply(normal, iA, iB, ldacc(a, N + 2), vA, vB);
     }
     template <class PR, class AR> BEPU_DI static void solve(const Inertia& iA, const Inertia& iB, float dt, float inverseDt, PR p, AR a, Velocity& vA, Velocity& vB) {  // e.g. L1488-1513
         V3 normal = ldrow3(p, L::kNormal), offsetB = ldrow3(p, L::kOffsetB);
         float friction = ldrow(p, L::kFriction), maxRecovery = ldrow(p, L::kMaxRecovery);
         Springiness sp = compute_springiness(ldrow(p, L::kAngularFrequency), ldrow(p, L::kTwiceDampingRatio), dt);
+#ifdef BEPU_ROLLED_CONTACTS
+        if constexpr (N > 1) {
+            // experiment: the N penetration rows as a real loop. The friction centre is a pure function of the prestep rows, so
+            // it moves in front; the two friction sums accumulate left to right exactly like the unrolled expressions below.
+            V3 offs[N];
+            float depths[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { offs[i] = ldrow3(p, 4 * i); depths[i] = ldrow(p, 4 * i + 3); }
+            const V3 centerA = friction_center<N>(offs, depths);
+            float penSum = 0.0f, twistSum = 0.0f;
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) {
+                V3 offset = ldrow3(p, 4 * i);
+                float pen = ldacc(a, 2 + i);
+                penetration_solve(iA, iB, normal, offset, offset - offsetB, ldrow(p, 4 * i + 3), sp, maxRecovery, inverseDt, pen, vA, vB);
+                stacc(a, 2 + i, pen);
+                const float lever = pen * distance(centerA, offset);
+                penSum = i == 0 ? pen : penSum + pen;  // (not 0 + pen: the sign of a zero impulse must survive)
+                twistSum = i == 0 ? lever : twistSum + lever;
+            }
+            V3 x, z;
+            build_orthonormal_basis(normal, x, z);
+            V2 tangent{ldacc(a, 0), ldacc(a, 1)};
+            float twist = ldacc(a, N + 2);
+            const float premultiplied = (1.0f / N) * friction;
+            tangent_solve(x, z, centerA, centerA - offsetB, iA, iB, premultiplied * penSum, tangent, vA, vB);
+            twist_solve(normal, iA, iB, premultiplied * twistSum, twist, vA, vB);
+            stacc(a, 0, tangent.x);
+            stacc(a, 1, tangent.y);
+            stacc(a, N + 2, twist);
+            return;
+        }
+#endif
         V3 offs[N];
         float depths[N], pen[N];
 #pragma unroll
@@ -319,14 +361,50 @@ template <int N> struct ConvexOneBody {
         V3 centerA;
         if constexpr (N == 1) centerA = offs[0]; else centerA = friction_center<N>(offs, depths);
         tangent1_apply(M23{x, z}, M23{cross(centerA, x), cross(centerA, z)}, iA, V2{ldacc(a, 0), ldacc(a, 1)}, vA);
+#ifdef BEPU_ROLLED_CONTACTS
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) penetration1_apply(iA, normal, cross(ldrow3(p, 4 * i), normal), ldacc(a, 2 + i), vA);
+#else
 #pragma unroll
         for (int i = 0; i < N; ++i) penetration1_apply(iA, normal, cross(offs[i], normal), ldacc(a, 2 + i), vA);
+#endif
         twist1_apply(normal, iA, ldacc(a, N + 2), vA);
     }
     template <class PR, class AR> BEPU_DI static void solve(const Inertia& iA, float dt, float inverseDt, PR p, AR a, Velocity& vA) {  // e.g. L311-328
         V3 normal = ldrow3(p, L::kNormal);
         float friction = ldrow(p, L::kFriction), maxRecovery = ldrow(p, L::kMaxRecovery);
         Springiness sp = compute_springiness(ldrow(p, L::kAngularFrequency), ldrow(p, L::kTwiceDampingRatio), dt);
+#ifdef BEPU_ROLLED_CONTACTS
+        if constexpr (N > 1) {  // see ConvexTwoBody::solve
+            V3 offs[N];
+            float depths[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { offs[i] = ldrow3(p, 4 * i); depths[i] = ldrow(p, 4 * i + 3); }
+            const V3 centerA = friction_center<N>(offs, depths);
+            float penSum = 0.0f, twistSum = 0.0f;
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) {
+                V3 offset = ldrow3(p, 4 * i);
+                float pen = ldacc(a, 2 + i);
+                penetration1_solve(iA, normal, offset, ldrow(p, 4 * i + 3), sp, maxRecovery, inverseDt, pen, vA);
+                stacc(a, 2 + i, pen);
+                const float lever = pen * distance(centerA, offset);
+                penSum = i == 0 ? pen : penSum + pen;
+                twistSum = i == 0 ? lever : twistSum + lever;
+            }
+            V3 x, z;
+            build_orthonormal_basis(normal, x, z);
+            V2 tangent{ldacc(a, 0), ldacc(a, 1)};
+            float twist = ldacc(a, N + 2);
+            const float premultiplied = (1.0f / N) * friction;
+            tangent1_solve(x, z, centerA, iA, premultiplied * penSum, tangent, vA);
+            twist1_solve(normal, iA, premultiplied * twistSum, twist, vA);
+            stacc(a, 0, tangent.x);
+            stacc(a, 1, tangent.y);
+            stacc(a, N + 2, twist);
+            return;
+        }
+#endif
         V3 offs[N];
         float depths[N], pen[N];
 #pragma unroll
@@ -366,6 +444,12 @@ template <int N> struct ConvexOneBody {
 };
 
 // ---- nonconvex manifolds: ContactNonconvexCommon.cs:L171-299 ----
+// Every contact of a nonconvex manifold is a self-contained block (own normal, penetration row and friction), so its loops can run rolled.
+#ifdef BEPU_ROLLED_CONTACTS
+#define BEPU_CONTACT_LOOP _Pragma("unroll 1")
+#else
+#define BEPU_CONTACT_LOOP _Pragma("unroll")
+#endif
 // prestep rows: Friction, AngularFrequency, TwiceDampingRatio, MaxRecovery, [OffsetB xyz (two body)], [contact i: Offset xyz, Depth, Normal xyz]x N
 // impulse rows: [contact i: Tangent xy, Penetration]x N
 template <int N, bool TwoBody> struct NonconvexLayout {
@@ -383,7 +467,7 @@ template <int N> struct NonconvexTwoBody {
     static constexpr bool kNeedsPose = false;
     template <class PR, class AR> BEPU_DI static void warm_start(const Inertia& iA, const Inertia& iB, PR p, AR a, Velocity& vA, Velocity& vB) {  // L246-261
         V3 offsetB = ldrow3(p, L::kOffsetB);
-#pragma unroll
+BEPU_CONTACT_LOOP
         for (int i = 0; i < N; ++i) {
             const int c = L::kContacts + 7 * i;
             V3 offset = ldrow3(p, c), normal = ldrow3(p, c + 4);
@@ -398,7 +482,7 @@ template <int N> struct NonconvexTwoBody {
         V3 offsetB = ldrow3(p, L::kOffsetB);
         float friction = ldrow(p, 0), maxRecovery = ldrow(p, 3);
         Springiness sp = compute_springiness(ldrow(p, 1), ldrow(p, 2), dt);
-#pragma unroll
+BEPU_CONTACT_LOOP
         for (int i = 0; i < N; ++i) {
             const int c = L::kContacts + 7 * i;
             V3 offset = ldrow3(p, c), normal = ldrow3(p, c + 4);
@@ -432,7 +516,7 @@ template <int N> struct NonconvexOneBody {
     static constexpr bool kIncremental = true;
     static constexpr bool kNeedsPose = false;
     template <class PR, class AR> BEPU_DI static void warm_start(const Inertia& iA, PR p, AR a, Velocity& vA) {  // L186-199
-#pragma unroll
+BEPU_CONTACT_LOOP
         for (int i = 0; i < N; ++i) {
             const int c = L::kContacts + 7 * i;
             V3 offset = ldrow3(p, c), normal = ldrow3(p, c + 4);
@@ -445,7 +529,7 @@ template <int N> struct NonconvexOneBody {
     template <class PR, class AR> BEPU_DI static void solve(const Inertia& iA, float dt, float inverseDt, PR p, AR a, Velocity& vA) {  // L201-219
         float friction = ldrow(p, 0), maxRecovery = ldrow(p, 3);
         Springiness sp = compute_springiness(ldrow(p, 1), ldrow(p, 2), dt);
-#pragma unroll
+BEPU_CONTACT_LOOP
         for (int i = 0; i < N; ++i) {
             const int c = L::kContacts + 7 * i;
             V3 offset = ldrow3(p, c), normal = ldrow3(p, c + 4);

@@ -23,13 +23,15 @@ LANES = 32
 DT = 1.0 / 240.0  # a substep of the 8 x 2 configuration at 1/30 s
 
 
-@pytest.fixture(scope="module")
-def device_on_host():
-    lib = os.path.join(HERE, "libdevice_on_host.so")
+# "rolled": the same headers with -DBEPU_ROLLED_CONTACTS, the experimental loop-shaped contact path, which must stay bit-identical.
+@pytest.fixture(scope="module", params=["default", "rolled"])
+def device_on_host(request):
+    lib = os.path.join(HERE, "libdevice_on_host%s.so" % ("" if request.param == "default" else "_" + request.param))
+    defines = ["-DBEPU_ROLLED_CONTACTS"] if request.param == "rolled" else []
     srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas",
-                               "-I", os.path.join(HERE, "stubs"), "-I", CSRC, "-shared", "-fPIC", "-o", lib, srcs[0]])
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas"] + defines +
+                              ["-I", os.path.join(HERE, "stubs"), "-I", CSRC, "-shared", "-fPIC", "-o", lib, srcs[0]])
     dev = C.CDLL(lib)
     fp = C.POINTER(C.c_float)
     dev.device_on_host_eval_lane.argtypes = [C.c_int32, C.c_int32, fp, C.c_float, fp, fp, fp]

@@ -337,7 +337,20 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
     __shared__ __align__(128) float slab[kStaged ? kWarps * kStageSlabRows * kLanes : 1];
     __shared__ __align__(8) unsigned long long bars[kWarps];
     const int warp_in_block = threadIdx.x >> 5;
+#ifdef BEPU_STAGE_SM_LOCALITY
+    // experiment: in the single-wave instantiation give every SM a CONTIGUOUS run of work records instead of every S-th CTA, so the
+    // warps of an SM -- which leave griddepcontrol.wait together -- mostly run the same constraint type and share instruction fetch.
+    // blockIdx -> record block is a bijection: CTA k * S + s takes block start(s) + k, start(s) = s * q + min(s, r), q = G / S, r = G % S
+    // (k <= q, and k == q only for s < r). BEPU_STAGE_SM_LOCALITY is S, the SM count (148 on B200).
+    int block = blockIdx.x;
+    if (MINB == 1 && (int)gridDim.x > BEPU_STAGE_SM_LOCALITY) {
+        const int S = BEPU_STAGE_SM_LOCALITY, q = (int)gridDim.x / S, r = (int)gridDim.x % S, s = (int)blockIdx.x % S, k = (int)blockIdx.x / S;
+        block = s * q + (s < r ? s : r) + k;
+    }
+    const int warp = (block * kStageBlockThreads + threadIdx.x) >> 5;
+#else
     const int warp = (blockIdx.x * kStageBlockThreads + threadIdx.x) >> 5;
+#endif
     const int lane = threadIdx.x & 31;
     WorkRecord rec{};
     uint32_t enc0 = (uint32_t)kRefEmpty, enc1 = 0;

@@ -299,9 +299,9 @@ template <int N> struct ConvexTwoBody {
             stacc(a, 0, tangent.x);
             stacc(a, 1, tangent.y);
             stacc(a, N + 2, twist);
-            return;
-        }
+        } else
 #endif
+        {
         V3 offs[N];
         float depths[N], pen[N];
 #pragma unroll
@@ -334,6 +334,7 @@ template <int N> struct ConvexTwoBody {
 #pragma unroll
         for (int i = 0; i < N; ++i) stacc(a, 2 + i, pen[i]);
         stacc(a, N + 2, twist);
+        }
     }
     BEPU_DI static void incremental_update(float dt, const Velocity& vA, const Velocity& vB, float* p) {  // e.g. L1464-1471
         V3 normal = ldrow3(p, L::kNormal), offsetB = ldrow3(p, L::kOffsetB);
@@ -402,9 +403,9 @@ template <int N> struct ConvexOneBody {
             stacc(a, 0, tangent.x);
             stacc(a, 1, tangent.y);
             stacc(a, N + 2, twist);
-            return;
-        }
+        } else
 #endif
+        {
         V3 offs[N];
         float depths[N], pen[N];
 #pragma unroll
@@ -435,6 +436,7 @@ template <int N> struct ConvexOneBody {
 #pragma unroll
         for (int i = 0; i < N; ++i) stacc(a, 2 + i, pen[i]);
         stacc(a, N + 2, twist);
+        }
     }
     BEPU_DI static void incremental_update(float dt, const Velocity& vA, float* p) {
         V3 normal = ldrow3(p, L::kNormal);

@@ -794,6 +794,36 @@ extern "C" int32_t oracle_eval_lane(int32_t type_id, int32_t stage, const float*
     return 0;
 }
 
+// The integration arithmetic, one call per function (same operand layout as device_on_host_eval_integration in tests/device_on_host).
+extern "C" int32_t oracle_eval_integration(int32_t op, const float* in, float* out) {
+    auto sym = [&](int i) { return Sym3<float>{in[i], in[i + 1], in[i + 2], in[i + 3], in[i + 4], in[i + 5]}; };
+    if (op == 0) {
+        Q4<float> q = integrate_orientation<float>(Q4<float>{in[0], in[1], in[2], in[3]}, V3<float>{in[4], in[5], in[6]}, in[7]);
+        out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+    } else if (op == 1) {
+        Sym3<float> r = rotate_inverse_inertia<float>(sym(0), Q4<float>{in[6], in[7], in[8], in[9]});
+        out[0] = r.xx; out[1] = r.yx; out[2] = r.yy; out[3] = r.zx; out[4] = r.zy; out[5] = r.zz;
+    } else if (op == 2) {
+        V3<float> w{in[16], in[17], in[18]};
+        integrate_angular_conserve_momentum<float>(Q4<float>{in[0], in[1], in[2], in[3]}, sym(4), sym(10), w);
+        out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    } else if (op == 3) {
+        V3<float> w{in[10], in[11], in[12]};
+        integrate_angular_gyroscopic<float>(Q4<float>{in[0], in[1], in[2], in[3]}, sym(4), w, in[13]);
+        out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    } else if (op == 4) {
+        Callbacks cb{};
+        cb.gravity_dt[0] = in[6]; cb.gravity_dt[1] = in[7]; cb.gravity_dt[2] = in[8];
+        cb.linear_damping_dt = in[9]; cb.angular_damping_dt = in[10];
+        Velocity<float> v{{in[0], in[1], in[2]}, {in[3], in[4], in[5]}};
+        cb.integrate_velocity(v);
+        out[0] = v.lin.x; out[1] = v.lin.y; out[2] = v.lin.z; out[3] = v.ang.x; out[4] = v.ang.y; out[5] = v.ang.z;
+    } else {
+        return -1;
+    }
+    return 0;
+}
+
 extern "C" int32_t oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

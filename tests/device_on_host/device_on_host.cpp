@@ -6,6 +6,7 @@
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -march=x86-64-v3 -I tests/device_on_host/stubs -I bepuphysics2_b200/csrc -shared -fPIC
 #define BEPU_NS bepu_device_on_host
 #include "bepu_joints_more.cuh"  // pulls in bepu_joints.cuh, bepu_contacts.cuh, bepu_device_math.cuh (with the stub cuda_runtime.h)
+#include "bepu_integration.cuh"
 
 namespace BEPU_NS {
 
@@ -88,4 +89,34 @@ extern "C" int32_t device_on_host_type_info(int32_t type_id, int32_t* bodies, in
 #undef CASE
         default: return -1;
     }
+}
+
+// The integration arithmetic of csrc/bepu_integration.cuh. op 0: integrate_orientation(q[0..3], w[4..6], halfDt[7]) -> q; 1: rotate_inverse_inertia(
+// local[0..5], q[6..9]) -> 6 floats; 2: integrate_angular_conserve_momentum(previous q[0..3], local[4..9], world[10..15], w[16..18]) -> w;
+// 3: integrate_angular_gyroscopic(q[0..3], local[4..9], w[10..12], dt[13]) -> w; 4: callback_integrate_velocity(v[0..5], gravity dt[6..8],
+// linear damping dt[9], angular damping dt[10]) -> v.
+extern "C" int32_t device_on_host_eval_integration(int32_t op, const float* in, float* out) {
+    auto sym = [&](int i) { return Sym3{in[i], in[i + 1], in[i + 2], in[i + 3], in[i + 4], in[i + 5]}; };
+    if (op == 0) {
+        Q4 q = integrate_orientation(Q4{in[0], in[1], in[2], in[3]}, V3{in[4], in[5], in[6]}, in[7]);
+        out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+    } else if (op == 1) {
+        Sym3 r = rotate_inverse_inertia(sym(0), Q4{in[6], in[7], in[8], in[9]});
+        out[0] = r.xx; out[1] = r.yx; out[2] = r.yy; out[3] = r.zx; out[4] = r.zy; out[5] = r.zz;
+    } else if (op == 2) {
+        V3 w{in[16], in[17], in[18]};
+        integrate_angular_conserve_momentum(Q4{in[0], in[1], in[2], in[3]}, sym(4), sym(10), w);
+        out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    } else if (op == 3) {
+        V3 w{in[10], in[11], in[12]};
+        integrate_angular_gyroscopic(Q4{in[0], in[1], in[2], in[3]}, sym(4), w, in[13]);
+        out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    } else if (op == 4) {
+        Velocity v{{in[0], in[1], in[2]}, {in[3], in[4], in[5]}};
+        callback_integrate_velocity(v, in[6], in[7], in[8], in[9], in[10]);
+        out[0] = v.lin.x; out[1] = v.lin.y; out[2] = v.lin.z; out[3] = v.ang.x; out[4] = v.ang.y; out[5] = v.ang.z;
+    } else {
+        return -1;
+    }
+    return 0;
 }

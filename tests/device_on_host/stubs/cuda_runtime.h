@@ -8,8 +8,14 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 
 // cache-hinted loads / stores are plain memory accesses on the host
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+static inline float __int_as_float(int i) {
+    float f;
+    std::memcpy(&f, &i, sizeof f);
+    return f;
+}

@@ -28,7 +28,7 @@ DT = 1.0 / 240.0  # a substep of the 8 x 2 configuration at 1/30 s
 def device_on_host(request):
     lib = os.path.join(HERE, "libdevice_on_host%s.so" % ("" if request.param == "default" else "_" + request.param))
     defines = ["-DBEPU_ROLLED_CONTACTS"] if request.param == "rolled" else []
-    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh")]
+    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh", "bepu_integration.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas"] + defines +
                               ["-I", os.path.join(HERE, "stubs"), "-I", CSRC, "-shared", "-fPIC", "-o", lib, srcs[0]])
@@ -38,6 +38,8 @@ def device_on_host(request):
     dev.device_on_host_type_info.argtypes = [C.c_int32] + [C.POINTER(C.c_int32)] * 4
     orc = ob.load()
     orc.oracle_eval_lane.argtypes = [C.c_int32, C.c_int32, fp, C.c_float, fp, fp, fp, C.c_int32]
+    dev.device_on_host_eval_integration.argtypes = [C.c_int32, fp, fp]
+    orc.oracle_eval_integration.argtypes = [C.c_int32, fp, fp]
     return dev, orc
 
 
@@ -106,6 +108,43 @@ def test_device_constraint_source_matches_the_oracle_bit_for_bit(libs, device_on
                     assert not np.array_equal(v_dev, velocities) or not impulses.any(), what + ": the stage did something"
                 checked += 1
     assert checked > 44 * 2 * 16
+
+
+def test_device_integration_source_matches_the_oracle_bit_for_bit(libs, device_on_host):
+    """csrc/bepu_integration.cuh (orientation integration through the custom sin / cos, inertia rotation, both momentum-conserving angular
+    updates, the velocity callback) against the oracle's restatement of PoseIntegrator.cs:L146-253, function by function."""
+    dev, orc = device_on_host
+    rng = np.random.default_rng(11)
+
+    def unit_q():
+        q = rng.normal(0, 1, 4)
+        return q / np.linalg.norm(q)
+
+    def spd():
+        r = np.linalg.qr(rng.normal(0, 1, (3, 3)))[0]
+        m = r @ np.diag(rng.uniform(0.3, 5.0, 3)) @ r.T
+        return np.array([m[0, 0], m[1, 0], m[1, 1], m[2, 0], m[2, 1], m[2, 2]])
+
+    for trial in range(400):
+        w = rng.normal(0, 1, 3) * 10.0 ** rng.uniform(-3, 1.5)
+        if trial % 50 == 0:
+            w = w * 0.0  # |w| <= 1e-15: the identity branch
+        q, local = unit_q(), spd()
+        world = spd()
+        cases = {
+            0: np.r_[q, w, rng.choice([1, -1]) * 0.5 / rng.choice([60.0, 240.0, 480.0])],
+            1: np.r_[local, q],
+            2: np.r_[q, local, world, w],
+            3: np.r_[q, local, w, 1.0 / rng.choice([60.0, 240.0])],
+            4: np.r_[rng.normal(0, 3, 6), 0.0, -10.0 / 240.0, 0.0, 0.97 ** (1 / 240.0), 0.97 ** (1 / 240.0)],
+        }
+        for op, operands in cases.items():
+            operands = np.ascontiguousarray(operands, dtype=np.float32)
+            a, b = np.zeros(6, dtype=np.float32), np.zeros(6, dtype=np.float32)
+            assert dev.device_on_host_eval_integration(op, _ptr(operands), _ptr(a)) == 0
+            assert orc.oracle_eval_integration(op, _ptr(operands), _ptr(b)) == 0
+            assert np.isfinite(b).all()
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "integration op %d, trial %d: %s vs %s" % (op, trial, a, b)
 
 
 def test_experimental_kernel_flags_still_compile(tmp_path):

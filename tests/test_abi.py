@@ -66,6 +66,21 @@ def test_product_sources_never_reference_the_oracle():
                 assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text.lower(), "%s mentions the oracle" % os.path.join(dirpath, f)
 
 
+def test_only_the_checkers_load_the_oracle():
+    """Outside tests/ (which includes the diagnostic scripts of tests/tools) only bench.py (cpu_baseline / --impl reference legs) and
+    __graft_entry__.py (build() compiles it, smoke() checks against it) may touch oracle/."""
+    allowed = {"bench.py", "__graft_entry__.py"}
+    for dirpath, dirnames, files in os.walk(ROOT):
+        rel = os.path.relpath(dirpath, ROOT)
+        dirnames[:] = [d for d in dirnames if not d.startswith(".") and d not in ("gpurun_out", "baseline", "build", "__pycache__")]
+        if rel == "." :
+            dirnames[:] = [d for d in dirnames if d not in ("tests", "oracle")]
+        for f in files:
+            if f.endswith(".py") and not (rel == "." and f in allowed):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b|oracle[/\\.]binding|libbepu_oracle", text, flags=re.M), "%s uses the oracle" % os.path.join(rel, f)
+
+
 def test_public_header_is_plain_c(tmp_path):
     """include/bepucuda.h is the drop-in boundary: it has to compile as C99 (what a P/Invoke / cgo / ctypes binding generator consumes) and as
     C++11, with no CUDA or torch types in any signature."""

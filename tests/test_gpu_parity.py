@@ -101,7 +101,7 @@ def test_ragdolls_substepped_servo_variant_bit_exact(libs):
 
 def test_ragdolls_persistent_fast_within_tolerance(libs):
     """Fast build on joints: relative RMS error <= 1e-3, max abs error <= 2e-2 after one frame (measured ~3e-5 / 1e-3; the twist/servo angle
-    measurements go through acos near 1, which amplifies rounding: see tools/fast_error_stats.py)."""
+    measurements go through acos near 1, which amplifies rounding: see tests/tools/fast_error_stats.py)."""
     _parity(scenes.ragdolls(60, seed=5), exact=False, mode=EXEC_PERSISTENT, rel_rms=1e-3, max_abs=2e-2, substeps=1, velocity_iterations=4)
 
 

@@ -5,14 +5,14 @@ held to a tolerance by the GPU tests; over many frames a rigid-body simulation i
 size of that effect with a CPU proxy: the oracle compiled with `-ffp-contract=fast -mfma` against the regular `-ffp-contract=off` build, same
 scenes, same seeds (the GPU's contraction choices differ in detail, the growth rate does not).
 
-    python tools/drift_curve.py
+    python tests/tools/drift_curve.py
 """
 import ctypes as C
 import os
 import subprocess
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 
 from bepuphysics2_b200 import scenes
@@ -25,7 +25,7 @@ DT = 1 / 60
 
 def build_contracting_oracle():
     out = os.path.join(HERE, "bin", "libbepu_oracle_fma.so")
-    src = os.path.join(HERE, "..", "oracle", "bepu_oracle.cpp")
+    src = os.path.join(HERE, "..", "..", "oracle", "bepu_oracle.cpp")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=fast", "-mfma", "-fno-fast-math", "-march=x86-64-v3", "-Wno-psabi",
                            "-shared", "-o", out, src])

@@ -1,15 +1,15 @@
 """One constraint graph over N GPUs (bepucuda_set_boundary_bodies): every rank holds all bodies and its slab's share of every batch; after each
 WarmStart / Solve stage the written body records are all-reduced with NCCL (int32 sum of bit patterns, one writer per body and stage).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/sharded_nccl.py --bodies 20000 --check
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/tools/sharded_nccl.py --bodies 20000 --check
 
 --check compares every rank's final body state with the CPU oracle's single-process result, bit for bit (strict build). Prints ms per step."""
 import argparse
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np
 import torch
 import torch.distributed as dist

@@ -249,7 +249,7 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, r["description"]),
         "cpu_baseline": {"value": r["value"], "unit": "constraint-iterations/s", "cores": r["cores"], "kind": "port",
-                         "sample": "%d full frames of the same workload (C++ restatement of the reference solver, AVX2 8-wide + OpenMP; the C# reference cannot be built here)" % args.steps},
+                         "sample": "%d full frames of the same workload (C++ restatement of the reference solver, AVX2 8-wide, one worker per core with spin syncs between batch stages; the C# reference cannot be built here)" % args.steps},
         "e2e": {"value": r["value"], "unit": "constraint-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -413,7 +413,7 @@ def main():
             cb = cpu_reference_run(args, steps=3, warmup=1, threads=args.cpu_threads)
             c1 = cpu_reference_run(args, steps=1, warmup=0, threads=1)  # the reference's own benchmarks run single-threaded (ShapePileBenchmark.cs:L228)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "constraint-iterations/s", "cores": cb["cores"], "kind": "port",
-                                    "sample": "3 full frames of the same workload after 1 warm-up (C++ restatement of the reference solver, AVX2 8-wide + OpenMP over bundles; %.1f ms/frame)" % cb["ms_per_step"],
+                                    "sample": "3 full frames of the same workload after 1 warm-up (C++ restatement of the reference solver, AVX2 8-wide, one worker per core with spin syncs between batch stages; %.1f ms/frame)" % cb["ms_per_step"],
                                     "single_thread": {"value": c1["value"], "ms_per_step": c1["ms_per_step"], "sample": "1 frame, 1 thread, same code"}}
         print(json.dumps(line))
     if ts is not None:

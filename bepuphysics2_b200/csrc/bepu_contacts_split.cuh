@@ -1,11 +1,12 @@
-// PROTOTYPE ("two lanes per two-body constraint") -- lives under tests/ until a kernel uses it.
+// EXPERIMENT ("two lanes per two-body constraint"): only compiled into the kernels with -DBEPU_SPLIT_CONTACTS (off in the shipped
+// library); the arithmetic is checked on the CPU by tests/test_device_source_on_host.py.
 //
 // A two-body contact manifold evaluated by a PAIR of lanes: lane `side` 0 owns body A, lane 1 owns body B. Each lane gathers, updates and
 // scatters only its own body and computes only its own body's jacobian terms; the few scalars the other side needs cross through
 // X::swap(v) (device: __shfl_xor_sync(0xffffffff, v, 1); the host test uses a two-thread rendezvous). Every floating-point expression is
 // assembled in the operand order of the one-lane functions in csrc/bepu_contacts.cuh (which follow ContactConvexTypes.cs, PenetrationLimit.cs,
-// TangentFriction.cs, TwistFriction.cs), so both lanes hold bit-identical impulses and the result is bit-identical to the one-lane evaluation:
-// tests/test_device_source_on_host.py::test_split_lane_contacts_match_the_oracle_bit_for_bit.
+// TangentFriction.cs, TwistFriction.cs), so both lanes hold bit-identical impulses and the result is bit-identical to the one-lane evaluation
+// (tests/test_device_source_on_host.py, split-lane test).
 // The dependent chain per lane roughly halves (one cross product, one inertia sandwich, two dot products and one body update per row instead
 // of two each), for 3 exchanges per penetration row, 10 for the tangent friction, 2 for the twist friction and none in WarmStart.
 #pragma once

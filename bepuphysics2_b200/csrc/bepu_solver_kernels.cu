@@ -34,7 +34,12 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
         cudaFuncSetAttribute(constraint_stage_kernel<STAGE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carveout_set[device & 63] = true;
     }
+#ifdef BEPU_SPLIT_CONTACTS
+    const size_t warps = (MINB == 1 && STAGE != kStageIncremental) ? (size_t)work_count * 2 : (size_t)work_count;  // experiment: two warps per bundle
+    const unsigned blocks = (unsigned)((warps * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
+#else
     const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
+#endif
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(blocks);
     cfg.blockDim = dim3(kStageBlockThreads);

@@ -7,7 +7,7 @@
 #define BEPU_NS bepu_device_on_host
 #include "bepu_joints_more.cuh"  // pulls in bepu_joints.cuh, bepu_contacts.cuh, bepu_device_math.cuh (with the stub cuda_runtime.h)
 #include "bepu_integration.cuh"
-#include "experiments/contacts_split.cuh"
+#include "bepu_contacts_split.cuh"
 
 #include <atomic>
 #include <thread>
@@ -125,7 +125,7 @@ extern "C" int32_t device_on_host_eval_integration(int32_t op, const float* in, 
     return 0;
 }
 
-// ---- lane-pair prototype (experiments/contacts_split.cuh): two host threads stand in for the two lanes, X::swap is a rendezvous ------------
+// ---- lane-pair experiment (csrc/bepu_contacts_split.cuh): two host threads stand in for the two lanes, X::swap is a rendezvous ------------
 namespace {
 struct PairExchange {
     std::atomic<int> arrived{0};

@@ -28,7 +28,7 @@ DT = 1.0 / 240.0  # a substep of the 8 x 2 configuration at 1/30 s
 def device_on_host(request):
     lib = os.path.join(HERE, "libdevice_on_host%s.so" % ("" if request.param == "default" else "_" + request.param))
     defines = ["-DBEPU_ROLLED_CONTACTS"] if request.param == "rolled" else []
-    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h"), os.path.join(HERE, "experiments", "contacts_split.cuh")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh", "bepu_integration.cuh")]
+    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h"), os.path.join(CSRC, "bepu_contacts_split.cuh")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh", "bepu_integration.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-pthread"] + defines +
                               ["-I", os.path.join(HERE, "stubs"), "-I", HERE, "-I", CSRC, "-shared", "-fPIC", "-o", lib, srcs[0]])
@@ -112,7 +112,7 @@ def test_device_constraint_source_matches_the_oracle_bit_for_bit(libs, device_on
 
 
 def test_split_lane_contacts_match_the_oracle_bit_for_bit(libs, device_on_host):
-    """Prototype of DESIGN.md §9 "two lanes per two-body constraint" (tests/device_on_host/experiments/contacts_split.cuh): Contact1..4 evaluated
+    """Experiment of DESIGN.md §9 "two lanes per two-body constraint" (csrc/bepu_contacts_split.cuh, compiled into the kernels only with -DBEPU_SPLIT_CONTACTS): Contact1..4 evaluated
     by a PAIR of lanes, each owning one body and exchanging a few scalars (two host threads and a rendezvous stand in for the lane pair and its
     shuffle). WarmStart and Solve must reproduce the oracle -- hence the one-lane device functions -- bit for bit."""
     dev, orc = device_on_host
@@ -179,13 +179,13 @@ def test_device_integration_source_matches_the_oracle_bit_for_bit(libs, device_o
 
 
 def test_experimental_kernel_flags_still_compile(tmp_path):
-    """The staged experiments of DESIGN.md §9 (-DBEPU_ROLLED_CONTACTS, -DBEPU_STAGE_SM_LOCALITY) are compiled out of the shipped library; keep them
+    """The staged experiments of DESIGN.md §9 (-DBEPU_ROLLED_CONTACTS, -DBEPU_STAGE_SM_LOCALITY, -DBEPU_SPLIT_CONTACTS) are compiled out of the shipped library; keep them
     building (Solve unit, both register budgets, no warnings) so that a GPU A/B can start from a working variant."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-DBEPU_NS=bepu_fast", "-prec-div=false",
-           "-prec-sqrt=false", "-DBEPU_UNIT=2", "-DBEPU_ROLLED_CONTACTS", "-DBEPU_STAGE_SM_LOCALITY=148", "-c", os.path.join(CSRC, "bepu_solver_kernels.cu"), "-o", str(tmp_path / "solve_variant.o")]
+           "-prec-sqrt=false", "-DBEPU_UNIT=2", "-DBEPU_ROLLED_CONTACTS", "-DBEPU_STAGE_SM_LOCALITY=148", "-DBEPU_SPLIT_CONTACTS", "-c", os.path.join(CSRC, "bepu_solver_kernels.cu"), "-o", str(tmp_path / "solve_variant.o")]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     assert "warning" not in r.stdout, r.stdout

@@ -569,6 +569,7 @@ int32_t bepucuda_begin_constraints(bepucuda_ctx* ctx, int32_t source_bundle_widt
     ctx->W = source_bundle_width;
     ctx->batch_count = batch_count;
     ctx->sources.clear();
+    ctx->pending_h2d.clear();  // queued refreshes target raw-arena addresses that are recycled below; a re-describe uploads everything anyway
     ctx->raw_arena.reset();
     ctx->pinned_arena.reset();
     ctx->constraints_open = true;
@@ -1108,6 +1109,7 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
     CK(cudaSetDevice(ctx->device));
     std::memset(out, 0, sizeof(*out));
     if (ctx->data_dirty) {
+        { int rc = flush_chunks(ctx, ctx->pending_h2d); if (rc != BEPUCUDA_OK) return rc; }  // refreshed rows may still be queued (bepucuda_update_type_batch)
         launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
                                 kTransposePrestep | kTransposeImpulses, ctx->stream);
         ctx->data_dirty = false;

@@ -1,5 +1,5 @@
 // ORACLE — test infrastructure only (see bepu_math.h header). Joint / motor / servo / limit constraint functions, each restating the
-// reference file:line cited next to it. PARITY UNPINNED (no golden vectors in the reference for these).
+// reference file:line cited next to it. Pinned bit for bit to the reference's C# text through oracle/ref_transpile (tests/test_oracle_pinned_to_reference.py).
 #pragma once
 #include "bepu_contacts.h"
 #include "bepu_math.h"

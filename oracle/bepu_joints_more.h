@@ -1,6 +1,6 @@
 // ORACLE — test infrastructure only (see bepu_math.h header). The remaining joint / motor / servo / limit constraint functions of the
-// reference's default type set (DefaultTypes.cs), each restating the reference file:line cited next to it. PARITY UNPINNED (the reference
-// holds no golden vectors for these).
+// reference's default type set (DefaultTypes.cs), each restating the reference file:line cited next to it. Pinned bit for bit to the reference's C# text
+// through oracle/ref_transpile (tests/test_oracle_pinned_to_reference.py).
 //
 // MathHelper.FastReciprocal / FastReciprocalSquareRoot (MathHelper.cs:L380-413) are hardware approximations (rcpps / rsqrtps) on x86 and
 // exact 1/v, 1/sqrt(v) elsewhere; their approximation error differs between CPU vendors, so this restatement (and the CUDA path it checks)

@@ -2,9 +2,13 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use anything
 // under oracle/. The product (libbepucuda) never includes, links or calls this.
 //
-// PARITY UNPINNED: the reference ships no golden numeric vectors for the solver path and cannot be
-// built here (no .NET). This restatement follows the reference source operation-for-operation; each function cites
-// the file:line it restates.
+// PARITY: the reference ships no golden numeric vectors for the solver path and cannot be built here
+// (no .NET). This restatement follows the reference source operation-for-operation; each function cites the file:line it
+// restates. The constraint functions (all 44 types), the wide math underneath and PoseIntegration are PINNED to the C# text:
+// oracle/ref_transpile/cs2cpp.py transpiles those reference sources mechanically (syntax only) into oracle/_ref/libbepu_ref.so
+// and tests/test_oracle_pinned_to_reference.py holds this restatement to it bit for bit, live and through the committed
+// known-answer vectors tests/golden/reference_vectors.npz. UNPINNED (by construction + closed-form tests only): the solver
+// driver in bepu_oracle.cpp (substep loop, batch order, integration responsibilities, gather/scatter, bundle loops).
 //
 // Everything is templated on a lane type F: `float` (scalar-per-lane checker) or `f8` (8 x fp32 GCC vector, the
 // AVX2 shape of System.Numerics.Vector<float> on the reference's usual hosts; used for the timed CPU baseline).

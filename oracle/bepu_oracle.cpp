@@ -1,6 +1,7 @@
 // ORACLE — test infrastructure only (see bepu_math.h). Driver: body gather/scatter, embedded integration, the substep loop,
 // integration responsibilities and the final pose pass, restated from the reference's single-threaded executable spec.
-// PARITY UNPINNED: no golden vectors exist in the reference for this path; fidelity is by construction + self-checks.
+// Parity: the constraint / math / integration functions called from here are pinned to the reference's C# text (oracle/ref_transpile); THIS file's
+// driver logic (stage order, integration responsibilities, gather/scatter, bundle loops) is UNPINNED: fidelity by construction + closed-form tests.
 #include "bepu_oracle.h"
 
 #include <algorithm>

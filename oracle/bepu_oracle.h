@@ -1,6 +1,7 @@
 /* ORACLE — test infrastructure only. C API of the CPU restatement of bepuphysics2's solver + integrator path.
  * Consumes exactly the buffers the reference holds (128-B AOS BodyDynamics, AOSOA-W type batches) and mutates them in
- * place, like Simulation.Solve (BepuPhysics/Simulation.cs:L278-290) does. PARITY UNPINNED (see bepu_math.h).
+ * place, like Simulation.Solve (BepuPhysics/Simulation.cs:L278-290) does. Parity: constraint functions / wide math / pose integration pinned to the reference's C# text
+ * (oracle/ref_transpile, tests/test_oracle_pinned_to_reference.py); the driver in bepu_oracle.cpp unpinned (see bepu_math.h).
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this. */
 #ifndef BEPU_ORACLE_H
 #define BEPU_ORACLE_H

@@ -1,5 +1,5 @@
 """ORACLE — test infrastructure only. ctypes loader for oracle/libbepu_oracle.so and a helper that runs it on a host `Simulation`'s buffers
-(in place, like the reference's Simulation.Solve). PARITY UNPINNED: the reference has no golden vectors for this path and cannot run here."""
+(in place, like the reference's Simulation.Solve). Parity: the arithmetic is pinned to the reference's C# text (oracle/ref_transpile); the solver driver is unpinned (see oracle/bepu_math.h)."""
 import ctypes as C
 import os
 import subprocess

@@ -331,3 +331,100 @@ def test_fast_build_is_run_to_run_deterministic(libs, mode):
     runs = [util.run_gpu(util.make_sim(scene, substeps=4, velocity_iterations=2), DT, frames=3, strict=False, mode=mode) for _ in range(3)]
     for other in runs[1:]:
         util.compare(runs[0], other, exact=True)
+
+
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
+def test_kinematic_velocity_integration_all_execution_modes(libs, mode):
+    """IntegrateVelocityForKinematics = true (PoseIntegrator.cs:L451-487 first substep, L493-535 later substeps): the callback's gravity and damping
+    are applied to constrained kinematic bodies by the prepass, so a moving kinematic ground accelerates under the stacks resting on it, and an
+    UNconstrained kinematic takes the velocity callback in IntegrateAfterSubstepping (L596-597 `integrateVelocity`)."""
+    scene = scenes.box_stacks(5, 6)
+    extra = scenes.make_bodies(np.array([[100, 5, 0], [120, 5, 0]], dtype=np.float32), linear=np.array([[1, 2, 3], [0.5, 0, -0.25]], dtype=np.float32),
+                               angular=np.array([[0.5, 0.1, -0.3], [0, 1, 0]], dtype=np.float32), inverse_mass=np.array([1, 0], dtype=np.float32),
+                               inverse_inertia=np.array([[2, 0, 2, 0, 0, 2], [0, 0, 0, 0, 0, 0]], dtype=np.float32))
+    scene["bodies"] = np.concatenate([scene["bodies"], extra])
+    scene["bodies"][0, 8:11] = (0.2, 0.05, 0.1)   # moving, spinning, constrained kinematic ground
+    scene["bodies"][0, 12:15] = (0.0, 0.3, 0.05)
+    for allow in (0, 1):
+        integ = util.bp.IntegratorDesc.default()
+        integ.integrate_velocity_for_kinematics = 1
+        integ.allow_substeps_for_unconstrained = allow
+        a = util.make_sim(scene, substeps=3, velocity_iterations=2, integrator=integ)
+        assert len(a.constrained_kinematics) == 1
+        before = a.bodies[0, 8:11].copy()
+        got = _parity(scene, mode=mode, substeps=3, velocity_iterations=2, integrator=integ, frames=3)
+        # the prepass really ran: gravity changed the kinematic's linear velocity (it would stay constant with the flag off)
+        assert not np.array_equal(got["bodies"][0, 8:11], before)
+        assert got["bodies"][0, 9] < before[1]
+
+
+def test_kinematic_velocity_integration_with_joints_and_momentum_modes(libs):
+    """The same flag on the joint zoo (5 % kinematic partners of 1-4 body joints) with the gyroscopic angular mode: the kinematic prepass
+    never applies a momentum-conserving update (PoseIntegrator.cs:L451-535 integrate pose + callback only)."""
+    integ = util.bp.IntegratorDesc.default()
+    integ.integrate_velocity_for_kinematics = 1
+    integ.angular_integration_mode = 2
+    scene = scenes.joint_zoo(600, 40, seed=31, kinematic_fraction=0.15)
+    kin = np.flatnonzero(scene["bodies"][:, 22] == 0)
+    scene["bodies"][kin, 8:11] = np.random.default_rng(3).uniform(-0.5, 0.5, size=(kin.size, 3)).astype(np.float32)
+    _parity(scene, substeps=3, velocity_iterations=2, integrator=integ, frames=2)
+
+
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_STREAM])
+def test_benchmark_scale_pile_bit_exact(libs, mode):
+    """BASELINE config 2 at its own size (100 k bodies, ~333 k manifolds, 8 substeps x 2 iterations): the strict build against the oracle, bit for
+    bit, several frames. Unlike the small scenes a stage here is hundreds of CTAs and several grids are in flight under programmatic dependent launch."""
+    scene = scenes.shape_pile(100_000, seed=5)
+    kw = dict(substeps=8, velocity_iterations=2)
+    a = util.make_sim(scene, **kw)
+    ref = util.run_oracle(a, DT, frames=2, threads=16, simd=True)
+    for _ in range(2):  # a race would not show every time
+        got = util.run_gpu(util.make_sim(scene, **kw), DT, frames=2, strict=True, mode=mode)
+        util.compare(ref, got, exact=True)
+
+
+def _fast_drift(scene, frames, **kw):
+    """Runs `frames` frames (refresh between them, like a host application) through the oracle and through the default fast build and returns
+    the per-quantity relative RMS / max abs differences of the final body state."""
+    a, b = util.make_sim(scene, **kw), util.make_sim(scene, **kw)
+    ref = util.run_oracle(a, DT, frames=frames, threads=16, simd=True)
+    got = util.run_gpu(b, DT, frames=frames, strict=False)
+    out = {}
+    for label, cols in (("position", np.r_[4:7]), ("orientation", np.r_[0:4]), ("linear", np.r_[8:11]), ("angular", np.r_[12:15])):
+        x, y = ref["bodies"][:, cols].astype(np.float64), got["bodies"][:, cols].astype(np.float64)
+        assert np.isfinite(y).all(), label
+        d = np.abs(x - y)
+        out[label] = (float(np.sqrt((d ** 2).sum() / max((x ** 2).sum(), 1e-300))), float(d.max()))
+    imp_num = imp_den = 0.0
+    for ta, tb in zip(ref["type_batches"], got["type_batches"]):
+        v = np.broadcast_to(ta["valid"][:, None, :], ta["impulses"].shape)
+        x, y = np.where(v, ta["impulses"], 0).astype(np.float64), np.where(v, tb["impulses"], 0).astype(np.float64)
+        assert np.isfinite(y).all()
+        imp_num += ((x - y) ** 2).sum()
+        imp_den += (x ** 2).sum()
+    out["impulses"] = (float(np.sqrt(imp_num / max(imp_den, 1e-300))), 0.0)
+    print("fast-build drift after %d frames:" % frames, {k: "%.2e / %.2e" % v for k, v in out.items()})
+    return out
+
+
+def test_fast_build_benchmark_scale_multi_frame_drift_bound(libs):
+    """The BENCHMARKED build (FMA contraction, approximate div/sqrt) at the benchmark's own size, 8 frames of 8 x 2 with per-frame refresh. A
+    contracting evaluation of a chaotic system separates from the non-contracting one; profiles/r01_summary.md section 6 measured the growth
+    with a CPU proxy (frame 8, 3000-body pile: position 1.1e-8, linear 3.4e-7, angular 6.4e-7 relative RMS). Bound asserted here: 100x that."""
+    d = _fast_drift(scenes.shape_pile(100_000, seed=5), 8, substeps=8, velocity_iterations=2)
+    assert d["position"][0] <= 1e-6 and d["orientation"][0] <= 1e-5
+    assert d["linear"][0] <= 5e-5 and d["angular"][0] <= 1e-4
+    assert d["impulses"][0] <= 1e-4
+
+
+def test_fast_build_ragdoll_tube_multi_frame_drift_bound(libs):
+    """Config-3-shaped scene (ragdolls: BallSocket / SwingLimit / TwistLimit / TwistServo / SwivelHinge / Hinge / AngularMotor + contacts), 1 x 4,
+    8 frames. CPU-proxy growth at frame 8: position 2.4e-7, linear 2.4e-5, angular 2.5e-4 relative RMS; bound: 20x."""
+    d = _fast_drift(scenes.ragdolls(2000, seed=5), 8, substeps=1, velocity_iterations=4)
+    assert d["position"][0] <= 5e-6 and d["linear"][0] <= 5e-4 and d["angular"][0] <= 5e-3
+
+
+def test_fast_build_fallback_stress_multi_frame_drift_bound(libs):
+    """Config-5-shaped scene (hub bodies above the fallback threshold: levelised sequential fallback batch), 1 x 4, 8 frames."""
+    d = _fast_drift(scenes.fallback_stress(5000, hubs=5, seed=5), 8, substeps=1, velocity_iterations=4)
+    assert d["position"][0] <= 1e-5 and d["linear"][0] <= 1e-3 and d["angular"][0] <= 1e-2

@@ -1,4 +1,5 @@
-"""CPU tests that pin the oracle itself. The reference ships no golden numeric vectors for the solver path (parity unpinned), so the
+"""CPU tests that pin the oracle itself. The reference ships no golden numeric vectors for the solver path; the arithmetic is pinned to the C# text by
+tests/test_oracle_pinned_to_reference.py, and for the DRIVER (unpinned) the
 oracle is anchored on analytic known answers and internal consistency: scalar vs 8-wide evaluation, thread-count invariance, bundle-width invariance,
 momentum conservation, steady-state stack impulses, and joint error decay."""
 import numpy as np

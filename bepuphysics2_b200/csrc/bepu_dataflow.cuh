@@ -85,7 +85,7 @@ __device__ __noinline__ void run_lane_dataflow(const WorkRecord& rec, int lane, 
         }
         // once any dependency has timed out the results are void anyway: stop waiting everywhere so the kernel drains quickly
         if ((spins & 255u) == 0u && __any_sync(0xffffffffu, *reinterpret_cast<volatile int32_t*>(error_flag) == 4)) break;
-        if (spins > 4) __nanosleep(spins > 64 ? 200 : 40);
+        if (spins > 4) __nanosleep(spins > 64 ? (fp.tune[1] > 0 ? fp.tune[1] : 200) : (fp.tune[0] > 0 ? fp.tune[0] : 40));
     }
     if (empty) return;
 #pragma unroll

@@ -62,6 +62,7 @@ struct FrameParams {
     int32_t angular_mode;
     int32_t integrate_velocity_for_kinematics;
     uint32_t pass_base;        // dataflow mode: number of WarmStart/Solve passes executed since the body versions were last reset
+    int32_t tune[4];           // development knobs (env BEPUCUDA_TUNE=a,b,c,d; 0 = built-in default), never set in production
 };
 
 enum Stage : int32_t {

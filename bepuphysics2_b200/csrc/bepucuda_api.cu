@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -133,6 +134,7 @@ struct SourceTypeBatch {
 
 struct bepucuda_ctx {
     bepucuda_config cfg{};
+    int32_t tune[4] = {0, 0, 0, 0};
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_solve_begin = nullptr, ev_solve_end = nullptr, ev_up_begin = nullptr, ev_up_end = nullptr, ev_down_begin = nullptr, ev_down_end = nullptr;
@@ -392,6 +394,7 @@ void compute_frame_params(bepucuda_ctx* ctx, float dt, FrameParams* fp) {
     fp->final_steps = d.allow_substeps_for_unconstrained ? substeps : 1;
     fp->angular_mode = d.angular_integration_mode;
     fp->integrate_velocity_for_kinematics = d.integrate_velocity_for_kinematics;
+    for (int i = 0; i < 4; ++i) fp->tune[i] = ctx->tune[i];
 }
 
 }  // namespace
@@ -415,6 +418,7 @@ int32_t bepucuda_create(const bepucuda_config* cfg, bepucuda_ctx** out) {
     if (cfg->device_ordinal < 0 || cfg->device_ordinal >= count) return BEPUCUDA_ERR_INVALID_ARGUMENT;
     bepucuda_ctx* ctx = new bepucuda_ctx();
     ctx->cfg = *cfg;
+    if (const char* tune = getenv("BEPUCUDA_TUNE")) sscanf(tune, "%d,%d,%d,%d", &ctx->tune[0], &ctx->tune[1], &ctx->tune[2], &ctx->tune[3]);
     ctx->device = cfg->device_ordinal;
     ctx->launchers = cfg->strict_fp ? get_launchers_bepu_strict() : get_launchers_bepu_fast();
     ctx->pinned_arena.pinned_host = true;

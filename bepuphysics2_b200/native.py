@@ -214,8 +214,14 @@ class Simulation:
             self._host.bepuhost_destroy(self._sim)
             self._sim = None
 
-    def set_solve_description(self, substeps, velocity_iterations):
-        """SolveDescription(velocityIterationCount, substepCount); `velocity_iterations` may be a per-substep list (SolveDescription.cs:L21-38)."""
+    def set_solve_description(self, substeps, velocity_iterations, velocity_iteration_scheduler=None):
+        """SolveDescription(velocityIterationCount, substepCount); `velocity_iterations` may be a per-substep list (SolveDescription.cs:L21-38).
+        With a `velocity_iteration_scheduler` (SubstepVelocityIterationScheduler) the per-substep counts are evaluated here, host-side, with the
+        reference's rule: a scheduled count below 1 falls back to VelocityIterationCount (Solver_Solve.cs:L743-751)."""
+        if velocity_iteration_scheduler is not None:
+            assert np.isscalar(velocity_iterations)
+            scheduled = [int(velocity_iteration_scheduler(i)) for i in range(substeps)]
+            velocity_iterations = [velocity_iterations if n < 1 else n for n in scheduled]
         its = [velocity_iterations] * substeps if np.isscalar(velocity_iterations) else list(velocity_iterations)
         assert len(its) == substeps
         self.velocity_iterations = its
@@ -293,7 +299,7 @@ class CudaTimestepper:
         self.sim = simulation
         cfg = Config()
         cfg.device_ordinal, cfg.strict_fp, cfg.execution_mode = device, int(bool(strict_fp)), execution_mode
-        cfg.reserved[0] = persistent_blocks_per_sm
+        cfg.reserved[0] = persistent_blocks_per_sm or int(os.environ.get("BEPUCUDA_BLOCKS_PER_SM", "0"))  # development knob
         cfg.reserved[1] = int(bool(disable_pdl))
         ctx = C.c_void_p()
         rc = self._cuda.bepucuda_create(C.byref(cfg), C.byref(ctx))

@@ -1,26 +1,46 @@
-// CudaTimestepper : ITimestepper — DefaultTimestepper.Timestep (BepuPhysics/DefaultTimestepper.cs:L28-43) with the Solve stage on the GPU.
-// Not compiled here (no .NET toolchain in the build image). Usage: Simulation.Create(pool, narrowPhaseCallbacks, poseIntegratorCallbacks,
-// solveDescription, new CudaTimestepper(gravity, linearDamping, angularDamping)).
+// CudaTimestepper<TCallbacks> : ITimestepper — DefaultTimestepper.Timestep (BepuPhysics/DefaultTimestepper.cs:L28-43) with the Solve stage on the GPU.
+// Not compiled here (no .NET toolchain in the build image). Usage:
+//   var callbacks = new DemoPoseIntegratorCallbacks(gravity, linearDamping, angularDamping);
+//   Simulation.Create(pool, narrowPhaseCallbacks, callbacks, solveDescription,
+//                     new CudaTimestepper<DemoPoseIntegratorCallbacks>(callbacks, gravity, linearDamping, angularDamping));
+// The device integrates velocities with the declarative descriptor (gravity, damping) — it cannot call the user's IntegrateVelocity — so the three
+// BEHAVIOURAL properties of the callbacks (IPoseIntegratorCallbacks, PoseIntegrator.cs:L42-94) are taken from the SAME callbacks instance the
+// simulation was created with, and checked again every frame against the simulation's own copy: the two paths cannot diverge silently.
 using System;
 using System.Numerics;
 using BepuPhysics;
 using BepuUtilities;
 using BepuCuda;
 
-public unsafe class CudaTimestepper : ITimestepper, IDisposable
+public unsafe class CudaTimestepper<TCallbacks> : ITimestepper, IDisposable where TCallbacks : struct, IPoseIntegratorCallbacks
 {
     public event TimestepperStageHandler BeforeCollisionDetection;   // ITimestepper.cs:L20
     public event TimestepperStageHandler CollisionsDetected;         // ITimestepper.cs:L25
+    /// <summary>Set when the application subscribes to Solver.SubstepStarted / SubstepEnded (Solver_Solve.cs:L1423,L1478): the device solve raises
+    /// neither, so frames are then solved by simulation.Solve on the CPU.</summary>
+    public bool SubstepEventsInUse;
     IntPtr ctx;
     IntegratorDesc integrator;
     ulong uploadedTopology;   // signature of the constraint graph the device currently holds (0 = none)
 
-    public CudaTimestepper(Vector3 gravity, float linearDamping = 0.03f, float angularDamping = 0.03f, int device = 0, bool strict = false)
+    public CudaTimestepper(in TCallbacks callbacks, Vector3 gravity, float linearDamping = 0.03f, float angularDamping = 0.03f, int device = 0, bool strict = false)
     {
         Config cfg = default; cfg.DeviceOrdinal = device; cfg.StrictFp = strict ? 1 : 0; cfg.ExecutionMode = 0;
         IntPtr c; Check(Native.bepucuda_create(&cfg, &c)); ctx = c;
         integrator.Gravity[0] = gravity.X; integrator.Gravity[1] = gravity.Y; integrator.Gravity[2] = gravity.Z;
         integrator.LinearDamping = linearDamping; integrator.AngularDamping = angularDamping;   // DemoPoseIntegratorCallbacks (Demos/DemoCallbacks.cs:L12-105)
+        integrator.AngularIntegrationMode = (int)callbacks.AngularIntegrationMode;               // PoseIntegrator.cs:L59
+        integrator.AllowSubstepsForUnconstrained = callbacks.AllowSubstepsForUnconstrainedBodies ? 1 : 0;   // L66
+        integrator.IntegrateVelocityForKinematics = callbacks.IntegrateVelocityForKinematics ? 1 : 0;             // L72
+    }
+
+    bool CallbacksMatch(Simulation simulation)
+    {
+        if (simulation.PoseIntegrator is not PoseIntegrator<TCallbacks> poseIntegrator) return false;
+        ref var live = ref poseIntegrator.Callbacks;
+        return (int)live.AngularIntegrationMode == integrator.AngularIntegrationMode
+            && (live.AllowSubstepsForUnconstrainedBodies ? 1 : 0) == integrator.AllowSubstepsForUnconstrained
+            && (live.IntegrateVelocityForKinematics ? 1 : 0) == integrator.IntegrateVelocityForKinematics;
     }
 
     public void Timestep(Simulation simulation, float dt, IThreadDispatcher threadDispatcher = null)
@@ -30,8 +50,10 @@ public unsafe class CudaTimestepper : ITimestepper, IDisposable
         BeforeCollisionDetection?.Invoke(dt, threadDispatcher);
         simulation.CollisionDetection(dt, threadDispatcher);
         CollisionsDetected?.Invoke(dt, threadDispatcher);
-        if (!SolveOnDevice(simulation, dt))
-            simulation.Solve(dt, threadDispatcher);          // unsupported constraint type this frame: CPU path, as before
+        // CPU path, as before, when the frame cannot run on the device: an unsupported constraint type, callbacks whose behavioural properties differ
+        // from the descriptor this timestepper was built with, or substep events in use.
+        if (SubstepEventsInUse || !CallbacksMatch(simulation) || !SolveOnDevice(simulation, dt))
+            simulation.Solve(dt, threadDispatcher);
         simulation.IncrementallyOptimizeDataStructures(threadDispatcher);
     }
 
@@ -41,8 +63,12 @@ public unsafe class CudaTimestepper : ITimestepper, IDisposable
         ref var bodies = ref simulation.Bodies.ActiveSet;
         // SolveDescription (SolveDescription.cs:L21-38): the scheduler is evaluated host-side (Solver_Solve.cs:L743-751).
         var iterations = stackalloc int[solver.SubstepCount];
+        // GetVelocityIterationCountForSubstepIndex: a scheduler result below 1 falls back to VelocityIterationCount (Solver_Solve.cs:L743-751).
         for (int i = 0; i < solver.SubstepCount; ++i)
-            iterations[i] = solver.VelocityIterationScheduler == null ? solver.VelocityIterationCount : Math.Max(1, solver.VelocityIterationScheduler(i));
+        {
+            int scheduled = solver.VelocityIterationScheduler == null ? solver.VelocityIterationCount : solver.VelocityIterationScheduler(i);
+            iterations[i] = scheduled < 1 ? solver.VelocityIterationCount : scheduled;
+        }
         Check(Native.bepucuda_set_solve_description(ctx, solver.SubstepCount, iterations, solver.FallbackBatchThreshold));
         fixed (IntegratorDesc* d = &integrator) Check(Native.bepucuda_set_integrator(ctx, d));
         Check(Native.bepucuda_upload_bodies(ctx, bodies.DynamicsState.Memory, bodies.Count));                       // BodySet.cs:L33

@@ -110,3 +110,19 @@ def test_csharp_binding_declares_every_entry_point():
     count = lambda args: 0 if args.strip() in ("", "void") else args.count(",") + 1
     for name in declared:
         assert count(declared[name]) == count(bound[name]), "%s: %d C parameters vs %d in the C# binding" % (name, count(declared[name]), count(bound[name]))
+
+
+def test_csharp_timestepper_follows_the_reference_scheduler_rule_and_checks_the_callbacks():
+    """integration/csharp/CudaTimestepper.cs evaluates the velocity-iteration scheduler host-side: a result below 1 means VelocityIterationCount
+    (Solver_Solve.cs:L743-751), never Math.Max(1, n); and it takes the behavioural integrator properties from the simulation's callbacks."""
+    cs = open(os.path.join(ROOT, "integration", "csharp", "CudaTimestepper.cs")).read()
+    assert "Math.Max(1, solver.VelocityIterationScheduler" not in cs
+    assert re.search(r"scheduled\s*<\s*1\s*\?\s*solver\.VelocityIterationCount\s*:\s*scheduled", cs)
+    for prop in ("AngularIntegrationMode", "AllowSubstepsForUnconstrainedBodies", "IntegrateVelocityForKinematics"):
+        assert "callbacks." + prop in cs and "live." + prop in cs
+    # the Python host mirror applies the same rule
+    import bepuphysics2_b200 as bp
+
+    sim = bp.Simulation(substeps=4, velocity_iterations=3)
+    sim.set_solve_description(4, 3, velocity_iteration_scheduler=lambda i: [2, 0, -1, 5][i])
+    assert sim.velocity_iterations == [2, 3, 3, 5]

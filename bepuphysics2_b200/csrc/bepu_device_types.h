@@ -107,6 +107,15 @@ struct StageOp {
 constexpr int kChainDegreeShift = 16;
 constexpr uint32_t kChainRankMask = 0xFFFFu;
 
+// Dataflow mode tables (built at bepucuda_end_constraints, see bepu_dataflow.cuh). Arrays parallel to the body reference arena are addressed as
+// refs + delta (in int32 elements).
+struct DataflowTables {
+    long long chain_delta;      // chain words
+    long long succ_delta;       // per (lane, body slot): work index of the bundle holding the NEXT constraint on that body (the first one after the last)
+    const int2* dep_counts;     // per bundle: x = (lane, dynamic body) dependencies per pass, y = those that are the first constraint on their body
+    unsigned int* counters;     // per bundle: notifications received since the start of the solve, starting at y
+};
+
 struct TypeInfo {
     int32_t bodies, prestep_rows, impulse_rows, incremental;
     int32_t solve_bytes, warm_start_bytes, incremental_bytes;  // SURVEY.md §8d algorithmic bytes per evaluation

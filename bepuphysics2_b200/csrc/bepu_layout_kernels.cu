@@ -191,6 +191,51 @@ __global__ void chain_degree_kernel(const DeviceTypeBatch* __restrict__ tbs, con
         *c |= (uint32_t)degree << kChainDegreeShift;
     }
 }
+// Dataflow successor table. Phase 0 (one launch per device batch, LAST batch first): succ = work index of the bundle that holds the next constraint
+// on the body (none yet for the body's last constraint); next_bundle[body] ends as the body's FIRST bundle. Phase 1 (one launch): the last
+// constraint's successor wraps around to the first, and the per-bundle dependency counts are taken.
+__global__ void chain_succ_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, int work_base, const int32_t* __restrict__ bodies_per_type,
+                                  long long succ_delta, int32_t* next_bundle) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int nb = bodies_per_type[tb.type_id];
+    for (int s = 0; s < nb; ++s) {
+        int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
+        const int32_t enc = *r;
+        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) { r[succ_delta] = -1; continue; }
+        const int idx = enc & kRefIndexMask;
+        r[succ_delta] = next_bundle[idx];  // a dynamic body appears at most once per device batch: no race inside a launch
+        next_bundle[idx] = work_base + warp;
+    }
+}
+__global__ void chain_finish_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
+                                    long long chain_delta, long long succ_delta, const int32_t* __restrict__ next_bundle, int2* dep_counts) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int nb = bodies_per_type[tb.type_id];
+    int deps = 0, first = 0;
+    for (int s = 0; s < nb; ++s) {
+        int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
+        const int32_t enc = *r;
+        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
+        if (r[succ_delta] < 0) r[succ_delta] = next_bundle[enc & kRefIndexMask];
+        ++deps;
+        first += ((uint32_t)r[chain_delta] & kChainRankMask) == 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        deps += __shfl_xor_sync(0xffffffffu, deps, o);
+        first += __shfl_xor_sync(0xffffffffu, first, o);
+    }
+    if (lane == 0) dep_counts[warp] = make_int2(deps, first);
+}
+__global__ void reset_counters_kernel(const int2* __restrict__ dep_counts, unsigned int* counters, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counters[i] = (unsigned int)dep_counts[i].y;
+}
 __global__ void reset_versions_kernel(float4* velocity, int body_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= body_count) return;
@@ -265,6 +310,20 @@ void launch_chain_degree(const DeviceTypeBatch* tbs, const WorkItem* work, int w
                          int32_t* error_flag, cudaStream_t s) {
     if (work_count <= 0) return;
     chain_degree_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, chain_delta, body_counter, error_flag);
+}
+void launch_chain_succ(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, int work_base, const int32_t* bodies_per_type, long long succ_delta, int32_t* next_bundle,
+                       cudaStream_t s) {
+    if (work_count <= 0) return;
+    chain_succ_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, work_base, bodies_per_type, succ_delta, next_bundle);
+}
+void launch_chain_finish(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, long long succ_delta,
+                         const int32_t* next_bundle, int2* dep_counts, cudaStream_t s) {
+    if (work_count <= 0) return;
+    chain_finish_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, chain_delta, succ_delta, next_bundle, dep_counts);
+}
+void launch_reset_counters(const int2* dep_counts, unsigned int* counters, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    reset_counters_kernel<<<blocks_for((size_t)n, 256), 256, 0, s>>>(dep_counts, counters, n);
 }
 void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s) {
     if (body_count <= 0) return;

@@ -32,6 +32,12 @@ void launch_batched_copy(const CopyChunk* chunks, int chunk_count, cudaStream_t 
 void launch_chain_rank(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, int32_t* body_counter, cudaStream_t s);
 void launch_chain_degree(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, const int32_t* body_counter,
                          int32_t* error_flag, cudaStream_t s);
+// Dataflow successor table and per-bundle dependency counts (see DataflowTables).
+void launch_chain_succ(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, int work_base, const int32_t* bodies_per_type, long long succ_delta, int32_t* next_bundle,
+                       cudaStream_t s);
+void launch_chain_finish(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, long long succ_delta,
+                         const int32_t* next_bundle, int2* dep_counts, cudaStream_t s);
+void launch_reset_counters(const int2* dep_counts, unsigned int* counters, int n, cudaStream_t s);
 void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s);
 void launch_ownership_pass1(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
                             int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, int32_t* error_flag, cudaStream_t s);
@@ -59,8 +65,8 @@ struct SolverLaunchers {
     int (*persistent)(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                       unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
     // Dataflow persistent kernel: like `persistent`, but kStageRegion ops run a whole substep's WarmStart + Solve passes with per-body version
-    // dependencies (chain words at refs + chain_delta) instead of a barrier per (batch, stage). error_flag is set to 4 if a dependency never arrives.
-    int (*dataflow)(const StageOp* program, int op_count, const WorkRecord* records, long long chain_delta, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
+    // dependencies (DataflowTables) instead of a barrier per (batch, stage). error_flag is set to 4 if a dependency never arrives.
+    int (*dataflow)(const StageOp* program, int op_count, const WorkRecord* records, const DataflowTables& df, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                     unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s);
 };
 const SolverLaunchers* get_launchers_bepu_fast();

@@ -17,7 +17,7 @@ void launch_stage_warm_start(const WorkRecord* records, int work_count, const Bo
 void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
 int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                            unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
-int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, long long chain_delta, const int32_t* kinematics, const BodyBuffers& B,
+int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, const DataflowTables& df, const int32_t* kinematics, const BodyBuffers& B,
                          const FrameParams* fp, unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s);
 
 #if BEPU_UNIT <= 3
@@ -34,12 +34,7 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
         cudaFuncSetAttribute(constraint_stage_kernel<STAGE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carveout_set[device & 63] = true;
     }
-#ifdef BEPU_SPLIT_CONTACTS
-    const size_t warps = (MINB == 1 && STAGE != kStageIncremental) ? (size_t)work_count * 2 : (size_t)work_count;  // experiment: two warps per bundle
-    const unsigned blocks = (unsigned)((warps * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
-#else
     const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
-#endif
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(blocks);
     cfg.blockDim = dim3(kStageBlockThreads);
@@ -99,9 +94,9 @@ int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecor
     return launch_persistent(program, op_count, records, kinematics, B, fp, barrier_counter, blocks_per_sm, s);
 }
 #elif BEPU_UNIT == 5
-int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, long long chain_delta, const int32_t* kinematics, const BodyBuffers& B,
+int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, const DataflowTables& df, const int32_t* kinematics, const BodyBuffers& B,
                          const FrameParams* fp, unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s) {
-    return launch_dataflow(program, op_count, records, chain_delta, kinematics, B, fp, barrier_counter, error_flag, blocks_per_sm, s);
+    return launch_dataflow(program, op_count, records, df, kinematics, B, fp, barrier_counter, error_flag, blocks_per_sm, s);
 }
 #else
 #error "BEPU_UNIT must be 0..5"

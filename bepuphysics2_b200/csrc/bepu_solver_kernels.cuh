@@ -10,9 +10,6 @@
 #include "bepu_contacts.cuh"
 #include "bepu_joints_more.cuh"
 #include "bepu_integration.cuh"
-#ifdef BEPU_SPLIT_CONTACTS
-#include "bepu_contacts_split.cuh"
-#endif
 #include "bepu_device_types.h"
 
 namespace BEPU_NS {
@@ -265,42 +262,6 @@ BEPU_DI void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32
                  "l"(policy)
                  : "memory");
 }
-#ifdef BEPU_SPLIT_CONTACTS
-// experiment: Contact1..4 (two bodies) by lane PAIRS -- lane 2c owns body A of constraint c, lane 2c + 1 body B; a warp covers half
-// a bundle (16 constraints), so such stages are launched with two warps per bundle. See bepu_contacts_split.cuh.
-struct DevicePair {
-    BEPU_DI static float swap(float v) { return __shfl_xor_sync(3u << (threadIdx.x & 30), v, 1); }
-};
-template <int N, int STAGE> BEPU_DI void run_split_lane(int side, const Inertia& mine, const FrameParams& fp, StagedRows p, StagedAcc a, Velocity& v) {
-    if constexpr (STAGE == kStageSolve) ConvexTwoBodySplit<N>::template solve<DevicePair>(side, mine, fp.dt, fp.inverse_dt, p, a, v);
-    else ConvexTwoBodySplit<N>::warm_start(side, mine, p, a, v);
-}
-template <int STAGE>
-BEPU_DI void run_split_bundle(const WorkRecord& rec, int lane, int half, uint32_t slab_addr, uint32_t prestep_bytes, uint32_t bar, uint32_t encA, uint32_t encB, const BodyBuffers& B,
-                              const FrameParams& fp) {
-    const int c = half * 16 + (lane >> 1), side = lane & 1;
-    if ((int32_t)encA == kRefEmpty) return;  // both lanes of the pair see the same reference: they leave together, before any exchange
-    const uint32_t enc = side ? encB : encA;
-    const StagedRows p{slab_addr + c * 4, bar};
-    const StagedAcc a{slab_addr + prestep_bytes + c * 4, rec.impulses + c};
-    BodyState b;
-    Velocity v;
-    if constexpr (STAGE == kStageSolve) {
-        load_velocity(B.velocity, enc & kRefIndexMask, v);
-        load_inertia(B.inertia_world, enc & kRefIndexMask, b.inertia);
-    } else {
-        gather_for_warm_start<STAGE, false>(enc, B, fp, b, v);
-    }
-    rows_ready(p);
-    switch (rec.type_id) {
-        case 4: run_split_lane<1, STAGE>(side, b.inertia, fp, p, a, v); break;
-        case 5: run_split_lane<2, STAGE>(side, b.inertia, fp, p, a, v); break;
-        case 6: run_split_lane<3, STAGE>(side, b.inertia, fp, p, a, v); break;
-        default: run_split_lane<4, STAGE>(side, b.inertia, fp, p, a, v); break;
-    }
-    if (!(enc & kRefKinematicBit)) store_velocity(B.velocity, enc & kRefIndexMask, v);
-}
-#endif
 
 // ---- kernels ------------------------------------------------------------------------------------------------------------
 #ifndef BEPU_STAGE_BLOCK_THREADS
@@ -326,48 +287,18 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
     __shared__ __align__(128) float slab[kStaged ? kWarps * kStageSlabRows * kLanes : 1];
     __shared__ __align__(8) unsigned long long bars[kWarps];
     const int warp_in_block = threadIdx.x >> 5;
-#ifdef BEPU_STAGE_SM_LOCALITY
-    // experiment: in the single-wave instantiation give every SM a CONTIGUOUS run of work records instead of every S-th CTA, so the
-    // warps of an SM -- which leave griddepcontrol.wait together -- mostly run the same constraint type and share instruction fetch.
-    // blockIdx -> record block is a bijection: CTA k * S + s takes block start(s) + k, start(s) = s * q + min(s, r), q = G / S, r = G % S
-    // (k <= q, and k == q only for s < r). BEPU_STAGE_SM_LOCALITY is S, the SM count (148 on B200).
-    int block = blockIdx.x;
-    if (MINB == 1 && (int)gridDim.x > BEPU_STAGE_SM_LOCALITY) {
-        const int S = BEPU_STAGE_SM_LOCALITY, q = (int)gridDim.x / S, r = (int)gridDim.x % S, s = (int)blockIdx.x % S, k = (int)blockIdx.x / S;
-        block = s * q + (s < r ? s : r) + k;
-    }
-    const int global_warp = (block * kStageBlockThreads + threadIdx.x) >> 5;
-#else
     const int global_warp = (blockIdx.x * kStageBlockThreads + threadIdx.x) >> 5;
-#endif
     const int lane = threadIdx.x & 31;
     WorkRecord rec{};
     uint32_t enc0 = (uint32_t)kRefEmpty, enc1 = 0;
-#ifdef BEPU_SPLIT_CONTACTS
-    // two warps per bundle in the single-wave WarmStart / Solve instantiations: `half` picks the 16 constraints a warp's lane pairs take when the
-    // bundle is a two-body convex contact type; for every other type warp 0 runs the whole bundle as usual and warp 1 idles.
-    constexpr bool kSplit = MINB == 1 && kStaged;
-    const int warp = kSplit ? global_warp >> 1 : global_warp, half = kSplit ? global_warp & 1 : 0;
-    bool split_type = false;
-    int ref_lane = lane;
-    bool active = warp < work_count;
-#else
     const int warp = global_warp;
     const bool active = warp < work_count;
-#endif
     const uint32_t slab_addr = kStaged ? smem_u32(slab) + warp_in_block * kStageSlabBytes : 0;
     const uint32_t bar = smem_u32(&bars[warp_in_block]);
     const bool early_rows = kStaged && (flags & kStagePrefetchRows);
     uint32_t prestep_bytes = 0, impulse_bytes = 0;
     if (active) {
         rec = load_record(records + warp);
-#ifdef BEPU_SPLIT_CONTACTS
-        split_type = kSplit && rec.type_id >= 4 && rec.type_id <= 7;
-        if (kSplit && !split_type && half == 1) active = false;
-        if (split_type) ref_lane = half * 16 + (lane >> 1);
-    }
-    if (active) {
-#endif
         if constexpr (kStaged) {
             prestep_bytes = kStageRowCounts.prestep[rec.type_id] * (kLanes * 4);
             impulse_bytes = kStageRowCounts.impulses[rec.type_id] * (kLanes * 4);
@@ -381,13 +312,8 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
                 }
             }
         }
-#ifdef BEPU_SPLIT_CONTACTS
-        enc0 = ldg_nc_u32(rec.refs + ref_lane);
-        enc1 = ldg_nc_u32(rec.refs + kLanes + ref_lane);
-#else
         enc0 = ldg_nc_u32(rec.refs + lane);
         enc1 = ldg_nc_u32(rec.refs + kLanes + lane);
-#endif
     }
     const FrameParams fp = *fpp;
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -401,13 +327,7 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
             bulk_copy_g2s(slab_addr + prestep_bytes, rec.impulses, impulse_bytes, bar, policy);
         }
         __syncwarp();
-#ifdef BEPU_SPLIT_CONTACTS
-        if (split_type) {
-            run_split_bundle<STAGE>(rec, lane, half, slab_addr, prestep_bytes, bar, enc0, enc1, B, fp);
-            return;
-        }
-#endif
-        run_bundle_rows<STAGE>(rec, lane, StagedRows{slab_addr + lane * 4, bar}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp);
+        run_bundle_rows<STAGE>(rec, lane, StagedRows{slab_addr + lane * 4, bar, 0u}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp);
     } else {
         run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
     }

@@ -159,7 +159,7 @@ struct bepucuda_ctx {
     bool constraints_open = false, constraints_ready = false, data_dirty = false;
     std::vector<SourceTypeBatch> sources;
     ChunkArena raw_arena, pinned_arena;
-    DeviceBuffer chain32, body_counter, record_table, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
+    DeviceBuffer chain32, succ32, next_bundle, dep_counts, df_counters, body_counter, record_table, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
     std::vector<DeviceTypeBatch> tbs;
     std::vector<TransposeDesc> tdescs;
     std::vector<WorkItem> work;                 // grouped by device batch, then the incremental list
@@ -451,7 +451,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
     DeviceBuffer* bufs[] = {&ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
-                            &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
+                            &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
     ctx->raw_arena.release();
@@ -763,6 +763,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     }
     CK(ctx->refs32.reserve(refs_floats * 4 + 1024));  // slack: solver warps always read two body-reference rows
     CK(ctx->chain32.reserve(refs_floats * 4 + 1024));
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) CK(ctx->succ32.reserve(refs_floats * 4 + 1024));
     CK(ctx->prestep32.reserve(prestep_floats * 4 + 4));
     CK(ctx->impulses32.reserve(impulse_floats * 4 + 4));
     CK(ctx->map_table.reserve(maps.size() * 4 + 4));
@@ -873,6 +874,17 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
                               ctx->body_counter.as<int32_t>(), ctx->stream);
         launch_chain_degree(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), chain_delta,
                             ctx->body_counter.as<int32_t>(), ctx->error_dev.as<int32_t>(), ctx->stream);
+        // successor bundles (device batches visited last to first) and per-bundle dependency counts
+        const long long succ_delta = ctx->succ32.as<int32_t>() - ctx->refs32.as<int32_t>();
+        CK(ctx->next_bundle.reserve(nb * 4));
+        CK(ctx->dep_counts.reserve((size_t)std::max(ctx->all_work_count, 1) * sizeof(int2)));
+        CK(ctx->df_counters.reserve((size_t)std::max(ctx->all_work_count, 1) * 4));
+        launch_fill_i32(ctx->next_bundle.as<int32_t>(), nb, -1, ctx->stream);
+        for (auto bw = ctx->batch_work.rbegin(); bw != ctx->batch_work.rend(); ++bw)
+            launch_chain_succ(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>() + bw->first, bw->second, bw->first, ctx->bodies_per_type.as<int32_t>(), succ_delta,
+                              ctx->next_bundle.as<int32_t>(), ctx->stream);
+        launch_chain_finish(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), chain_delta, succ_delta,
+                            ctx->next_bundle.as<int32_t>(), ctx->dep_counts.as<int2>(), ctx->stream);
         ctx->versions_dirty = true;
     }
     CK(cudaGetLastError());
@@ -967,8 +979,13 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
         launches = 1;
     } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
         CK(cudaMemsetAsync(ctx->barrier_dev.ptr, 0, sizeof(unsigned int), ctx->stream));
-        const long long chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
-        int rc = ctx->launchers->dataflow(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->record_table.as<WorkRecord>(), chain_delta, ctx->kinematics_dev.as<int32_t>(),
+        DataflowTables df{};
+        df.chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
+        df.succ_delta = ctx->succ32.as<int32_t>() - ctx->refs32.as<int32_t>();
+        df.dep_counts = ctx->dep_counts.as<int2>();
+        df.counters = ctx->df_counters.as<unsigned int>();
+        launch_reset_counters(df.dep_counts, df.counters, ctx->all_work_count, ctx->stream);
+        int rc = ctx->launchers->dataflow(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->record_table.as<WorkRecord>(), df, ctx->kinematics_dev.as<int32_t>(),
                                           ctx->B, ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->error_dev.as<int32_t>(), ctx->cfg.reserved[0], ctx->stream);
         if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "dataflow kernel launch");
         launches = 1;

@@ -7,7 +7,6 @@
 #define BEPU_NS bepu_device_on_host
 #include "bepu_joints_more.cuh"  // pulls in bepu_joints.cuh, bepu_contacts.cuh, bepu_device_math.cuh (with the stub cuda_runtime.h)
 #include "bepu_integration.cuh"
-#include "bepu_contacts_split.cuh"
 
 #include <atomic>
 #include <thread>
@@ -123,63 +122,4 @@ extern "C" int32_t device_on_host_eval_integration(int32_t op, const float* in, 
         return -1;
     }
     return 0;
-}
-
-// ---- lane-pair experiment (csrc/bepu_contacts_split.cuh): two host threads stand in for the two lanes, X::swap is a rendezvous ------------
-namespace {
-struct PairExchange {
-    std::atomic<int> arrived{0};
-    std::atomic<int> epoch{0};
-    float slot[2];
-    void barrier() {
-        const int e = epoch.load(std::memory_order_acquire);
-        if (arrived.fetch_add(1, std::memory_order_acq_rel) == 1) {
-            arrived.store(0, std::memory_order_relaxed);
-            epoch.store(e + 1, std::memory_order_release);
-        } else {
-            while (epoch.load(std::memory_order_acquire) == e) std::this_thread::yield();
-        }
-    }
-};
-thread_local PairExchange* t_exchange = nullptr;
-thread_local int t_side = 0;
-struct HostPair {
-    static float swap(float v) {  // what __shfl_xor_sync(0xffffffff, v, 1) gives a lane pair
-        PairExchange& x = *t_exchange;
-        x.slot[t_side] = v;
-        x.barrier();
-        const float other = x.slot[1 - t_side];
-        x.barrier();
-        return other;
-    }
-};
-template <int N> void eval_split(int stage, const float* body_states, float dt, float* prestep, float* impulses, float* velocities) {
-    PairExchange exchange;
-    auto lane = [&](int side) {
-        t_exchange = &exchange;
-        t_side = side;
-        const float* f = body_states + 14 * side;
-        Inertia mine{{f[7], f[8], f[9], f[10], f[11], f[12]}, f[13]};
-        float* w = velocities + 6 * side;
-        Velocity v{{w[0], w[1], w[2]}, {w[3], w[4], w[5]}};
-        if (stage == 0) ConvexTwoBodySplit<N>::warm_start(side, mine, GlobalRows{prestep}, GlobalAcc{impulses}, v);
-        else ConvexTwoBodySplit<N>::template solve<HostPair>(side, mine, dt, 1.0f / dt, GlobalRows{prestep}, GlobalAcc{impulses}, v);
-        w[0] = v.lin.x; w[1] = v.lin.y; w[2] = v.lin.z; w[3] = v.ang.x; w[4] = v.ang.y; w[5] = v.ang.z;
-    };
-    std::thread other(lane, 1);
-    lane(0);
-    other.join();
-}
-}  // namespace
-
-// Contact1..4 (type ids 4..7), stage 0 WarmStart / 1 Solve, evaluated by a lane pair. Same buffers as device_on_host_eval_lane.
-extern "C" int32_t device_on_host_eval_split(int32_t type_id, int32_t stage, const float* body_states, float dt, float* prestep, float* impulses, float* velocities) {
-    if (stage != 0 && stage != 1) return -1;
-    switch (type_id) {
-        case 4: eval_split<1>(stage, body_states, dt, prestep, impulses, velocities); return 0;
-        case 5: eval_split<2>(stage, body_states, dt, prestep, impulses, velocities); return 0;
-        case 6: eval_split<3>(stage, body_states, dt, prestep, impulses, velocities); return 0;
-        case 7: eval_split<4>(stage, body_states, dt, prestep, impulses, velocities); return 0;
-        default: return -1;
-    }
 }

@@ -23,12 +23,11 @@ LANES = 32
 DT = 1.0 / 240.0  # a substep of the 8 x 2 configuration at 1/30 s
 
 
-# "rolled": the same headers with -DBEPU_ROLLED_CONTACTS, the experimental loop-shaped contact path, which must stay bit-identical.
-@pytest.fixture(scope="module", params=["default", "rolled"])
-def device_on_host(request):
-    lib = os.path.join(HERE, "libdevice_on_host%s.so" % ("" if request.param == "default" else "_" + request.param))
-    defines = ["-DBEPU_ROLLED_CONTACTS"] if request.param == "rolled" else []
-    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h"), os.path.join(CSRC, "bepu_contacts_split.cuh")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh", "bepu_integration.cuh")]
+@pytest.fixture(scope="module")
+def device_on_host():
+    lib = os.path.join(HERE, "libdevice_on_host.so")
+    defines = []
+    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh", "bepu_integration.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-pthread"] + defines +
                               ["-I", os.path.join(HERE, "stubs"), "-I", HERE, "-I", CSRC, "-shared", "-fPIC", "-o", lib, srcs[0]])
@@ -39,7 +38,6 @@ def device_on_host(request):
     orc = ob.load()
     orc.oracle_eval_lane.argtypes = [C.c_int32, C.c_int32, fp, C.c_float, fp, fp, fp, C.c_int32]
     dev.device_on_host_eval_integration.argtypes = [C.c_int32, fp, fp]
-    dev.device_on_host_eval_split.argtypes = dev.device_on_host_eval_lane.argtypes
     orc.oracle_eval_integration.argtypes = [C.c_int32, fp, fp]
     return dev, orc
 
@@ -111,36 +109,6 @@ def test_device_constraint_source_matches_the_oracle_bit_for_bit(libs, device_on
     assert checked > 44 * 2 * 16
 
 
-def test_split_lane_contacts_match_the_oracle_bit_for_bit(libs, device_on_host):
-    """Experiment of DESIGN.md §9 "two lanes per two-body constraint" (csrc/bepu_contacts_split.cuh, compiled into the kernels only with -DBEPU_SPLIT_CONTACTS): Contact1..4 evaluated
-    by a PAIR of lanes, each owning one body and exchanging a few scalars (two host threads and a rendezvous stand in for the lane pair and its
-    shuffle). WarmStart and Solve must reproduce the oracle -- hence the one-lane device functions -- bit for bit."""
-    dev, orc = device_on_host
-    samples = _prestep_samples()
-    rng = np.random.default_rng(13)
-    for type_id in (4, 5, 6, 7):
-        bodies, prestep_rows, impulse_rows = ob.type_info(type_id)
-        for prestep in samples[type_id][:16]:
-            states = _random_states(rng, bodies)
-            velocities = rng.normal(0, 1.5, (bodies, 6)).astype(np.float32)
-            impulses = np.abs(rng.normal(0, 0.2, impulse_rows)).astype(np.float32)
-            if rng.random() < 0.3:
-                impulses[2:-1] = 0.0  # resting at zero penetration impulse: the clamp and the zero friction cone
-            for stage in (0, 1):
-                p_dev = np.zeros(prestep_rows * LANES, dtype=np.float32)
-                p_dev[::LANES] = prestep
-                a_dev = np.zeros(impulse_rows * LANES, dtype=np.float32)
-                a_dev[::LANES] = impulses
-                v_dev = velocities.copy()
-                p_orc, a_orc, v_orc = p_dev.copy(), a_dev.copy(), v_dev.copy()
-                assert dev.device_on_host_eval_split(type_id, stage, _ptr(states), DT, _ptr(p_dev), _ptr(a_dev), _ptr(v_dev)) == 0
-                assert orc.oracle_eval_lane(type_id, stage, _ptr(states), DT, _ptr(p_orc), _ptr(a_orc), _ptr(v_orc), LANES) == 0
-                what = "type %d stage %d" % (type_id, stage)
-                assert np.array_equal(v_dev.view(np.uint32), v_orc.view(np.uint32)), what + ": velocities"
-                assert np.array_equal(a_dev.view(np.uint32), a_orc.view(np.uint32)), what + ": accumulated impulses"
-                assert not np.array_equal(v_dev, velocities)
-
-
 def test_device_integration_source_matches_the_oracle_bit_for_bit(libs, device_on_host):
     """csrc/bepu_integration.cuh (orientation integration through the custom sin / cos, inertia rotation, both momentum-conserving angular
     updates, the velocity callback) against the oracle's restatement of PoseIntegrator.cs:L146-253, function by function."""
@@ -176,16 +144,3 @@ def test_device_integration_source_matches_the_oracle_bit_for_bit(libs, device_o
             assert orc.oracle_eval_integration(op, _ptr(operands), _ptr(b)) == 0
             assert np.isfinite(b).all()
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "integration op %d, trial %d: %s vs %s" % (op, trial, a, b)
-
-
-def test_experimental_kernel_flags_still_compile(tmp_path):
-    """The staged experiments of DESIGN.md §9 (-DBEPU_ROLLED_CONTACTS, -DBEPU_STAGE_SM_LOCALITY, -DBEPU_SPLIT_CONTACTS) are compiled out of the shipped library; keep them
-    building (Solve unit, both register budgets, no warnings) so that a GPU A/B can start from a working variant."""
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-DBEPU_NS=bepu_fast", "-prec-div=false",
-           "-prec-sqrt=false", "-DBEPU_UNIT=2", "-DBEPU_ROLLED_CONTACTS", "-DBEPU_STAGE_SM_LOCALITY=148", "-DBEPU_SPLIT_CONTACTS", "-c", os.path.join(CSRC, "bepu_solver_kernels.cu"), "-o", str(tmp_path / "solve_variant.o")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    assert r.returncode == 0, r.stdout
-    assert "warning" not in r.stdout, r.stdout

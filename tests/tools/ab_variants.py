@@ -13,13 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PKG = os.path.join(ROOT, "bepuphysics2_b200")
 VARIANTS = {
-    "rolled": ["-DBEPU_ROLLED_CONTACTS"],
-    "local": ["-DBEPU_STAGE_SM_LOCALITY=148"],
-    "rolledlocal": ["-DBEPU_ROLLED_CONTACTS", "-DBEPU_STAGE_SM_LOCALITY=148"],
-    "split": ["-DBEPU_SPLIT_CONTACTS"],
-    "all": ["-DBEPU_ROLLED_CONTACTS", "-DBEPU_STAGE_SM_LOCALITY=148", "-DBEPU_SPLIT_CONTACTS"],
     "deep16": ["-DBEPU_DEEP_MINB=16"],
-    "deep16rolled": ["-DBEPU_DEEP_MINB=16", "-DBEPU_ROLLED_CONTACTS"],
 }
 PARITY = "box_stack or shape_pile or fallback or randomised or unconstrained or registered_host or deterministic"
 

@@ -14,13 +14,15 @@
 //     counter (one 4-byte load per poll for the whole warp) until all of its (lane, body) dependencies of this pass have reported, and only then
 //     gathers the velocity records. The counter is a wake-up hint, not the synchronisation: the gather still checks every record's version and
 //     re-reads a record whose store has not landed yet, so no fence is needed between a producer's record store and its notification;
-//   * warps own bundles statically (bundle g -> warp g mod T) and walk their bundles in program order pass by pass; while a warp waits it already
-//     holds its bundle's prestep + impulse block in its shared-memory slab (one cp.async.bulk pair), its body references and -- in Solve passes --
-//     the world inertias, so a dependency link costs (notification visible) + (velocity gather) + math + (store);
+//   * warps own bundles statically (bundle g -> warp g mod T) and walk their bundles in program order; while a warp waits it already holds its
+//     bundle's prestep + impulse block in its shared-memory slab (one cp.async.bulk pair), its body references and -- in Solve passes -- the world
+//     inertias, so a dependency link costs (notification visible) + (velocity gather) + math + (store);
 //   * progress: the earliest unfinished evaluation in program order never waits (all its producers are earlier), and every warp reaches its items in
-//     program order, so with all CTAs co-resident (cooperative launch) the schedule cannot deadlock. A spin limit raises an error flag instead of hanging.
+//     program order, so with all CTAs co-resident (cooperative launch) a pass cannot deadlock. A spin limit raises an error flag instead of hanging.
 //
-// Grid barriers remain only where the reference has whole-set passes: IncrementallyUpdateForSubstep, the kinematic prepass, the final pose pass.
+// One launch = one WarmStart or Solve pass over ALL device batches (dataflow_pass_kernel<STAGE>): a step of 8 substeps x (1 + 2) passes is 24 of these
+// plus the whole-set stages the reference has anyway (IncrementallyUpdateForSubstep, kinematic prepass, final pose pass) instead of 392 stage kernels.
+// Everything is inlined into the type switch: a call per bundle would put the callee-saved registers and by-reference arguments in local memory.
 #pragma once
 #include "bepu_persistent.cuh"
 
@@ -29,6 +31,9 @@ namespace BEPU_NS {
 constexpr unsigned int kDataflowSpinLimit = 20000000u;  // ~1 s of polling: a dependency that never arrives is a bug, not a reason to hang the GPU
 constexpr int kDataflowWarps = kPersistentThreads / 32;
 constexpr int kDataflowSmemBytes = kDataflowWarps * kStageSlabBytes + kDataflowWarps * 8;
+#ifndef BEPU_DATAFLOW_MINB
+#define BEPU_DATAFLOW_MINB 2
+#endif
 
 BEPU_DI void store_velocity_versioned(float4* vel, uint32_t i, const Velocity& v, uint32_t version) {
     const float ver = __uint_as_float(version);
@@ -41,23 +46,96 @@ BEPU_DI unsigned int ld_relaxed_u32(const unsigned int* p) {
 }
 BEPU_DI void red_add_u32(unsigned int* p, unsigned int v) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// What a warp knows about its bundle before it waits.
-struct DataflowBundle {
-    WorkRecord rec;
-    unsigned int* counters;      // base of the per-bundle notification counters
-    unsigned int* my_counter;    // this bundle's
-    unsigned int target;         // notifications that must have arrived before this pass may gather
-    long long chain_delta, succ_delta;
-    uint32_t slab_addr, bar, parity, prestep_bytes;
-};
+// World inertia / pose records written by the integrating (first) constraint of a body carry a stamp in their padding word: the number of the
+// WarmStart pass that wrote them + 1. Readers of the same substep wait for that stamp instead of relying on a fence in the writer.
+BEPU_DI void store_inertia_stamped(float4* in, uint32_t i, const Inertia& r, uint32_t stamp) {
+    st256(in + 2 * (size_t)i, r.t.xx, r.t.yx, r.t.yy, r.t.zx, r.t.zy, r.t.zz, r.inv_mass, __uint_as_float(stamp));
+}
+BEPU_DI void store_pose_stamped(float4* pose, uint32_t i, V3 pos, Q4 q, uint32_t stamp) { st256(pose + 2 * (size_t)i, q.x, q.y, q.z, q.w, pos.x, pos.y, pos.z, __uint_as_float(stamp)); }
+BEPU_DI bool load_inertia_stamped(const float4* in, uint32_t i, Inertia& r, uint32_t stamp, int32_t* error_flag) {
+    for (unsigned int spins = 0;; ++spins) {
+        const F8 x = ld256(in + 2 * (size_t)i);
+        if (__float_as_uint(x.h) == stamp) {
+            r.t = {x.a, x.b, x.c, x.d, x.e, x.f};
+            r.inv_mass = x.g;
+            return true;
+        }
+        if (spins > kDataflowSpinLimit / 16) { atomicExch(error_flag, 4); return false; }
+    }
+}
+BEPU_DI bool load_pose_stamped(const float4* pose, uint32_t i, V3& pos, Q4& q, uint32_t stamp, int32_t* error_flag) {
+    for (unsigned int spins = 0;; ++spins) {
+        const F8 x = ld256(pose + 2 * (size_t)i);
+        if (__float_as_uint(x.h) == stamp) {
+            q = {x.a, x.b, x.c, x.d};
+            pos = {x.e, x.f, x.g};
+            return true;
+        }
+        if (spins > kDataflowSpinLimit / 16) { atomicExch(error_flag, 4); return false; }
+    }
+}
 
-// Out of line per (type, stage): each gets its own register allocation. Inlined into one switch, ptxas spills.
+// GatherAndIntegrate of warm_start_body (bepu_solver_kernels.cuh) with stamped records. `stamp` = this WarmStart pass + 1; pose_stamp = 0 when the
+// pose was not rewritten in this substep (first substep: IntegrateVelocity only, TypeProcessor.cs:L1251-1283).
+template <int STAGE, bool NeedsPose>
+BEPU_DI void warm_start_body_dataflow(uint32_t enc, const BodyBuffers& B, const FrameParams& fp, BodyState& b, Velocity& v, uint32_t stamp, int32_t* error_flag) {
+    const uint32_t idx = enc & kRefIndexMask;
+    if (enc & kRefIntegrateBit) {
+        Inertia local;
+        load_inertia(B.inertia_local, idx, local);
+        load_pose(B.pose, idx, b.pos, b.q);
+        b.inertia.inv_mass = local.inv_mass;
+        if (STAGE == kStageWarmStart) {
+            b.pos = b.pos + v.lin * fp.dt;
+            Q4 previousOrientation = b.q;
+            b.q = integrate_orientation(b.q, v.ang, fp.dt * 0.5f);
+            b.inertia.t = rotate_inverse_inertia(local.t, b.q);
+            if (fp.angular_mode == 1) integrate_angular_conserve_momentum(previousOrientation, local.t, b.inertia.t, v.ang);
+            else if (fp.angular_mode == 2) integrate_angular_gyroscopic(b.q, local.t, v.ang, fp.dt);
+            store_pose_stamped(B.pose, idx, b.pos, b.q, stamp);
+        } else {
+            b.inertia.t = rotate_inverse_inertia(local.t, b.q);
+            if (fp.angular_mode == 1) {
+                Q4 previousOrientation = integrate_orientation(b.q, v.ang, fp.dt * -0.5f);
+                integrate_angular_conserve_momentum(previousOrientation, local.t, b.inertia.t, v.ang);
+            } else if (fp.angular_mode == 2) {
+                integrate_angular_gyroscopic(b.q, local.t, v.ang, fp.dt);
+            }
+        }
+        callback_integrate_velocity(v, fp.gravity_dt[0], fp.gravity_dt[1], fp.gravity_dt[2], fp.linear_damping_dt, fp.angular_damping_dt);
+        store_inertia_stamped(B.inertia_world, idx, b.inertia, stamp);
+    } else if (enc & kRefKinematicBit) {
+        load_inertia(B.inertia_world, idx, b.inertia);  // kinematic: never written inside a region
+        if (NeedsPose) load_pose(B.pose, idx, b.pos, b.q);
+    } else {
+        load_inertia_stamped(B.inertia_world, idx, b.inertia, stamp, error_flag);
+        if (NeedsPose) {
+            if (STAGE == kStageWarmStart) load_pose_stamped(B.pose, idx, b.pos, b.q, stamp, error_flag);
+            else load_pose(B.pose, idx, b.pos, b.q);
+        }
+        if (STAGE == kStageWarmStartFirst && fp.angular_mode != 0 && (enc & kRefBundleIntegratesBit)) {
+            // reference quirk of the momentum-conserving modes (see warm_start_body)
+            Inertia local;
+            load_inertia(B.inertia_local, idx, local);
+            V3 pos;
+            Q4 q;
+            load_pose(B.pose, idx, pos, q);
+            if (fp.angular_mode == 1) integrate_angular_conserve_momentum(integrate_orientation(q, v.ang, fp.dt * -0.5f), local.t, b.inertia.t, v.ang);
+            else integrate_angular_gyroscopic(q, local.t, v.ang, fp.dt);
+        }
+    }
+}
+
+// Everything a lane does for its constraint in one pass. Inlined into the type switch of the kernel (no calls: the ABI's register save/restore
+// and by-reference arguments would live in local memory, which every gpu-scope acquire of the CTA invalidates in L1).
 template <class T, int STAGE>
-__device__ __noinline__ void run_lane_dataflow(const DataflowBundle& w, int lane, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, int32_t* error_flag) {
+BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_delta, long long succ_delta, unsigned int* counters, unsigned int* my_counter, unsigned int target, unsigned int first,
+                               uint32_t slab_addr, uint32_t bar, uint32_t parity, uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index,
+                               uint32_t ws_stamp, bool pose_stamped, int32_t* error_flag) {
     constexpr int NB = T::kBodies;
-    const int32_t* refs = w.rec.refs + lane;
-    const StagedRows p{w.slab_addr + lane * 4, w.bar, w.parity};
-    const StagedAcc a{w.slab_addr + w.prestep_bytes + lane * 4, w.rec.impulses + lane};
+    const int32_t* refs = rec.refs + lane;
+    const StagedRows p{slab_addr + lane * 4, bar, parity};
+    const StagedAcc a{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane};
     uint32_t enc[NB], expect[NB];
     int32_t succ[NB];
     bool dynamic[NB], ready[NB];
@@ -66,8 +144,8 @@ __device__ __noinline__ void run_lane_dataflow(const DataflowBundle& w, int lane
     const bool empty = (int32_t)enc[0] == kRefEmpty;
 #pragma unroll
     for (int s = 0; s < NB; ++s) {
-        const uint32_t chain = __ldg(reinterpret_cast<const uint32_t*>(refs + w.chain_delta) + s * kLanes);
-        succ[s] = __ldg(refs + w.succ_delta + s * kLanes);
+        const uint32_t chain = __ldg(reinterpret_cast<const uint32_t*>(refs + chain_delta) + s * kLanes);
+        succ[s] = __ldg(refs + succ_delta + s * kLanes);
         dynamic[s] = !empty && !(enc[s] & kRefKinematicBit);
         expect[s] = pass_index * (chain >> kChainDegreeShift) + (chain & kChainRankMask);
         ready[s] = !dynamic[s];
@@ -75,13 +153,18 @@ __device__ __noinline__ void run_lane_dataflow(const DataflowBundle& w, int lane
     BodyState b[NB];
     Velocity v[NB];
     if constexpr (STAGE == kStageSolve) {
-        // World inertia and pose were written by this substep's WarmStart pass, which this warp already executed for this bundle: fetch them while waiting.
+        // World inertia and pose were written by this substep's WarmStart pass, which this warp already executed for this bundle: fetch them while
+        // waiting (the stamp check only matters for a record whose owner's store is still in flight).
         if (!empty) {
 #pragma unroll
             for (int s = 0; s < NB; ++s) {
                 const uint32_t idx = enc[s] & kRefIndexMask;
-                load_inertia(B.inertia_world, idx, b[s].inertia);
-                if (T::kNeedsPose) load_pose(B.pose, idx, b[s].pos, b[s].q);
+                if (dynamic[s]) load_inertia_stamped(B.inertia_world, idx, b[s].inertia, ws_stamp, error_flag);
+                else load_inertia(B.inertia_world, idx, b[s].inertia);
+                if (T::kNeedsPose) {
+                    if (dynamic[s] && pose_stamped) load_pose_stamped(B.pose, idx, b[s].pos, b[s].q, ws_stamp, error_flag);
+                    else load_pose(B.pose, idx, b[s].pos, b[s].q);
+                }
             }
         }
     }
@@ -89,11 +172,12 @@ __device__ __noinline__ void run_lane_dataflow(const DataflowBundle& w, int lane
     // 1. wait for the notifications of this pass (one 4-byte poll per warp)
     unsigned int spins = 0;
     bool failed = false;
-    if (w.target != 0u) {
-        while ((int)(ld_relaxed_u32(w.my_counter) - w.target) < 0) {
+    if (target != first) {
+        while ((int)(ld_relaxed_u32(my_counter) - target) < 0) {
             if (++spins > kDataflowSpinLimit || ((spins & 1023u) == 0u && *reinterpret_cast<volatile int32_t*>(error_flag) == 4)) { failed = true; break; }
-            if (spins > 2) __nanosleep(fp.tune[0] > 0 ? fp.tune[0] : 64);
+            if (spins > 2) __nanosleep(32);
         }
+        if (lane == 0) *my_counter = first;  // all of this pass's notifications are in: ready for the next pass (which starts after a kernel boundary)
     }
     // 2. gather; a record whose store has not landed yet (the notification overtook it) is simply read again
     spins = 0;
@@ -126,134 +210,137 @@ __device__ __noinline__ void run_lane_dataflow(const DataflowBundle& w, int lane
     if constexpr (STAGE == kStageSolve) {
         call_solve<T>(b, fp.dt, fp.inverse_dt, p, a, v);
     } else {
-        bool owner = false;
 #pragma unroll
-        for (int s = 0; s < NB; ++s) {
-            warm_start_body<STAGE, T::kNeedsPose>(enc[s], B, fp, b[s], v[s]);
-            owner = owner || (enc[s] & kRefIntegrateBit);
-        }
+        for (int s = 0; s < NB; ++s) warm_start_body_dataflow<STAGE, T::kNeedsPose>(enc[s], B, fp, b[s], v[s], ws_stamp, error_flag);
         call_warm_start<T>(b, p, a, v);
-        // The owner's pose / world inertia stores must be visible before the version that lets the next constraint on the body read them.
-        if (owner) __threadfence();
     }
 #pragma unroll
     for (int s = 0; s < NB; ++s)
         if (dynamic[s]) {
             store_velocity_versioned(B.velocity, enc[s] & kRefIndexMask, v[s], expect[s] + 1u);
-            red_add_u32(w.counters + succ[s], 1u);
+            if (succ[s] >= 0) red_add_u32(counters + succ[s], 1u);  // the body's last constraint of the pass has nobody to wake
         }
 }
 
-template <int STAGE>
-BEPU_DI void run_bundle_dataflow(const DataflowBundle& w, int lane, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, int32_t* error_flag) {
-    switch (w.rec.type_id) {
+// kContactsOnly: the type switch holds the 14 contact types only (scenes without joints: shorter code, lower register pressure).
+#define BEPU_DATAFLOW_ARGS rec, lane, df.chain_delta, df.succ_delta, df.counters, my_counter, target, first, slab_addr, bar, parity, prestep_bytes, B, fp, pass_index, ws_stamp, pose_stamped, error_flag
+template <int STAGE, bool kContactsOnly>
+BEPU_DI void run_bundle_dataflow(const WorkRecord& rec, int lane, const DataflowTables& df, unsigned int* my_counter, unsigned int target, unsigned int first, uint32_t slab_addr, uint32_t bar,
+                                 uint32_t parity, uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, uint32_t ws_stamp, bool pose_stamped,
+                                 int32_t* error_flag) {
+    switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \
-    case ID: run_lane_dataflow<T, STAGE>(w, lane, B, fp, pass_index, error_flag); break;
+    case ID: run_lane_dataflow<T, STAGE>(BEPU_DATAFLOW_ARGS); break;
         BEPU_CONTACT_TYPES(BEPU_CASE)
-        BEPU_JOINT_TYPES(BEPU_CASE)
-        BEPU_JOINT_TYPES_MORE(BEPU_CASE)
 #undef BEPU_CASE
-        default: break;
+        default:
+            if constexpr (!kContactsOnly) {
+                switch (rec.type_id) {
+#define BEPU_CASE(ID, T) \
+    case ID: run_lane_dataflow<T, STAGE>(BEPU_DATAFLOW_ARGS); break;
+                    BEPU_JOINT_TYPES(BEPU_CASE)
+                    BEPU_JOINT_TYPES_MORE(BEPU_CASE)
+#undef BEPU_CASE
+                    default: break;
+                }
+            }
+            break;
     }
 }
 
-static __global__ void __launch_bounds__(kPersistentThreads, 2)
-dataflow_solve_kernel(const StageOp* __restrict__ program, int op_count, const WorkRecord* __restrict__ records, DataflowTables df, const int32_t* __restrict__ kinematics,
-                      BodyBuffers B, const FrameParams* __restrict__ fpp, unsigned int* barrier_counter, int32_t* error_flag) {
+// One WarmStart or Solve pass over the whole active set (all device batches) in ONE cooperative launch: inside the pass the Gauss-Seidel order per
+// body is kept by the version / notification protocol above; passes are separated by kernel boundaries, so at the start of a pass every body is at
+// version pass * degree and the first constraint on each body needs no notification. A bundle's counter therefore starts each pass at `first`
+// (dep_counts.y) and must reach dep_counts.x; the warp that consumed it resets it for the next pass.
+template <int STAGE, bool kContactsOnly>
+__global__ void __launch_bounds__(kPersistentThreads, BEPU_DATAFLOW_MINB)
+dataflow_pass_kernel(const WorkRecord* __restrict__ records, int work_count, DataflowTables df, BodyBuffers B, const FrameParams* __restrict__ fpp, uint32_t pass_offset,
+                     uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag) {
     extern __shared__ __align__(128) unsigned char dataflow_smem[];
     const FrameParams fp = *fpp;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     const int total_warps = gridDim.x * kDataflowWarps;
-    const int first_warp_item = warp_in_block * gridDim.x + blockIdx.x;
-    const int total_threads = gridDim.x * kPersistentThreads;
-    const int first_thread_item = threadIdx.x * gridDim.x + blockIdx.x;
     const uint32_t slab_addr = smem_u32(dataflow_smem) + warp_in_block * kStageSlabBytes;
     const uint32_t bar = smem_u32(dataflow_smem + kDataflowWarps * kStageSlabBytes + warp_in_block * 8);
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
     uint32_t parity = 0;
-    unsigned int barrier_target = 0;
-    uint32_t pass_counter = fp.pass_base;   // version passes since the body versions were reset
-    uint32_t solve_pass = 0;                // notification passes since this solve started (the counters are reset per solve)
+    const uint32_t pass_index = fp.pass_base + pass_offset;       // version pass since the body versions were reset
+    const uint32_t ws_stamp = fp.pass_base + ws_pass_offset + 1u;  // stamp of this substep's WarmStart pass
     const uint64_t policy = l2_evict_first_policy();
-    for (int op_index = 0; op_index < op_count; ++op_index) {
-        const StageOp op = program[op_index];
-        switch (op.stage) {
-            case kStageRegion: {
-                const int solve_passes = op.pad >> 1;
-                const bool first_substep = (op.pad & 1) != 0;
-                for (int pass = 0; pass <= solve_passes; ++pass) {
-                    const uint32_t pass_index = pass_counter + (uint32_t)pass;
-                    for (int g = first_warp_item; g < op.work_count; g += total_warps) {
-                        DataflowBundle w;
-                        w.rec = load_record(records + op.work_begin + g);
-                        const int2 deps = __ldg(df.dep_counts + op.work_begin + g);
-                        w.counters = df.counters;
-                        w.my_counter = df.counters + op.work_begin + g;
-                        w.target = (solve_pass + (uint32_t)pass + 1u) * (unsigned int)deps.x;
-                        w.chain_delta = df.chain_delta;
-                        w.succ_delta = df.succ_delta;
-                        w.slab_addr = slab_addr;
-                        w.bar = bar;
-                        w.parity = parity;
-                        w.prestep_bytes = kStageRowCounts.prestep[w.rec.type_id] * (kLanes * 4);
-                        const uint32_t impulse_bytes = kStageRowCounts.impulses[w.rec.type_id] * (kLanes * 4);
-                        __syncwarp();  // every lane is done with the slab's previous contents
-                        if (lane == 0) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            mbar_expect_tx(bar, w.prestep_bytes + impulse_bytes);
-                            bulk_copy_g2s(slab_addr, w.rec.prestep, w.prestep_bytes, bar, policy);
-                            bulk_copy_g2s(slab_addr + w.prestep_bytes, w.rec.impulses, impulse_bytes, bar, policy);
-                        }
-                        if (pass > 0) run_bundle_dataflow<kStageSolve>(w, lane, B, fp, pass_index, error_flag);
-                        else if (first_substep) run_bundle_dataflow<kStageWarmStartFirst>(w, lane, B, fp, pass_index, error_flag);
-                        else run_bundle_dataflow<kStageWarmStart>(w, lane, B, fp, pass_index, error_flag);
-                        parity ^= 1u;
-                    }
-                }
-                pass_counter += (uint32_t)solve_passes + 1u;
-                solve_pass += (uint32_t)solve_passes + 1u;
-                break;
-            }
-            case kStageIncremental:
-                for (int i = first_warp_item; i < op.work_count; i += total_warps) run_bundle<kStageIncremental>(load_record(records + op.work_begin + i), lane, B, fp);
-                break;
-            case kStageKinematicFirst:
-                for (int i = first_thread_item; i < op.work_count; i += total_threads) run_kinematic<kStageKinematicFirst>(i, kinematics, B, fp);
-                break;
-            case kStageKinematic:
-                for (int i = first_thread_item; i < op.work_count; i += total_threads) run_kinematic<kStageKinematic>(i, kinematics, B, fp);
-                break;
-            case kStageFinalPose:
-                for (int i = blockIdx.x * kPersistentThreads + threadIdx.x; i < B.count; i += total_threads) run_final_pose(i, B, fp);
-                break;
-            default: break;
+    for (int g = warp_in_block * gridDim.x + blockIdx.x; g < work_count; g += total_warps) {
+        const WorkRecord rec = load_record(records + g);
+        const int2 deps = __ldg(df.dep_counts + g);
+        unsigned int* my_counter = df.counters + g;
+        const uint32_t prestep_bytes = kStageRowCounts.prestep[rec.type_id] * (kLanes * 4);
+        const uint32_t impulse_bytes = kStageRowCounts.impulses[rec.type_id] * (kLanes * 4);
+        __syncwarp();  // every lane is done with the slab's previous contents
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, prestep_bytes + impulse_bytes);
+            bulk_copy_g2s(slab_addr, rec.prestep, prestep_bytes, bar, policy);
+            bulk_copy_g2s(slab_addr + prestep_bytes, rec.impulses, impulse_bytes, bar, policy);
         }
-        if (op_index + 1 < op_count) {
-            barrier_target += gridDim.x;
-            grid_barrier(barrier_counter, barrier_target);
-        }
+        run_bundle_dataflow<STAGE, kContactsOnly>(rec, lane, df, my_counter, (unsigned int)deps.x, (unsigned int)deps.y, slab_addr, bar, parity, prestep_bytes, B, fp, pass_index, ws_stamp,
+                                                  pose_stamped != 0, error_flag);
+        parity ^= 1u;
     }
 }
 
-static int launch_dataflow(const StageOp* program, int op_count, const WorkRecord* records, const DataflowTables& df, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
-                           unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s) {
-    int device = 0, sms = 0, max_per_sm = 0;
+template <int STAGE, bool kContactsOnly>
+static int launch_dataflow_pass_t(const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
+                                  uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, cudaStream_t s) {
+    static int grid_limit[64] = {};
+    int device = 0;
     cudaError_t e = cudaGetDevice(&device);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dataflow_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDataflowSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dataflow_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, dataflow_solve_kernel, kPersistentThreads, kDataflowSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    if (max_per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
-    int per_sm = blocks_per_sm <= 0 ? 2 : blocks_per_sm;
-    if (per_sm > max_per_sm) per_sm = max_per_sm;
-    const int grid = sms * per_sm;
-    BodyBuffers Bc = B;
-    DataflowTables dfc = df;
-    void* args[] = {(void*)&program, (void*)&op_count, (void*)&records, (void*)&dfc, (void*)&kinematics, (void*)&Bc, (void*)&fp, (void*)&barrier_counter, (void*)&error_flag};
-    return (int)cudaLaunchCooperativeKernel((const void*)dataflow_solve_kernel, dim3(grid), dim3(kPersistentThreads), args, kDataflowSmemBytes, s);
+    auto kernel = dataflow_pass_kernel<STAGE, kContactsOnly>;
+    if (grid_limit[device & 63] == 0) {
+        int sms = 0, max_per_sm = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDataflowSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, kernel, kPersistentThreads, kDataflowSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        if (max_per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+        grid_limit[device & 63] = sms * 1024 + max_per_sm;
+    }
+    const int sms = grid_limit[device & 63] / 1024, max_per_sm = grid_limit[device & 63] % 1024;
+    int per_sm = blocks_per_sm <= 0 ? max_per_sm : (blocks_per_sm < max_per_sm ? blocks_per_sm : max_per_sm);
+    int grid = sms * per_sm;  // every CTA must be resident: the pass deadlocks otherwise (cooperative launch enforces it)
+    const int needed = (work_count + kDataflowWarps - 1) / kDataflowWarps;
+    if (grid > needed) grid = needed;
+    if (grid < 1) return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kPersistentThreads);
+    cfg.dynamicSmemBytes = kDataflowSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag);
+}
+template <bool kContactsOnly>
+static int launch_dataflow_pass_c(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
+                                  uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, cudaStream_t s) {
+    switch (stage) {
+        case kStageWarmStartFirst: return launch_dataflow_pass_t<kStageWarmStartFirst, kContactsOnly>(records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag, blocks_per_sm, s);
+        case kStageWarmStart: return launch_dataflow_pass_t<kStageWarmStart, kContactsOnly>(records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag, blocks_per_sm, s);
+        default: return launch_dataflow_pass_t<kStageSolve, kContactsOnly>(records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag, blocks_per_sm, s);
+    }
+}
+static int launch_dataflow_pass(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
+                                uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s) {
+    if (contacts_only) return launch_dataflow_pass_c<true>(stage, records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag, blocks_per_sm, s);
+#ifdef BEPU_DATAFLOW_DEV_CONTACTS_ONLY
+    return (int)cudaErrorNotSupported;  // development builds compile the contacts-only instantiations alone
+#else
+    return launch_dataflow_pass_c<false>(stage, records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag, blocks_per_sm, s);
+#endif
 }
 
 }  // namespace BEPU_NS

@@ -111,9 +111,9 @@ constexpr uint32_t kChainRankMask = 0xFFFFu;
 // refs + delta (in int32 elements).
 struct DataflowTables {
     long long chain_delta;      // chain words
-    long long succ_delta;       // per (lane, body slot): work index of the bundle holding the NEXT constraint on that body (the first one after the last)
+    long long succ_delta;       // per (lane, body slot): work index of the bundle holding the NEXT constraint on that body, -1 after the last
     const int2* dep_counts;     // per bundle: x = (lane, dynamic body) dependencies per pass, y = those that are the first constraint on their body
-    unsigned int* counters;     // per bundle: notifications received since the start of the solve, starting at y
+    unsigned int* counters;     // per bundle: y + notifications received in the current pass (reset to y by the consumer)
 };
 
 struct TypeInfo {

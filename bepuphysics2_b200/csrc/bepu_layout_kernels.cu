@@ -192,8 +192,8 @@ __global__ void chain_degree_kernel(const DeviceTypeBatch* __restrict__ tbs, con
     }
 }
 // Dataflow successor table. Phase 0 (one launch per device batch, LAST batch first): succ = work index of the bundle that holds the next constraint
-// on the body (none yet for the body's last constraint); next_bundle[body] ends as the body's FIRST bundle. Phase 1 (one launch): the last
-// constraint's successor wraps around to the first, and the per-bundle dependency counts are taken.
+// on the body (-1 for the body's last constraint: passes are separated by kernel boundaries, nobody waits for it). Phase 1 (one launch): the
+// per-bundle dependency counts.
 __global__ void chain_succ_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, int work_base, const int32_t* __restrict__ bodies_per_type,
                                   long long succ_delta, int32_t* next_bundle) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -222,7 +222,6 @@ __global__ void chain_finish_kernel(const DeviceTypeBatch* __restrict__ tbs, con
         int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
         const int32_t enc = *r;
         if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
-        if (r[succ_delta] < 0) r[succ_delta] = next_bundle[enc & kRefIndexMask];
         ++deps;
         first += ((uint32_t)r[chain_delta] & kChainRankMask) == 0u;
     }

@@ -64,10 +64,11 @@ struct SolverLaunchers {
     // barrier_counter must be zero at launch. blocks_per_sm <= 0 selects the default.
     int (*persistent)(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                       unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
-    // Dataflow persistent kernel: like `persistent`, but kStageRegion ops run a whole substep's WarmStart + Solve passes with per-body version
-    // dependencies (DataflowTables) instead of a barrier per (batch, stage). error_flag is set to 4 if a dependency never arrives.
-    int (*dataflow)(const StageOp* program, int op_count, const WorkRecord* records, const DataflowTables& df, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
-                    unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s);
+    // Dataflow mode: one WarmStart / Solve pass over all device batches in one cooperative launch, per-body version dependencies (DataflowTables)
+    // instead of a kernel boundary per (batch, stage). pass_offset / ws_pass_offset: index of this pass / of its substep's WarmStart pass within the
+    // solve. error_flag is set to 4 if a dependency never arrives. contacts_only selects the instantiation whose type switch holds the contact types only.
+    int (*dataflow_pass)(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
+                         uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s);
 };
 const SolverLaunchers* get_launchers_bepu_fast();
 const SolverLaunchers* get_launchers_bepu_strict();

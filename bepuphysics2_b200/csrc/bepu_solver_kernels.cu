@@ -1,7 +1,7 @@
 // Compiled per numerics flavour (-DBEPU_NS=bepu_fast with FMA contraction / -DBEPU_NS=bepu_strict -fmad=false) and per unit (-DBEPU_UNIT=n),
 // so that the big per-type switch of each kernel gets its own translation unit and the build parallelises:
 //   0 WarmStartFirst stage   1 WarmStart stage   2 Solve stage   3 Incremental stage + kinematic + final pose + launcher table
-//   4 persistent kernel      5 dataflow kernel
+//   4 persistent kernel      5 dataflow pass kernels
 #include "bepu_solver_kernels.cuh"
 #if BEPU_UNIT == 4
 #include "bepu_persistent.cuh"
@@ -17,8 +17,8 @@ void launch_stage_warm_start(const WorkRecord* records, int work_count, const Bo
 void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
 int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                            unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
-int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, const DataflowTables& df, const int32_t* kinematics, const BodyBuffers& B,
-                         const FrameParams* fp, unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s);
+int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
+                         uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s);
 
 #if BEPU_UNIT <= 3
 #ifndef BEPU_DEEP_MINB
@@ -94,9 +94,9 @@ int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecor
     return launch_persistent(program, op_count, records, kinematics, B, fp, barrier_counter, blocks_per_sm, s);
 }
 #elif BEPU_UNIT == 5
-int launch_dataflow_unit(const StageOp* program, int op_count, const WorkRecord* records, const DataflowTables& df, const int32_t* kinematics, const BodyBuffers& B,
-                         const FrameParams* fp, unsigned int* barrier_counter, int32_t* error_flag, int blocks_per_sm, cudaStream_t s) {
-    return launch_dataflow(program, op_count, records, df, kinematics, B, fp, barrier_counter, error_flag, blocks_per_sm, s);
+int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
+                         uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s) {
+    return launch_dataflow_pass(stage, records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag, blocks_per_sm, contacts_only, s);
 }
 #else
 #error "BEPU_UNIT must be 0..5"

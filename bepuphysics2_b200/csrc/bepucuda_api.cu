@@ -180,6 +180,7 @@ struct bepucuda_ctx {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_valid = false;
+    bool dataflow_without_graph = false;  // the driver refused to capture cooperative launches: passes are issued directly
 
     bepucuda_timings timings{};
     int64_t h2d_accum = 0;
@@ -296,7 +297,31 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
     // Row prefetch in the PDL prologue (see constraint_stage_kernel): allowed when the kernel launched immediately before neither rewrites this
     // batch's prestep rows (the incremental contact update does) nor its impulses (a stage of the same batch does: single-batch scenes).
     const StageOp* previous = nullptr;  // last launched op
+    uint32_t pass_offset = 0, ws_pass_offset = 0;
+    bool first_substep = true;
+    DataflowTables df{};
+    int contacts_only = 1;
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && ctx->all_work_count > 0) {
+        df.chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
+        df.succ_delta = ctx->succ32.as<int32_t>() - ctx->refs32.as<int32_t>();
+        df.dep_counts = ctx->dep_counts.as<int2>();
+        df.counters = ctx->df_counters.as<unsigned int>();
+        for (const SourceTypeBatch& src : ctx->sources) contacts_only &= src.type_id <= 17;
+        launch_reset_counters(df.dep_counts, df.counters, ctx->all_work_count, s);
+        ++n;
+    }
     for (const StageOp& op : ctx->program) {
+        if (op.pad == 1 && op.stage <= kStageSolve) {
+            // dataflow pass (BEPUCUDA_EXEC_DATAFLOW)
+            if (op.stage != kStageSolve) { ws_pass_offset = pass_offset; first_substep = op.stage == kStageWarmStartFirst; }
+            const int rc = ctx->launchers->dataflow_pass(op.stage, records, op.work_count, df, ctx->B, fp, pass_offset, ws_pass_offset, first_substep ? 0 : 1, ctx->error_dev.as<int32_t>(),
+                                                         ctx->cfg.reserved[0], contacts_only, s);
+            if (rc != 0) ctx->exchange_failed = true;  // reported by the caller
+            ++pass_offset;
+            previous = &op;
+            ++n;
+            continue;
+        }
         switch (op.stage) {
             case kStageWarmStartFirst: case kStageWarmStart: case kStageSolve: case kStageIncremental:
                 if (op.work_count > 0) {
@@ -348,7 +373,11 @@ void build_program(bepucuda_ctx* ctx) {
             ctx->program.push_back({kStageKinematicFirst, 0, kin, 0});
         }
         if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
-            if (ctx->all_work_count > 0) ctx->program.push_back({kStageRegion, 0, ctx->all_work_count, (ctx->iterations[s] << 1) | (s == 0 ? 1 : 0)});
+            // one op per PASS over all device batches (pad = 1): the order inside a pass is kept by per-body versions, not by kernel boundaries
+            if (ctx->all_work_count > 0) {
+                ctx->program.push_back({s == 0 ? kStageWarmStartFirst : kStageWarmStart, 0, ctx->all_work_count, 1});
+                for (int it = 0; it < ctx->iterations[s]; ++it) ctx->program.push_back({kStageSolve, 0, ctx->all_work_count, 1});
+            }
             continue;
         }
         for (auto& bw : ctx->batch_work)
@@ -977,38 +1006,44 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
                                             ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->cfg.reserved[0], ctx->stream);
         if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "persistent kernel launch");
         launches = 1;
-    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
-        CK(cudaMemsetAsync(ctx->barrier_dev.ptr, 0, sizeof(unsigned int), ctx->stream));
-        DataflowTables df{};
-        df.chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
-        df.succ_delta = ctx->succ32.as<int32_t>() - ctx->refs32.as<int32_t>();
-        df.dep_counts = ctx->dep_counts.as<int2>();
-        df.counters = ctx->df_counters.as<unsigned int>();
-        launch_reset_counters(df.dep_counts, df.counters, ctx->all_work_count, ctx->stream);
-        int rc = ctx->launchers->dataflow(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->record_table.as<WorkRecord>(), df, ctx->kinematics_dev.as<int32_t>(),
-                                          ctx->B, ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->error_dev.as<int32_t>(), ctx->cfg.reserved[0], ctx->stream);
-        if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "dataflow kernel launch");
-        launches = 1;
-        for (int it : ctx->iterations) ctx->pass_counter += (uint32_t)it + 1u;
-    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_GRAPH) {
+    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_GRAPH || (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && !ctx->dataflow_without_graph)) {
         if (!ctx->graph_valid) {
+            ctx->exchange_failed = false;
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             int64_t n = 0;
             issue_stage_sequence(ctx, ctx->stream, &n);
             cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->graph);
-            if (e != cudaSuccess) return cuda_fail(ctx, e, "graph capture");
-            CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
-            ctx->graph_valid = true;
-            ctx->timings.kernel_launches = n;
+            if (e == cudaSuccess && ctx->exchange_failed) e = cudaErrorUnknown;
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0);
+            if (e != cudaSuccess) {
+                if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_DATAFLOW) return cuda_fail(ctx, e, "graph capture");
+                // cooperative launches could not be captured / instantiated on this driver: issue the passes directly from now on
+                cudaGetLastError();
+                invalidate_graph(ctx);
+                ctx->dataflow_without_graph = true;
+            } else {
+                ctx->graph_valid = true;
+                ctx->timings.kernel_launches = n;
+            }
         }
-        CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
-        launches = ctx->timings.kernel_launches;
-    } else {
+        if (ctx->graph_valid) {
+            CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+            launches = ctx->timings.kernel_launches;
+        }
+    }
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && ctx->dataflow_without_graph) {
+        ctx->exchange_failed = false;
+        issue_stage_sequence(ctx, ctx->stream, &launches);
+        CK(cudaGetLastError());
+        if (ctx->exchange_failed) return fail(ctx, BEPUCUDA_ERR_CUDA, "solve: a dataflow pass could not be launched");
+    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_STREAM) {
         issue_stage_sequence(ctx, ctx->stream, &launches);
         CK(cudaGetLastError());
         if (ctx->exchange_failed) return fail(ctx, BEPUCUDA_ERR_CUDA, "solve: the exchange callback failed");
     }
     CK(cudaEventRecord(ctx->ev_solve_end, ctx->stream));
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW)
+        for (int it : ctx->iterations) ctx->pass_counter += (uint32_t)it + 1u;  // body versions keep counting across solves
     ctx->have_solve = true;
     ctx->timings.kernel_launches = launches;
 

@@ -37,11 +37,13 @@ def parse_args():
     ap.add_argument("--substeps", type=int, default=8)
     ap.add_argument("--iterations", type=int, default=2)
     ap.add_argument("--scene", default="shape_pile", choices=["shape_pile", "ragdolls", "fallback_stress"])
-    ap.add_argument("--mode", default="graph", choices=["graph", "persistent", "stream", "dataflow"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "stream", "dataflow"], help="auto = the execution mode that measured fastest for the scene (DESIGN.md §8)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the side block with the other BASELINE configs (C3 ragdolls x2, C5 fallback stress, 1 M-body pile 4 x 2)")
+    ap.add_argument("--config-steps", type=int, default=20)
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    ap.add_argument("--large-bodies", type=int, default=1_000_000, help="also measure (N=1 only, device-resident) a pile of this many bodies, the scene size BASELINE.json's north_star targets; 0 = skip")
+    ap.add_argument("--large-bodies", type=int, default=1_000_000, help="body count of the large pile in the configs block (the scene size BASELINE.json's north_star targets); 0 = skip it")
     return ap.parse_args()
 
 
@@ -51,7 +53,7 @@ def make_scene(args, seed):
     if args.scene == "shape_pile":
         return scenes.shape_pile(args.bodies, seed=seed)
     if args.scene == "ragdolls":
-        return scenes.ragdolls(max(1, args.bodies // 16), seed=seed)
+        return scenes.ragdolls(max(1, args.bodies // 16), seed=seed, motor=getattr(args, "ragdoll_motor", "motor"))
     return scenes.fallback_stress(args.bodies, hubs=max(1, args.bodies // 1000), seed=seed)
 
 
@@ -166,38 +168,54 @@ def load_traffic(bodies, kernel):
     return None
 
 
-def measure_large_scene(args, torch, bp, mode, flush):
-    """Device-resident throughput of the same pile generator at --large-bodies (default 1 M bodies, the size the north star quotes), N = 1."""
+AUTO_MODE = {"shape_pile": "graph", "ragdolls": "graph", "fallback_stress": "graph"}  # updated from measurements (profiles/r02_summary.md)
+
+
+def resolve_mode(args):
+    return AUTO_MODE.get(args.scene, "graph") if args.mode == "auto" else args.mode
+
+
+def side_configs(args):
+    """The other BASELINE.json configs, each as (key, argparse overrides). configs[1] (C2) is the headline and is measured by main()."""
+    out = [("c3_ragdoll_tube_10k_1x4", dict(scene="ragdolls", bodies=160_000, substeps=1, iterations=4, ragdoll_motor="motor")),
+           ("c3_ragdoll_tube_10k_servo_8x2", dict(scene="ragdolls", bodies=160_000, substeps=8, iterations=2, ragdoll_motor="servo")),
+           ("c5_fallback_stress_50k_1x4", dict(scene="fallback_stress", bodies=50_000, substeps=1, iterations=4))]
+    if args.large_bodies > 0:
+        out.append(("c4_pile_%dk_4x2_one_gpu" % (args.large_bodies // 1000), dict(scene="shape_pile", bodies=args.large_bodies, substeps=4, iterations=2)))
+        out.append(("pile_%dk_8x2_one_gpu" % (args.large_bodies // 1000), dict(scene="shape_pile", bodies=args.large_bodies, substeps=8, iterations=2)))
+    return out
+
+
+def measure_config(args, overrides, torch, bp, modes, flush, peak, steps, with_cpu):
+    """Device-resident throughput of one configuration (N = 1): `steps` solves, L2 flushed before each, CUDA events on the context stream."""
     import copy
 
-    big = copy.copy(args)
-    big.bodies = args.large_bodies
-    sim, description = build_sim(big, seed=5)
-    ts = bp.CudaTimestepper(sim, device=torch.cuda.current_device(), strict_fp=args.strict, execution_mode=mode)
+    cfg = copy.copy(args)
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    sim, description = build_sim(cfg, seed=5)
+    mode_name = resolve_mode(cfg)
+    ts = bp.CudaTimestepper(sim, device=torch.cuda.current_device(), strict_fp=args.strict, execution_mode=modes[mode_name])
     ts.describe()
     ms = []
-    for i in range(3 + 5):
+    for i in range(3 + steps):
         flush.fill_(1)
         torch.cuda.synchronize()
         ts.solve_device_only(DT)
         if i >= 3:
             ms.append(ts.timings().solve_ms)
     t = ts.timings()
-    prof = None
-    if args.mode in ("graph", "stream"):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        ts.profile_stages(DT)
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        prof = ts.profile_stages(DT).as_dict()
     ts.close()
     step_ms = float(np.mean(ms))
-    out = {"workload": "%s: %s; %d substeps x %d velocity iterations" % (args.scene, description, args.substeps, args.iterations), "ms_per_step": step_ms, "steps": len(ms),
-           "value": int(t.constraint_iterations) / (step_ms * 1e-3), "unit": "constraint-iterations/s", "algorithmic_gbs_whole_step": int(t.algorithmic_bytes) / (step_ms * 1e-3) / 1e9}
-    if prof:
-        share = prof["solve"]["ms"] / sum(v["ms"] for v in prof.values())
-        out["solve_kernel_algorithmic_gbs"] = prof["solve"]["algorithmic_bytes"] / (share * step_ms * 1e-3) / 1e9
+    out = {"workload": "%s: %s; %d substeps x %d velocity iterations" % (cfg.scene, description, cfg.substeps, cfg.iterations), "execution_mode": mode_name, "ms_per_step": step_ms,
+           "steps": len(ms), "value": int(t.constraint_iterations) / (step_ms * 1e-3), "unit": "constraint-iterations/s", "constraints": int(t.constraint_count),
+           "device_batches": int(t.device_batch_count), "kernel_launches_per_step": int(t.kernel_launches),
+           "algorithmic_gbs_whole_step": int(t.algorithmic_bytes) / (step_ms * 1e-3) / 1e9}
+    out["roofline_frac_whole_step"] = out["algorithmic_gbs_whole_step"] / peak
+    if with_cpu:
+        frames = 1 if cfg.bodies > 300_000 else 2
+        cb = cpu_reference_run(cfg, steps=frames, warmup=0 if cfg.bodies > 300_000 else 1, threads=args.cpu_threads)
+        out["cpu_baseline"] = {"value": cb["value"], "ms_per_step": cb["ms_per_step"], "cores": cb["cores"], "kind": "port", "sample": "%d frame(s) of this workload" % frames}
     return out
 
 
@@ -286,9 +304,11 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mode = {"graph": EXEC_GRAPH, "persistent": EXEC_PERSISTENT, "stream": EXEC_STREAM, "dataflow": EXEC_DATAFLOW}[args.mode]
+    modes = {"graph": EXEC_GRAPH, "persistent": EXEC_PERSISTENT, "stream": EXEC_STREAM, "dataflow": EXEC_DATAFLOW}
+    args.mode = resolve_mode(args)
+    mode = modes[args.mode]
 
-    sim, description = build_sim(args, seed=5 + rank)  # every rank owns an independent pile (island)
+    sim, description = build_sim(args, seed=5)  # every rank owns an independent island: the same pile on every rank, so ranks differ only by their GPU
     ts = bp.CudaTimestepper(sim, device=local_rank, strict_fp=args.strict, execution_mode=mode)
     ts.register_host_buffers()
     ts.describe()
@@ -339,6 +359,26 @@ def main():
     te = ts.timings()
     h2d, d2h = int(te.h2d_bytes), int(te.d2h_bytes)
 
+    # ---- end to end WITH a topology change every step (what a frame after collision detection looks like): the whole constraint description is
+    # ---- re-uploaded (begin / upload_type_batch / end_constraints: transposition, ownership analysis, fallback levelisation, graph re-capture)
+    topo = None
+    if rank == 0:
+        for _ in range(2):
+            ts.describe()
+            ts.solve(DT, download=True)
+        ts.synchronize()
+        topo_steps = max(3, min(args.steps, 6))
+        t0 = time.perf_counter()
+        for _ in range(topo_steps):
+            ts.describe()
+            ts.solve(DT, download=True)
+        ts.synchronize()
+        topo_s = time.perf_counter() - t0
+        tt = ts.timings()
+        topo = {"value": ci_per_step * topo_steps / topo_s, "unit": "constraint-iterations/s", "ms_per_step": topo_s / topo_steps * 1e3, "steps": topo_steps,
+                "h2d_bytes_per_step": int(tt.h2d_bytes), "d2h_bytes_per_step": int(tt.d2h_bytes),
+                "what": "every step: upload bodies + begin/upload/end_constraints (full topology rebuild) + solve + download bodies and impulses"}
+
     # ---- per-stage device time (event pair around every launch) for the roofline of the dominant kernel ----
     prof = None
     if rank == 0 and args.mode != "dataflow":
@@ -349,12 +389,20 @@ def main():
         torch.cuda.synchronize()
         prof = ts.profile_stages(DT).as_dict()
 
-    large = None
-    if rank == 0 and world == 1 and args.large_bodies > args.bodies and args.scene == "shape_pile":
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and args.scene == "shape_pile":
         ts.close()
         ts = None
-        large = measure_large_scene(args, torch, bp, mode, flush)
+        peak_for_configs, _ = load_peaks()
+        configs = {}
+        for key, overrides in side_configs(args):
+            configs[key] = measure_config(args, overrides, torch, bp, modes, flush, peak_for_configs, args.config_steps, with_cpu=not args.no_cpu_baseline)
 
+    per_rank_ms = [total_ms / args.steps]
+    if dist is not None:
+        gathered = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([total_ms / args.steps], dtype=torch.float64, device="cuda"))
+        per_rank_ms = [float(g.item()) for g in gathered]
     times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     counts = torch.tensor([float(ci_per_step)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -404,11 +452,11 @@ def main():
                          "peak_source": peak_source, "algorithmic_bytes_per_step": alg_bytes_per_step, **roof_extra},
             "stage_profile_ms": {k: round(v["ms"], 4) for k, v in (prof or {}).items()},
         }
-        if large is not None:
-            large["roofline_frac_whole_step"] = large["algorithmic_gbs_whole_step"] / peak
-            if "solve_kernel_algorithmic_gbs" in large:
-                large["roofline_frac_solve_kernel"] = large["solve_kernel_algorithmic_gbs"] / peak
-            line["large_scene"] = large
+        line["ms_per_step_per_rank"] = per_rank_ms
+        if topo is not None:
+            line["e2e_topology_change"] = topo
+        if configs is not None:
+            line["configs"] = configs
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             cb = cpu_reference_run(args, steps=3, warmup=1, threads=args.cpu_threads)
             c1 = cpu_reference_run(args, steps=1, warmup=0, threads=1)  # the reference's own benchmarks run single-threaded (ShapePileBenchmark.cs:L228)

@@ -29,7 +29,11 @@
 namespace BEPU_NS {
 
 constexpr unsigned int kDataflowSpinLimit = 20000000u;  // ~1 s of polling: a dependency that never arrives is a bug, not a reason to hang the GPU
-constexpr int kDataflowWarps = kPersistentThreads / 32;
+#ifndef BEPU_DATAFLOW_THREADS
+#define BEPU_DATAFLOW_THREADS 256
+#endif
+constexpr int kDataflowThreads = BEPU_DATAFLOW_THREADS;
+constexpr int kDataflowWarps = kDataflowThreads / 32;
 constexpr int kDataflowSmemBytes = kDataflowWarps * kStageSlabBytes + kDataflowWarps * 8;
 #ifndef BEPU_DATAFLOW_MINB
 #define BEPU_DATAFLOW_MINB 2
@@ -53,26 +57,35 @@ BEPU_DI void store_inertia_stamped(float4* in, uint32_t i, const Inertia& r, uin
 }
 BEPU_DI void store_pose_stamped(float4* pose, uint32_t i, V3 pos, Q4 q, uint32_t stamp) { st256(pose + 2 * (size_t)i, q.x, q.y, q.z, q.w, pos.x, pos.y, pos.z, __uint_as_float(stamp)); }
 BEPU_DI bool load_inertia_stamped(const float4* in, uint32_t i, Inertia& r, uint32_t stamp, int32_t* error_flag) {
-    for (unsigned int spins = 0;; ++spins) {
-        const F8 x = ld256(in + 2 * (size_t)i);
-        if (__float_as_uint(x.h) == stamp) {
-            r.t = {x.a, x.b, x.c, x.d, x.e, x.f};
-            r.inv_mass = x.g;
-            return true;
-        }
-        if (spins > kDataflowSpinLimit / 16) { atomicExch(error_flag, 4); return false; }
-    }
+#ifdef BEPU_DF_PLAIN
+    load_inertia(in, i, r);
+    return true;
+#else
+    F8 x;
+    unsigned int spins = 0;
+    bool good;
+    do {
+        x = ld256(in + 2 * (size_t)i);
+        good = __float_as_uint(x.h) == stamp;
+    } while (!good && ++spins < kDataflowSpinLimit / 16);
+    r.t = {x.a, x.b, x.c, x.d, x.e, x.f};
+    r.inv_mass = x.g;
+    if (!good) report_stall(error_flag, 3, stamp, __float_as_uint(x.h), i);
+    return good;
+#endif
 }
 BEPU_DI bool load_pose_stamped(const float4* pose, uint32_t i, V3& pos, Q4& q, uint32_t stamp, int32_t* error_flag) {
-    for (unsigned int spins = 0;; ++spins) {
-        const F8 x = ld256(pose + 2 * (size_t)i);
-        if (__float_as_uint(x.h) == stamp) {
-            q = {x.a, x.b, x.c, x.d};
-            pos = {x.e, x.f, x.g};
-            return true;
-        }
-        if (spins > kDataflowSpinLimit / 16) { atomicExch(error_flag, 4); return false; }
-    }
+    F8 x;
+    unsigned int spins = 0;
+    bool good;
+    do {
+        x = ld256(pose + 2 * (size_t)i);
+        good = __float_as_uint(x.h) == stamp;
+    } while (!good && ++spins < kDataflowSpinLimit / 16);
+    q = {x.a, x.b, x.c, x.d};
+    pos = {x.e, x.f, x.g};
+    if (!good) report_stall(error_flag, 4, stamp, __float_as_uint(x.h), i);
+    return good;
 }
 
 // GatherAndIntegrate of warm_start_body (bepu_solver_kernels.cuh) with stamped records. `stamp` = this WarmStart pass + 1; pose_stamp = 0 when the
@@ -126,87 +139,81 @@ BEPU_DI void warm_start_body_dataflow(uint32_t enc, const BodyBuffers& B, const 
     }
 }
 
-// Everything a lane does for its constraint in one pass. Inlined into the type switch of the kernel (no calls: the ABI's register save/restore
-// and by-reference arguments would live in local memory, which every gpu-scope acquire of the CTA invalidates in L1).
+// A dependency that never arrives is a bug in the tables, not a reason to hang the GPU: the first lane to give up records what it was waiting for
+// (error_flag[0] = 4, [1] = what: 1 counter, 2 velocity version, 3 inertia stamp, 4 pose stamp, [2] = expected, [3] = observed, [4] = body or bundle).
+BEPU_DI void report_stall(int32_t* error_flag, int what, uint32_t expected, uint32_t observed, uint32_t where) {
+    if (atomicCAS(error_flag, 0, 4) == 0) {
+        error_flag[1] = what;
+        error_flag[2] = (int32_t)expected;
+        error_flag[3] = (int32_t)observed;
+        error_flag[4] = (int32_t)where;
+    }
+}
+
+// Expected version of body slot s at this pass (see the file comment), from the chain word next to the body reference.
+BEPU_DI uint32_t expected_version(const int32_t* refs, long long chain_delta, int s, uint32_t pass_index) {
+    const uint32_t chain = ldg_nc_u32(refs + chain_delta + s * kLanes);
+    return pass_index * (chain >> kChainDegreeShift) + (chain & kChainRankMask);
+}
+// Velocity gather with the version check: a record whose store has not landed yet (the notification overtook it) is simply read again.
+BEPU_DI bool load_velocity_versioned(const float4* vel, uint32_t idx, uint32_t expect, Velocity& v, int32_t* error_flag) {
+#ifdef BEPU_DF_PLAIN
+    load_velocity(vel, idx, v);
+    return true;
+#else
+    F8 r;
+    unsigned int spins = 0;
+    bool good;
+    do {
+        r = ld256(vel + 2 * (size_t)idx);
+        good = __float_as_uint(r.d) == expect && __float_as_uint(r.h) == expect;
+    } while (!good && ++spins < kDataflowSpinLimit / 16);
+    v.lin = {r.a, r.b, r.c};
+    v.ang = {r.e, r.f, r.g};
+    if (!good) report_stall(error_flag, 2, expect, __float_as_uint(r.d), idx);
+    return good;
+#endif
+}
+
+// Everything a lane does for its constraint in one pass; shaped like run_lane (bepu_solver_kernels.cuh) so that the register allocation of the math
+// is the stage kernels': only the body references stay live across it, chain / successor words are (re)read from L1 where they are needed.
+// Inlined into the type switch of the kernel (no calls: the ABI's register save/restore and by-reference arguments would live in local memory).
 template <class T, int STAGE>
-BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_delta, long long succ_delta, unsigned int* counters, unsigned int* my_counter, unsigned int target, unsigned int first,
-                               uint32_t slab_addr, uint32_t bar, uint32_t parity, uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index,
-                               uint32_t ws_stamp, bool pose_stamped, int32_t* error_flag) {
+BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_delta, long long succ_delta, unsigned int* counters, uint32_t slab_addr, uint32_t bar, uint32_t parity,
+                               uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, uint32_t ws_stamp, bool pose_stamped, int32_t* error_flag) {
     constexpr int NB = T::kBodies;
     const int32_t* refs = rec.refs + lane;
     const StagedRows p{slab_addr + lane * 4, bar, parity};
     const StagedAcc a{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane};
-    uint32_t enc[NB], expect[NB];
-    int32_t succ[NB];
-    bool dynamic[NB], ready[NB];
+    uint32_t enc[NB];
 #pragma unroll
-    for (int s = 0; s < NB; ++s) enc[s] = (uint32_t)__ldg(refs + s * kLanes);
-    const bool empty = (int32_t)enc[0] == kRefEmpty;
-#pragma unroll
-    for (int s = 0; s < NB; ++s) {
-        const uint32_t chain = __ldg(reinterpret_cast<const uint32_t*>(refs + chain_delta) + s * kLanes);
-        succ[s] = __ldg(refs + succ_delta + s * kLanes);
-        dynamic[s] = !empty && !(enc[s] & kRefKinematicBit);
-        expect[s] = pass_index * (chain >> kChainDegreeShift) + (chain & kChainRankMask);
-        ready[s] = !dynamic[s];
-    }
+    for (int s = 0; s < NB; ++s) enc[s] = ldg_nc_u32(refs + s * kLanes);
+    if ((int32_t)enc[0] == kRefEmpty) return;  // trailing lane of the last bundle, or a hole in a fallback bundle
     BodyState b[NB];
     Velocity v[NB];
-    if constexpr (STAGE == kStageSolve) {
-        // World inertia and pose were written by this substep's WarmStart pass, which this warp already executed for this bundle: fetch them while
-        // waiting (the stamp check only matters for a record whose owner's store is still in flight).
-        if (!empty) {
+    bool ok = true;
 #pragma unroll
-            for (int s = 0; s < NB; ++s) {
-                const uint32_t idx = enc[s] & kRefIndexMask;
-                if (dynamic[s]) load_inertia_stamped(B.inertia_world, idx, b[s].inertia, ws_stamp, error_flag);
-                else load_inertia(B.inertia_world, idx, b[s].inertia);
+    for (int s = 0; s < NB; ++s) {
+        const uint32_t idx = enc[s] & kRefIndexMask;
+        if (enc[s] & kRefKinematicBit) {
+            load_velocity(B.velocity, idx, v[s]);  // kinematic: read-only inside a pass
+            if constexpr (STAGE == kStageSolve) {
+                load_inertia(B.inertia_world, idx, b[s].inertia);
+                if (T::kNeedsPose) load_pose(B.pose, idx, b[s].pos, b[s].q);
+            }
+        } else {
+            ok &= load_velocity_versioned(B.velocity, idx, expected_version(refs, chain_delta, s, pass_index), v[s], error_flag);
+            if constexpr (STAGE == kStageSolve) {
+                ok &= load_inertia_stamped(B.inertia_world, idx, b[s].inertia, ws_stamp, error_flag);
                 if (T::kNeedsPose) {
-                    if (dynamic[s] && pose_stamped) load_pose_stamped(B.pose, idx, b[s].pos, b[s].q, ws_stamp, error_flag);
+                    if (pose_stamped) ok &= load_pose_stamped(B.pose, idx, b[s].pos, b[s].q, ws_stamp, error_flag);
                     else load_pose(B.pose, idx, b[s].pos, b[s].q);
                 }
             }
         }
     }
+    if (!ok) return;  // a dependency never arrived: the error flag is set, results are void
     rows_ready(p);
-    // 1. wait for the notifications of this pass (one 4-byte poll per warp)
-    unsigned int spins = 0;
-    bool failed = false;
-    if (target != first) {
-        while ((int)(ld_relaxed_u32(my_counter) - target) < 0) {
-            if (++spins > kDataflowSpinLimit || ((spins & 1023u) == 0u && *reinterpret_cast<volatile int32_t*>(error_flag) == 4)) { failed = true; break; }
-            if (spins > 2) __nanosleep(32);
-        }
-        if (lane == 0) *my_counter = first;  // all of this pass's notifications are in: ready for the next pass (which starts after a kernel boundary)
-    }
-    // 2. gather; a record whose store has not landed yet (the notification overtook it) is simply read again
-    spins = 0;
-    while (!failed) {
-        bool all = true;
-#pragma unroll
-        for (int s = 0; s < NB; ++s) {
-            if (!ready[s]) {
-                const F8 r = ld256(B.velocity + 2 * (size_t)(enc[s] & kRefIndexMask));
-                if (__float_as_uint(r.d) == expect[s] && __float_as_uint(r.h) == expect[s]) {
-                    v[s].lin = {r.a, r.b, r.c};
-                    v[s].ang = {r.e, r.f, r.g};
-                    ready[s] = true;
-                } else {
-                    all = false;
-                }
-            }
-        }
-        if (__all_sync(0xffffffffu, all)) break;
-        if (++spins > kDataflowSpinLimit / 16) failed = true;
-    }
-    if (__any_sync(0xffffffffu, failed)) {
-        atomicExch(error_flag, 4);  // results are void; drain quickly
-        return;
-    }
-    if (empty) return;
-#pragma unroll
-    for (int s = 0; s < NB; ++s)
-        if (!dynamic[s]) load_velocity(B.velocity, enc[s] & kRefIndexMask, v[s]);  // kinematic: read-only inside a region
     if constexpr (STAGE == kStageSolve) {
         call_solve<T>(b, fp.dt, fp.inverse_dt, p, a, v);
     } else {
@@ -216,18 +223,32 @@ BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_
     }
 #pragma unroll
     for (int s = 0; s < NB; ++s)
-        if (dynamic[s]) {
-            store_velocity_versioned(B.velocity, enc[s] & kRefIndexMask, v[s], expect[s] + 1u);
-            if (succ[s] >= 0) red_add_u32(counters + succ[s], 1u);  // the body's last constraint of the pass has nobody to wake
+        if (!(enc[s] & kRefKinematicBit)) {
+            const uint32_t idx = enc[s] & kRefIndexMask;
+            store_velocity_versioned(B.velocity, idx, v[s], expected_version(refs, chain_delta, s, pass_index) + 1u);
+            const int32_t succ = (int32_t)ldg_nc_u32(refs + succ_delta + s * kLanes);
+            if (succ >= 0) red_add_u32(counters + succ, 1u);  // the body's last constraint of the pass has nobody to wake
         }
 }
 
 // kContactsOnly: the type switch holds the 14 contact types only (scenes without joints: shorter code, lower register pressure).
-#define BEPU_DATAFLOW_ARGS rec, lane, df.chain_delta, df.succ_delta, df.counters, my_counter, target, first, slab_addr, bar, parity, prestep_bytes, B, fp, pass_index, ws_stamp, pose_stamped, error_flag
+#define BEPU_DATAFLOW_ARGS rec, lane, df.chain_delta, df.succ_delta, df.counters, slab_addr, bar, parity, prestep_bytes, B, fp, pass_index, ws_stamp, pose_stamped, error_flag
 template <int STAGE, bool kContactsOnly>
 BEPU_DI void run_bundle_dataflow(const WorkRecord& rec, int lane, const DataflowTables& df, unsigned int* my_counter, unsigned int target, unsigned int first, uint32_t slab_addr, uint32_t bar,
                                  uint32_t parity, uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, uint32_t ws_stamp, bool pose_stamped,
                                  int32_t* error_flag) {
+    // wait for the notifications of this pass: one 4-byte poll for the whole warp
+    if (target != first) {
+        unsigned int spins = 0;
+        while ((int)(ld_relaxed_u32(my_counter) - target) < 0) {
+            if (++spins > kDataflowSpinLimit || ((spins & 1023u) == 0u && *reinterpret_cast<volatile int32_t*>(error_flag) == 4)) {
+                if (lane == 0) report_stall(error_flag, 1, target, ld_relaxed_u32(my_counter), (uint32_t)(my_counter - df.counters));  // results are void; drain quickly
+                return;
+            }
+            if (spins > 2) __nanosleep(32);
+        }
+        if (lane == 0) *my_counter = first;  // all of this pass's notifications are in: ready for the next pass (which starts after a kernel boundary)
+    }
     switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \
     case ID: run_lane_dataflow<T, STAGE>(BEPU_DATAFLOW_ARGS); break;
@@ -253,7 +274,7 @@ BEPU_DI void run_bundle_dataflow(const WorkRecord& rec, int lane, const Dataflow
 // version pass * degree and the first constraint on each body needs no notification. A bundle's counter therefore starts each pass at `first`
 // (dep_counts.y) and must reach dep_counts.x; the warp that consumed it resets it for the next pass.
 template <int STAGE, bool kContactsOnly>
-__global__ void __launch_bounds__(kPersistentThreads, BEPU_DATAFLOW_MINB)
+__global__ void __launch_bounds__(kDataflowThreads, BEPU_DATAFLOW_MINB)
 dataflow_pass_kernel(const WorkRecord* __restrict__ records, int work_count, DataflowTables df, BodyBuffers B, const FrameParams* __restrict__ fpp, uint32_t pass_offset,
                      uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag) {
     extern __shared__ __align__(128) unsigned char dataflow_smem[];
@@ -270,6 +291,10 @@ dataflow_pass_kernel(const WorkRecord* __restrict__ records, int work_count, Dat
     const uint32_t ws_stamp = fp.pass_base + ws_pass_offset + 1u;  // stamp of this substep's WarmStart pass
     const uint64_t policy = l2_evict_first_policy();
     for (int g = warp_in_block * gridDim.x + blockIdx.x; g < work_count; g += total_warps) {
+        // The slab address is loop-invariant; laundering it keeps the compiler from hoisting every row address of every type out of this loop
+        // (hundreds of live registers, spilled), which the single-bundle stage kernels never suffer from.
+        uint32_t slab_it = slab_addr, bar_it = bar;
+        asm volatile("" : "+r"(slab_it), "+r"(bar_it));
         const WorkRecord rec = load_record(records + g);
         const int2 deps = __ldg(df.dep_counts + g);
         unsigned int* my_counter = df.counters + g;
@@ -278,11 +303,11 @@ dataflow_pass_kernel(const WorkRecord* __restrict__ records, int work_count, Dat
         __syncwarp();  // every lane is done with the slab's previous contents
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar, prestep_bytes + impulse_bytes);
-            bulk_copy_g2s(slab_addr, rec.prestep, prestep_bytes, bar, policy);
-            bulk_copy_g2s(slab_addr + prestep_bytes, rec.impulses, impulse_bytes, bar, policy);
+            mbar_expect_tx(bar_it, prestep_bytes + impulse_bytes);
+            bulk_copy_g2s(slab_it, rec.prestep, prestep_bytes, bar_it, policy);
+            bulk_copy_g2s(slab_it + prestep_bytes, rec.impulses, impulse_bytes, bar_it, policy);
         }
-        run_bundle_dataflow<STAGE, kContactsOnly>(rec, lane, df, my_counter, (unsigned int)deps.x, (unsigned int)deps.y, slab_addr, bar, parity, prestep_bytes, B, fp, pass_index, ws_stamp,
+        run_bundle_dataflow<STAGE, kContactsOnly>(rec, lane, df, my_counter, (unsigned int)deps.x, (unsigned int)deps.y, slab_it, bar_it, parity, prestep_bytes, B, fp, pass_index, ws_stamp,
                                                   pose_stamped != 0, error_flag);
         parity ^= 1u;
     }
@@ -300,8 +325,9 @@ static int launch_dataflow_pass_t(const WorkRecord* records, int work_count, con
         int sms = 0, max_per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDataflowSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, kernel, kPersistentThreads, kDataflowSmemBytes);
+        // shared memory for exactly the CTAs the register budget admits (slabs): the rest of the 256 KB stays L1, which also backs any register spill
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((BEPU_DATAFLOW_MINB * (kDataflowSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, kernel, kDataflowThreads, kDataflowSmemBytes);
         if (e != cudaSuccess) return (int)e;
         if (max_per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
         grid_limit[device & 63] = sms * 1024 + max_per_sm;
@@ -314,7 +340,7 @@ static int launch_dataflow_pass_t(const WorkRecord* records, int work_count, con
     if (grid < 1) return 0;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kPersistentThreads);
+    cfg.blockDim = dim3(kDataflowThreads);
     cfg.dynamicSmemBytes = kDataflowSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];

@@ -308,6 +308,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
         df.counters = ctx->df_counters.as<unsigned int>();
         for (const SourceTypeBatch& src : ctx->sources) contacts_only &= src.type_id <= 17;
         launch_reset_counters(df.dep_counts, df.counters, ctx->all_work_count, s);
+        cudaMemsetAsync(ctx->error_dev.ptr, 0, 32, s);  // stall report of this solve (see report_stall)
         ++n;
     }
     for (const StageOp& op : ctx->program) {
@@ -461,7 +462,7 @@ int32_t bepucuda_create(const bepucuda_config* cfg, bepucuda_ctx** out) {
     if (e == cudaSuccess) e = ctx->frame_params_dev.reserve(sizeof(FrameParams));
     if (e == cudaSuccess) e = ctx->barrier_dev.reserve(2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(ctx->barrier_dev.ptr, 0, 2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = ctx->error_dev.reserve(sizeof(int32_t));
+    if (e == cudaSuccess) e = ctx->error_dev.reserve(8 * sizeof(int32_t));
     if (e != cudaSuccess) {
         bepucuda_destroy(ctx);
         return e == cudaErrorMemoryAllocation ? BEPUCUDA_ERR_OUT_OF_MEMORY : BEPUCUDA_ERR_CUDA;
@@ -870,7 +871,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->sync_refcount.ptr, 0, nb * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->sync_mask.ptr, 0, nb * 8, ctx->stream));
     CK(cudaMemsetAsync(ctx->constrained.ptr, 0, nb, ctx->stream));
-    CK(cudaMemsetAsync(ctx->error_dev.ptr, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->error_dev.ptr, 0, 32, ctx->stream));
     CK(ctx->source_bundle_flags.reserve((size_t)std::max(total_source_bundles, 1) * 16));
     CK(cudaMemsetAsync(ctx->source_bundle_flags.ptr, 0, (size_t)std::max(total_source_bundles, 1) * 16, ctx->stream));
     launch_ownership_pass1(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), ctx->sync_batch_count,
@@ -1066,10 +1067,16 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
 
 static int check_device_error_flag(bepucuda_ctx* ctx) {
     if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_DATAFLOW) return BEPUCUDA_OK;
-    int32_t err = 0;
-    CK(cudaMemcpyAsync(&err, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t err[8] = {};
+    CK(cudaMemcpyAsync(err, ctx->error_dev.ptr, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (err == 4) return fail(ctx, BEPUCUDA_ERR_CUDA, "dataflow solve: a body version dependency never arrived (spin limit hit); results are invalid");
+    if (err[0] == 4) {
+        static const char* what[] = {"?", "bundle notification counter", "body velocity version", "world inertia stamp", "pose stamp"};
+        char msg[256];
+        snprintf(msg, sizeof(msg), "dataflow solve: a dependency never arrived (spin limit hit; %s: expected %u, observed %u, at %u); results are invalid",
+                 what[err[1] >= 0 && err[1] <= 4 ? err[1] : 0], (unsigned)err[2], (unsigned)err[3], (unsigned)err[4]);
+        return fail(ctx, BEPUCUDA_ERR_CUDA, msg);
+    }
     return BEPUCUDA_OK;
 }
 

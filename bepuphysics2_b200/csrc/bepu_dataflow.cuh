@@ -325,8 +325,10 @@ static int launch_dataflow_pass_t(const WorkRecord* records, int work_count, con
         int sms = 0, max_per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDataflowSmemBytes);
-        // shared memory for exactly the CTAs the register budget admits (slabs): the rest of the 256 KB stays L1, which also backs any register spill
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((BEPU_DATAFLOW_MINB * (kDataflowSmemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+        // Maximum shared-memory carveout: co-residency of the whole grid is what makes a pass deadlock-free, and a smaller preferred carveout that
+        // "just fits" two CTAs per SM was observed to leave the second CTA of every SM unscheduled (the cooperative-launch check uses the
+        // occupancy calculator, which assumes the largest carveout).
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, kernel, kDataflowThreads, kDataflowSmemBytes);
         if (e != cudaSuccess) return (int)e;
         if (max_per_sm < 1) return (int)cudaErrorLaunchOutOfResources;

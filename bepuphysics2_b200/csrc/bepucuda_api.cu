@@ -448,6 +448,7 @@ int32_t bepucuda_create(const bepucuda_config* cfg, bepucuda_ctx** out) {
     if (cfg->device_ordinal < 0 || cfg->device_ordinal >= count) return BEPUCUDA_ERR_INVALID_ARGUMENT;
     bepucuda_ctx* ctx = new bepucuda_ctx();
     ctx->cfg = *cfg;
+    if (getenv("BEPUCUDA_DATAFLOW_NOGRAPH")) ctx->dataflow_without_graph = true;  // development knob
     if (const char* tune = getenv("BEPUCUDA_TUNE")) sscanf(tune, "%d,%d,%d,%d", &ctx->tune[0], &ctx->tune[1], &ctx->tune[2], &ctx->tune[3]);
     ctx->device = cfg->device_ordinal;
     ctx->launchers = cfg->strict_fp ? get_launchers_bepu_strict() : get_launchers_bepu_fast();
@@ -1073,8 +1074,8 @@ static int check_device_error_flag(bepucuda_ctx* ctx) {
     if (err[0] == 4) {
         static const char* what[] = {"?", "bundle notification counter", "body velocity version", "world inertia stamp", "pose stamp"};
         char msg[256];
-        snprintf(msg, sizeof(msg), "dataflow solve: a dependency never arrived (spin limit hit; %s: expected %u, observed %u, at %u); results are invalid",
-                 what[err[1] >= 0 && err[1] <= 4 ? err[1] : 0], (unsigned)err[2], (unsigned)err[3], (unsigned)err[4]);
+        snprintf(msg, sizeof(msg), "dataflow solve: a dependency never arrived (spin limit hit; %s: expected %u, observed %u, at %u; raw %d %d %d %d %d %d); results are invalid",
+                 what[err[1] >= 0 && err[1] <= 4 ? err[1] : 0], (unsigned)err[2], (unsigned)err[3], (unsigned)err[4], err[0], err[1], err[2], err[3], err[4], err[5]);
         return fail(ctx, BEPUCUDA_ERR_CUDA, msg);
     }
     return BEPUCUDA_OK;

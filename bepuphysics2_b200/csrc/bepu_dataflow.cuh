@@ -50,6 +50,17 @@ BEPU_DI unsigned int ld_relaxed_u32(const unsigned int* p) {
 }
 BEPU_DI void red_add_u32(unsigned int* p, unsigned int v) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+// A dependency that never arrives is a bug in the tables, not a reason to hang the GPU: the first lane to give up records what it was waiting for
+// (error_flag[0] = 4, [1] = what: 1 counter, 2 velocity version, 3 inertia stamp, 4 pose stamp, [2] = expected, [3] = observed, [4] = body or bundle).
+BEPU_DI void report_stall(int32_t* error_flag, int what, uint32_t expected, uint32_t observed, uint32_t where) {
+    if (atomicCAS(error_flag, 0, 4) == 0) {
+        error_flag[1] = what;
+        error_flag[2] = (int32_t)expected;
+        error_flag[3] = (int32_t)observed;
+        error_flag[4] = (int32_t)where;
+    }
+}
+
 // World inertia / pose records written by the integrating (first) constraint of a body carry a stamp in their padding word: the number of the
 // WarmStart pass that wrote them + 1. Readers of the same substep wait for that stamp instead of relying on a fence in the writer.
 BEPU_DI void store_inertia_stamped(float4* in, uint32_t i, const Inertia& r, uint32_t stamp) {
@@ -136,17 +147,6 @@ BEPU_DI void warm_start_body_dataflow(uint32_t enc, const BodyBuffers& B, const 
             if (fp.angular_mode == 1) integrate_angular_conserve_momentum(integrate_orientation(q, v.ang, fp.dt * -0.5f), local.t, b.inertia.t, v.ang);
             else integrate_angular_gyroscopic(q, local.t, v.ang, fp.dt);
         }
-    }
-}
-
-// A dependency that never arrives is a bug in the tables, not a reason to hang the GPU: the first lane to give up records what it was waiting for
-// (error_flag[0] = 4, [1] = what: 1 counter, 2 velocity version, 3 inertia stamp, 4 pose stamp, [2] = expected, [3] = observed, [4] = body or bundle).
-BEPU_DI void report_stall(int32_t* error_flag, int what, uint32_t expected, uint32_t observed, uint32_t where) {
-    if (atomicCAS(error_flag, 0, 4) == 0) {
-        error_flag[1] = what;
-        error_flag[2] = (int32_t)expected;
-        error_flag[3] = (int32_t)observed;
-        error_flag[4] = (int32_t)where;
     }
 }
 

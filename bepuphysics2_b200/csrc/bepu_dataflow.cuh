@@ -226,6 +226,7 @@ BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_
         if (!(enc[s] & kRefKinematicBit)) {
             const uint32_t idx = enc[s] & kRefIndexMask;
             store_velocity_versioned(B.velocity, idx, v[s], expected_version(refs, chain_delta, s, pass_index) + 1u);
+            if (fp.tune[2]) __threadfence();  // development knob: release order between the record and its notification
             const int32_t succ = (int32_t)ldg_nc_u32(refs + succ_delta + s * kLanes);
             if (succ >= 0) red_add_u32(counters + succ, 1u);  // the body's last constraint of the pass has nobody to wake
         }
@@ -248,6 +249,7 @@ BEPU_DI void run_bundle_dataflow(const WorkRecord& rec, int lane, const Dataflow
             if (spins > 2) __nanosleep(32);
         }
         if (lane == 0) *my_counter = first;  // all of this pass's notifications are in: ready for the next pass (which starts after a kernel boundary)
+        if (fp.tune[3]) __threadfence();  // development knob
     }
     switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \

@@ -12,8 +12,8 @@
 //   * waiting costs no memory bandwidth: every bundle has ONE notification counter. A lane that has written body X adds 1 to the counter of the
 //     bundle holding the NEXT constraint on X (static: the "successor" table built at bepucuda_end_constraints); a warp polls only its bundle's
 //     counter (one 4-byte load per poll for the whole warp) until all of its (lane, body) dependencies of this pass have reported, and only then
-//     gathers the velocity records. The counter is a wake-up hint, not the synchronisation: the gather still checks every record's version and
-//     re-reads a record whose store has not landed yet, so no fence is needed between a producer's record store and its notification;
+//     gathers the velocity records. A producer releases (fence.acq_rel.gpu) between its record stores and its notifications; the gather still
+//     checks every record's version, so a consumer can never compute on a stale record;
 //   * warps own bundles statically (bundle g -> warp g mod T) and walk their bundles in program order; while a warp waits it already holds its
 //     bundle's prestep + impulse block in its shared-memory slab (one cp.async.bulk pair), its body references and -- in Solve passes -- the world
 //     inertias, so a dependency link costs (notification visible) + (velocity gather) + math + (store);
@@ -223,10 +223,13 @@ BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_
     }
 #pragma unroll
     for (int s = 0; s < NB; ++s)
+        if (!(enc[s] & kRefKinematicBit)) store_velocity_versioned(B.velocity, enc[s] & kRefIndexMask, v[s], expected_version(refs, chain_delta, s, pass_index) + 1u);
+    // Release: the records (and, for an integrating lane, the stamped pose / world inertia) must be visible before the notification that lets the next
+    // constraint on the body gather them. Without it the stores were observed to stay invisible for as long as the consumer spun (B200, 2 CTAs / SM).
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#pragma unroll
+    for (int s = 0; s < NB; ++s)
         if (!(enc[s] & kRefKinematicBit)) {
-            const uint32_t idx = enc[s] & kRefIndexMask;
-            store_velocity_versioned(B.velocity, idx, v[s], expected_version(refs, chain_delta, s, pass_index) + 1u);
-            if (fp.tune[2]) __threadfence();  // development knob: release order between the record and its notification
             const int32_t succ = (int32_t)ldg_nc_u32(refs + succ_delta + s * kLanes);
             if (succ >= 0) red_add_u32(counters + succ, 1u);  // the body's last constraint of the pass has nobody to wake
         }
@@ -249,7 +252,6 @@ BEPU_DI void run_bundle_dataflow(const WorkRecord& rec, int lane, const Dataflow
             if (spins > 2) __nanosleep(32);
         }
         if (lane == 0) *my_counter = first;  // all of this pass's notifications are in: ready for the next pass (which starts after a kernel boundary)
-        if (fp.tune[3]) __threadfence();  // development knob
     }
     switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \

@@ -39,9 +39,22 @@ constexpr int kDataflowSmemBytes = kDataflowWarps * kStageSlabBytes + kDataflowW
 #define BEPU_DATAFLOW_MINB 2
 #endif
 
+// Body records inside a pass are read and written with STRONG gpu-scope accesses (LDG/STG.E.256.STRONG.GPU): they are performed at the L2, the
+// coherence point of all SMs. Weak (.cg) stores were observed to stay invisible to other SMs for as long as a consumer spun on the record.
+BEPU_DI F8 ld256_strong(const float4* p) {
+    F8 r;
+    asm volatile("ld.relaxed.gpu.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a), "=f"(r.b), "=f"(r.c), "=f"(r.d), "=f"(r.e), "=f"(r.f), "=f"(r.g), "=f"(r.h)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+BEPU_DI void st256_strong(float4* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.relaxed.gpu.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+}
 BEPU_DI void store_velocity_versioned(float4* vel, uint32_t i, const Velocity& v, uint32_t version) {
     const float ver = __uint_as_float(version);
-    st256(vel + 2 * (size_t)i, v.lin.x, v.lin.y, v.lin.z, ver, v.ang.x, v.ang.y, v.ang.z, ver);
+    st256_strong(vel + 2 * (size_t)i, v.lin.x, v.lin.y, v.lin.z, ver, v.ang.x, v.ang.y, v.ang.z, ver);
 }
 BEPU_DI unsigned int ld_relaxed_u32(const unsigned int* p) {
     unsigned int v;
@@ -62,40 +75,39 @@ BEPU_DI void report_stall(int32_t* error_flag, int what, uint32_t expected, uint
 }
 
 // World inertia / pose records written by the integrating (first) constraint of a body carry a stamp in their padding word: the number of the
-// WarmStart pass that wrote them + 1. Readers of the same substep wait for that stamp instead of relying on a fence in the writer.
+// WarmStart pass that wrote them + 1. Readers of the same substep check that stamp instead of relying on a fence in the writer.
 BEPU_DI void store_inertia_stamped(float4* in, uint32_t i, const Inertia& r, uint32_t stamp) {
-    st256(in + 2 * (size_t)i, r.t.xx, r.t.yx, r.t.yy, r.t.zx, r.t.zy, r.t.zz, r.inv_mass, __uint_as_float(stamp));
+    st256_strong(in + 2 * (size_t)i, r.t.xx, r.t.yx, r.t.yy, r.t.zx, r.t.zy, r.t.zz, r.inv_mass, __uint_as_float(stamp));
 }
-BEPU_DI void store_pose_stamped(float4* pose, uint32_t i, V3 pos, Q4 q, uint32_t stamp) { st256(pose + 2 * (size_t)i, q.x, q.y, q.z, q.w, pos.x, pos.y, pos.z, __uint_as_float(stamp)); }
-BEPU_DI bool load_inertia_stamped(const float4* in, uint32_t i, Inertia& r, uint32_t stamp, int32_t* error_flag) {
-#ifdef BEPU_DF_PLAIN
-    load_inertia(in, i, r);
-    return true;
-#else
-    F8 x;
+BEPU_DI void store_pose_stamped(float4* pose, uint32_t i, V3 pos, Q4 q, uint32_t stamp) {
+    st256_strong(pose + 2 * (size_t)i, q.x, q.y, q.z, q.w, pos.x, pos.y, pos.z, __uint_as_float(stamp));
+}
+// Re-reads a record until its tag word(s) carry `tag` (`both`: the two version words of a velocity record). Only entered when the first read,
+// issued together with the bundle's other gathers, was early.
+BEPU_DI bool reload_until(const float4* p, uint32_t tag, bool both, F8& x, int what, uint32_t where, int32_t* error_flag) {
     unsigned int spins = 0;
     bool good;
     do {
-        x = ld256(in + 2 * (size_t)i);
-        good = __float_as_uint(x.h) == stamp;
+        x = ld256_strong(p);
+        good = __float_as_uint(x.h) == tag && (!both || __float_as_uint(x.d) == tag);
     } while (!good && ++spins < kDataflowSpinLimit / 16);
+    if (!good) report_stall(error_flag, what, tag, __float_as_uint(x.h), where);
+    return good;
+}
+BEPU_DI bool load_inertia_stamped(const float4* in, uint32_t i, Inertia& r, uint32_t stamp, int32_t* error_flag) {
+    F8 x = ld256_strong(in + 2 * (size_t)i);
+    bool good = __float_as_uint(x.h) == stamp;
+    if (!good) good = reload_until(in + 2 * (size_t)i, stamp, false, x, 3, i, error_flag);
     r.t = {x.a, x.b, x.c, x.d, x.e, x.f};
     r.inv_mass = x.g;
-    if (!good) report_stall(error_flag, 3, stamp, __float_as_uint(x.h), i);
     return good;
-#endif
 }
 BEPU_DI bool load_pose_stamped(const float4* pose, uint32_t i, V3& pos, Q4& q, uint32_t stamp, int32_t* error_flag) {
-    F8 x;
-    unsigned int spins = 0;
-    bool good;
-    do {
-        x = ld256(pose + 2 * (size_t)i);
-        good = __float_as_uint(x.h) == stamp;
-    } while (!good && ++spins < kDataflowSpinLimit / 16);
+    F8 x = ld256_strong(pose + 2 * (size_t)i);
+    bool good = __float_as_uint(x.h) == stamp;
+    if (!good) good = reload_until(pose + 2 * (size_t)i, stamp, false, x, 4, i, error_flag);
     q = {x.a, x.b, x.c, x.d};
     pos = {x.e, x.f, x.g};
-    if (!good) report_stall(error_flag, 4, stamp, __float_as_uint(x.h), i);
     return good;
 }
 
@@ -150,65 +162,70 @@ BEPU_DI void warm_start_body_dataflow(uint32_t enc, const BodyBuffers& B, const 
     }
 }
 
-// Expected version of body slot s at this pass (see the file comment), from the chain word next to the body reference.
-BEPU_DI uint32_t expected_version(const int32_t* refs, long long chain_delta, int s, uint32_t pass_index) {
-    const uint32_t chain = ldg_nc_u32(refs + chain_delta + s * kLanes);
-    return pass_index * (chain >> kChainDegreeShift) + (chain & kChainRankMask);
-}
-// Velocity gather with the version check: a record whose store has not landed yet (the notification overtook it) is simply read again.
-BEPU_DI bool load_velocity_versioned(const float4* vel, uint32_t idx, uint32_t expect, Velocity& v, int32_t* error_flag) {
-#ifdef BEPU_DF_PLAIN
-    load_velocity(vel, idx, v);
-    return true;
-#else
-    F8 r;
-    unsigned int spins = 0;
-    bool good;
-    do {
-        r = ld256(vel + 2 * (size_t)idx);
-        good = __float_as_uint(r.d) == expect && __float_as_uint(r.h) == expect;
-    } while (!good && ++spins < kDataflowSpinLimit / 16);
-    v.lin = {r.a, r.b, r.c};
-    v.ang = {r.e, r.f, r.g};
-    if (!good) report_stall(error_flag, 2, expect, __float_as_uint(r.d), idx);
-    return good;
-#endif
-}
-
 // Everything a lane does for its constraint in one pass; shaped like run_lane (bepu_solver_kernels.cuh) so that the register allocation of the math
-// is the stage kernels': only the body references stay live across it, chain / successor words are (re)read from L1 where they are needed.
-// Inlined into the type switch of the kernel (no calls: the ABI's register save/restore and by-reference arguments would live in local memory).
+// is the stage kernels'. Inlined into the type switch of the kernel (no calls: the ABI's register save/restore and by-reference arguments would live
+// in local memory). Order: static words (references, chain, successor) -> wait for this pass's notifications -> ALL body records gathered in one
+// round trip -> tag checks (re-read only what was early) -> math -> versioned stores -> notifications.
 template <class T, int STAGE>
-BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_delta, long long succ_delta, unsigned int* counters, uint32_t slab_addr, uint32_t bar, uint32_t parity,
-                               uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, uint32_t ws_stamp, bool pose_stamped, int32_t* error_flag) {
+BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_delta, long long succ_delta, unsigned int* counters, unsigned int* my_counter, unsigned int target,
+                               unsigned int first, uint32_t slab_addr, uint32_t bar, uint32_t parity, uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp,
+                               uint32_t pass_index, uint32_t ws_stamp, bool pose_stamped, int32_t* error_flag) {
     constexpr int NB = T::kBodies;
     const int32_t* refs = rec.refs + lane;
     const StagedRows p{slab_addr + lane * 4, bar, parity};
     const StagedAcc a{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane};
-    uint32_t enc[NB];
+    uint32_t enc[NB], version[NB];
+    int32_t succ[NB];
 #pragma unroll
-    for (int s = 0; s < NB; ++s) enc[s] = ldg_nc_u32(refs + s * kLanes);
+    for (int s = 0; s < NB; ++s) {
+        enc[s] = ldg_nc_u32(refs + s * kLanes);
+        const uint32_t chain = ldg_nc_u32(refs + chain_delta + s * kLanes);
+        succ[s] = (int32_t)ldg_nc_u32(refs + succ_delta + s * kLanes);
+        version[s] = pass_index * (chain >> kChainDegreeShift) + (chain & kChainRankMask);  // expected now; + 1 is what this lane publishes
+    }
+    // wait for the notifications of this pass: one 4-byte poll for the whole warp
+    if (target != first) {
+        unsigned int spins = 0;
+        while ((int)(ld_relaxed_u32(my_counter) - target) < 0) {
+            if (++spins > kDataflowSpinLimit || ((spins & 1023u) == 0u && *reinterpret_cast<volatile int32_t*>(error_flag) == 4)) {
+                if (lane == 0) report_stall(error_flag, 1, target, ld_relaxed_u32(my_counter), (uint32_t)(my_counter - counters));  // results are void; drain quickly
+                return;
+            }
+            if (spins > 2) __nanosleep(32);
+        }
+        if (lane == 0) *my_counter = first;  // all of this pass's notifications are in: ready for the next pass (which starts after a kernel boundary)
+    }
     if ((int32_t)enc[0] == kRefEmpty) return;  // trailing lane of the last bundle, or a hole in a fallback bundle
+    // gather: every record this lane needs, issued back to back
+    F8 rv[NB], ri[NB], rp[NB];
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+        const uint32_t idx = enc[s] & kRefIndexMask;
+        rv[s] = ld256_strong(B.velocity + 2 * (size_t)idx);
+        if constexpr (STAGE == kStageSolve) {
+            ri[s] = ld256_strong(B.inertia_world + 2 * (size_t)idx);
+            if (T::kNeedsPose) rp[s] = ld256_strong(B.pose + 2 * (size_t)idx);
+        }
+    }
     BodyState b[NB];
     Velocity v[NB];
     bool ok = true;
 #pragma unroll
     for (int s = 0; s < NB; ++s) {
         const uint32_t idx = enc[s] & kRefIndexMask;
-        if (enc[s] & kRefKinematicBit) {
-            load_velocity(B.velocity, idx, v[s]);  // kinematic: read-only inside a pass
-            if constexpr (STAGE == kStageSolve) {
-                load_inertia(B.inertia_world, idx, b[s].inertia);
-                if (T::kNeedsPose) load_pose(B.pose, idx, b[s].pos, b[s].q);
-            }
-        } else {
-            ok &= load_velocity_versioned(B.velocity, idx, expected_version(refs, chain_delta, s, pass_index), v[s], error_flag);
-            if constexpr (STAGE == kStageSolve) {
-                ok &= load_inertia_stamped(B.inertia_world, idx, b[s].inertia, ws_stamp, error_flag);
-                if (T::kNeedsPose) {
-                    if (pose_stamped) ok &= load_pose_stamped(B.pose, idx, b[s].pos, b[s].q, ws_stamp, error_flag);
-                    else load_pose(B.pose, idx, b[s].pos, b[s].q);
-                }
+        const bool dynamic = !(enc[s] & kRefKinematicBit);  // kinematic records are read-only inside a pass: nothing to check
+        if (dynamic && (__float_as_uint(rv[s].d) != version[s] || __float_as_uint(rv[s].h) != version[s]))
+            ok &= reload_until(B.velocity + 2 * (size_t)idx, version[s], true, rv[s], 2, idx, error_flag);
+        v[s].lin = {rv[s].a, rv[s].b, rv[s].c};
+        v[s].ang = {rv[s].e, rv[s].f, rv[s].g};
+        if constexpr (STAGE == kStageSolve) {
+            if (dynamic && __float_as_uint(ri[s].h) != ws_stamp) ok &= reload_until(B.inertia_world + 2 * (size_t)idx, ws_stamp, false, ri[s], 3, idx, error_flag);
+            b[s].inertia.t = {ri[s].a, ri[s].b, ri[s].c, ri[s].d, ri[s].e, ri[s].f};
+            b[s].inertia.inv_mass = ri[s].g;
+            if (T::kNeedsPose) {
+                if (dynamic && pose_stamped && __float_as_uint(rp[s].h) != ws_stamp) ok &= reload_until(B.pose + 2 * (size_t)idx, ws_stamp, false, rp[s], 4, idx, error_flag);
+                b[s].q = {rp[s].a, rp[s].b, rp[s].c, rp[s].d};
+                b[s].pos = {rp[s].e, rp[s].f, rp[s].g};
             }
         }
     }
@@ -223,36 +240,19 @@ BEPU_DI void run_lane_dataflow(const WorkRecord& rec, int lane, long long chain_
     }
 #pragma unroll
     for (int s = 0; s < NB; ++s)
-        if (!(enc[s] & kRefKinematicBit)) store_velocity_versioned(B.velocity, enc[s] & kRefIndexMask, v[s], expected_version(refs, chain_delta, s, pass_index) + 1u);
-    // Release: the records (and, for an integrating lane, the stamped pose / world inertia) must be visible before the notification that lets the next
-    // constraint on the body gather them. Without it the stores were observed to stay invisible for as long as the consumer spun (B200, 2 CTAs / SM).
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (!(enc[s] & kRefKinematicBit)) store_velocity_versioned(B.velocity, enc[s] & kRefIndexMask, v[s], version[s] + 1u);
+    if (fp.tune[2]) asm volatile("fence.acq_rel.gpu;" ::: "memory");  // development knob (A/B): release between the records and the notifications
 #pragma unroll
     for (int s = 0; s < NB; ++s)
-        if (!(enc[s] & kRefKinematicBit)) {
-            const int32_t succ = (int32_t)ldg_nc_u32(refs + succ_delta + s * kLanes);
-            if (succ >= 0) red_add_u32(counters + succ, 1u);  // the body's last constraint of the pass has nobody to wake
-        }
+        if (!(enc[s] & kRefKinematicBit) && succ[s] >= 0) red_add_u32(counters + succ[s], 1u);  // the body's last constraint of the pass has nobody to wake
 }
 
 // kContactsOnly: the type switch holds the 14 contact types only (scenes without joints: shorter code, lower register pressure).
-#define BEPU_DATAFLOW_ARGS rec, lane, df.chain_delta, df.succ_delta, df.counters, slab_addr, bar, parity, prestep_bytes, B, fp, pass_index, ws_stamp, pose_stamped, error_flag
+#define BEPU_DATAFLOW_ARGS rec, lane, df.chain_delta, df.succ_delta, df.counters, my_counter, target, first, slab_addr, bar, parity, prestep_bytes, B, fp, pass_index, ws_stamp, pose_stamped, error_flag
 template <int STAGE, bool kContactsOnly>
 BEPU_DI void run_bundle_dataflow(const WorkRecord& rec, int lane, const DataflowTables& df, unsigned int* my_counter, unsigned int target, unsigned int first, uint32_t slab_addr, uint32_t bar,
                                  uint32_t parity, uint32_t prestep_bytes, const BodyBuffers& B, const FrameParams& fp, uint32_t pass_index, uint32_t ws_stamp, bool pose_stamped,
                                  int32_t* error_flag) {
-    // wait for the notifications of this pass: one 4-byte poll for the whole warp
-    if (target != first) {
-        unsigned int spins = 0;
-        while ((int)(ld_relaxed_u32(my_counter) - target) < 0) {
-            if (++spins > kDataflowSpinLimit || ((spins & 1023u) == 0u && *reinterpret_cast<volatile int32_t*>(error_flag) == 4)) {
-                if (lane == 0) report_stall(error_flag, 1, target, ld_relaxed_u32(my_counter), (uint32_t)(my_counter - df.counters));  // results are void; drain quickly
-                return;
-            }
-            if (spins > 2) __nanosleep(32);
-        }
-        if (lane == 0) *my_counter = first;  // all of this pass's notifications are in: ready for the next pass (which starts after a kernel boundary)
-    }
     switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \
     case ID: run_lane_dataflow<T, STAGE>(BEPU_DATAFLOW_ARGS); break;

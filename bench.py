@@ -389,6 +389,36 @@ def main():
         torch.cuda.synchronize()
         prof = ts.profile_stages(DT).as_dict()
 
+    # ---- end to end with the device-side contact update: accumulated impulses stay on the device and are redistributed there from
+    # ---- the old to the new feature ids; per step the host sends the motion half of the bodies, the new prestep data and the new feature ids, and
+    # ---- reads back the motion half of the bodies only
+    resident = None
+    if rank == 0 and args.scene == "shape_pile":
+        frng = np.random.default_rng(11)
+        count = lambda tid: (tid & 3) + 1 if tid <= 7 else (tid - 6 if tid <= 10 else tid - 13)
+        feats = {(tb.batch_index, tb.type_batch_index): frng.integers(0, 1 << 20, size=(tb.constraint_count, count(tb.type_id)), dtype=np.int32) for tb in sim.type_batches() if tb.type_id <= 17}
+        ts.describe()
+        ts.set_contact_features(feats)
+        for _ in range(2):
+            ts.upload_body_motion()
+            ts.update_contacts(feats)
+            ts.solve_device_only(DT)
+            ts.download_body_motion()
+        ts.synchronize()
+        r_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(r_steps):
+            ts.upload_body_motion()
+            ts.update_contacts(feats)
+            ts.solve_device_only(DT)
+            ts.download_body_motion()
+        ts.synchronize()
+        r_s = time.perf_counter() - t0
+        tr = ts.timings()
+        resident = {"value": ci_per_step * r_steps / r_s, "unit": "constraint-iterations/s", "ms_per_step": r_s / r_steps * 1e3, "steps": r_steps,
+                    "h2d_bytes_per_step": int(tr.h2d_bytes), "d2h_bytes_per_step": int(tr.d2h_bytes),
+                    "what": "every step: upload the motion half of the bodies (64 B / body) + prestep + contact feature ids, redistribute the resident impulses on the device, solve, download the motion half of the bodies"}
+
     configs = None
     if rank == 0 and world == 1 and not args.no_configs and args.scene == "shape_pile":
         ts.close()
@@ -455,6 +485,8 @@ def main():
         line["ms_per_step_per_rank"] = per_rank_ms
         if topo is not None:
             line["e2e_topology_change"] = topo
+        if resident is not None:
+            line["e2e_resident_impulses"] = resident
         if configs is not None:
             line["configs"] = configs
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only

@@ -65,10 +65,73 @@ __global__ void transpose_in_all_kernel(const DeviceTypeBatch* __restrict__ tbs,
         float* dst = tb.prestep + (size_t)w.bundle * d.prestep_rows * 32 + lane;
         for (int r = 0; r < d.prestep_rows; ++r) dst[r * 32] = c < 0 ? 0.0f : d.src_prestep[(sb * d.prestep_rows + r) * W + sl];
     }
-    if (what & kTransposeImpulses) {
+    if ((what & kTransposeImpulses) && !(d.flags & kDescResidentImpulses)) {
         float* dst = tb.impulses + (size_t)w.bundle * d.impulse_rows * 32 + lane;
         for (int r = 0; r < d.impulse_rows; ++r) dst[r * 32] = c < 0 ? 0.0f : d.src_impulses[(sb * d.impulse_rows + r) * W + sl];
     }
+}
+
+// NarrowPhase.RedistributeImpulses (CollisionDetection/NarrowPhaseConstraintUpdate.cs:L81-135) on the device-resident penetration impulses of one
+// constraint: a new contact whose feature id matches an old one takes that contact's accumulated impulse; the impulse of unmatched old contacts is
+// shared equally among the unmatched new contacts. Same-type update: old and new contact counts are equal (L172-183). Penetration rows of the
+// accumulated impulses: convex types [2 + i] (after the two tangent rows, ContactConstraintAccessor.cs:L58-66), nonconvex types [3 i + 2] (L70-76).
+__global__ void redistribute_impulses_kernel(const DeviceTypeBatch* __restrict__ tbs, const TransposeDesc* __restrict__ descs, const WorkItem* __restrict__ work, int work_count) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= work_count) return;
+    const WorkItem w = work[warp];
+    const TransposeDesc d = descs[w.type_batch];
+    if (!(d.flags & kDescRedistribute)) return;
+    const DeviceTypeBatch tb = tbs[w.type_batch];
+    const int slot = w.bundle * 32 + lane;
+    const int c = d.map ? d.map[slot] : slot;
+    if (c < 0 || c >= d.src_count) return;
+    const bool convex = tb.type_id < 8;
+    const int n = convex ? (tb.type_id & 3) + 1 : (tb.type_id < 15 ? tb.type_id - 6 : tb.type_id - 13);  // ids 0-7: 1-4 contacts; 8-10 / 15-17: 2-4
+    float* acc = tb.impulses + (size_t)w.bundle * d.impulse_rows * 32 + lane;
+    const int32_t* oldIds = d.features_old + (size_t)c * n;
+    const int32_t* newIds = d.features_new + (size_t)c * n;
+    float oldImpulses[4], newImpulses[4];
+    for (int i = 0; i < n; ++i) oldImpulses[i] = acc[(convex ? 2 + i : 3 * i + 2) * 32];
+    int unmatchedCount = 0;
+    for (int i = 0; i < n; ++i) {
+        newImpulses[i] = -1.0f;  // accumulated impulses cannot be negative: negative = unmatched
+        for (int j = 0; j < n; ++j) {
+            if (oldIds[j] == newIds[i]) {
+                newImpulses[i] = oldImpulses[j];
+                oldImpulses[j] = 0.0f;  // not distributed to the unmatched contacts
+                break;
+            }
+        }
+        if (newImpulses[i] < 0.0f) ++unmatchedCount;
+    }
+    if (unmatchedCount > 0) {
+        float unmatchedImpulse = 0.0f;
+        for (int i = 0; i < n; ++i) unmatchedImpulse += oldImpulses[i];
+        const float impulsePerUnmatched = unmatchedImpulse / (float)unmatchedCount;
+        for (int i = 0; i < n; ++i)
+            if (newImpulses[i] < 0.0f) newImpulses[i] = impulsePerUnmatched;
+    }
+    for (int i = 0; i < n; ++i) acc[(convex ? 2 + i : 3 * i + 2) * 32] = newImpulses[i];
+}
+
+// One thread per float4 of the motion half of a BodyDynamics record (float4 0,1 -> pose, 2,3 -> velocity).
+__global__ void scatter_body_motion_kernel(const float4* __restrict__ raw, int body_count, BodyBuffers B) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)body_count * 4) return;
+    const size_t body = t >> 2;
+    const int part = (int)(t & 3);
+    float4 v = raw[body * 8 + part];
+    if (part != 0) v.w = 0.0f;  // padding floats carry no meaning (and hold versions / stamps on the device)
+    (part < 2 ? B.pose : B.velocity)[body * 2 + (part & 1)] = v;
+}
+__global__ void gather_body_motion_kernel(float4* __restrict__ raw, int body_count, BodyBuffers B) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)body_count * 4) return;
+    const size_t body = t >> 2;
+    const int part = (int)(t & 3);
+    float4 v = (part < 2 ? B.pose : B.velocity)[body * 2 + (part & 1)];
+    if (part != 0) v.w = 0.0f;
+    raw[body * 8 + part] = v;
 }
 __global__ void transpose_out_all_kernel(const DeviceTypeBatch* __restrict__ tbs, const TransposeDesc* __restrict__ descs, const WorkItem* __restrict__ work, int work_count,
                                          int W, int what) {
@@ -327,6 +390,18 @@ void launch_reset_counters(const int2* dep_counts, unsigned int* counters, int n
 void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s) {
     if (body_count <= 0) return;
     reset_versions_kernel<<<blocks_for(body_count, 256), 256, 0, s>>>(velocity, body_count);
+}
+void launch_redistribute_impulses(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, cudaStream_t s) {
+    if (work_count <= 0) return;
+    redistribute_impulses_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count);
+}
+void launch_scatter_body_motion(const void* raw, int body_count, const BodyBuffers& B, cudaStream_t s) {
+    if (body_count <= 0) return;
+    scatter_body_motion_kernel<<<blocks_for((size_t)body_count * 4, 256), 256, 0, s>>>((const float4*)raw, body_count, B);
+}
+void launch_gather_body_motion(void* raw, int body_count, const BodyBuffers& B, cudaStream_t s) {
+    if (body_count <= 0) return;
+    gather_body_motion_kernel<<<blocks_for((size_t)body_count * 4, 256), 256, 0, s>>>((float4*)raw, body_count, B);
 }
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
     if (n == 0) return;

@@ -15,12 +15,20 @@ struct TransposeDesc {
     int32_t src_count;    // TypeBatch.ConstraintCount of the source
     int32_t bodies, prestep_rows, impulse_rows;
     int32_t src_bundle_base;  // index of the source type batch's first host-width bundle in the per-bundle flag array
-    int32_t pad;
+    int32_t flags;            // kDescResidentImpulses: the accumulated impulses live on the device (bepucuda_update_contacts), transpose_in skips them
+    const int32_t* features_old;  // contact feature ids the resident impulses belong to / the frame's new ids ([constraint][contact]); null = none
+    const int32_t* features_new;
 };
+constexpr int32_t kDescResidentImpulses = 1, kDescRedistribute = 2;
 enum { kTransposeRefs = 1, kTransposePrestep = 2, kTransposeImpulses = 4 };
 void launch_transpose_in_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s);
 void launch_transpose_out_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s);
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s);
+// RedistributeImpulses (NarrowPhaseConstraintUpdate.cs:L81-135) for every device type batch whose descriptor has kDescRedistribute, on the AOSOA-32 impulses.
+void launch_redistribute_impulses(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, cudaStream_t s);
+// Motion half (floats 0-15) of 128-B BodyDynamics records <-> pose / velocity records. `raw` may be mapped host memory.
+void launch_scatter_body_motion(const void* raw, int body_count, const BodyBuffers& B, cudaStream_t s);
+void launch_gather_body_motion(void* raw, int body_count, const BodyBuffers& B, cudaStream_t s);
 // One chunk (<= 64 KiB, sizes multiple of 4 bytes) of a batched host<->device copy through mapped pinned memory.
 struct CopyChunk {
     void* dst;

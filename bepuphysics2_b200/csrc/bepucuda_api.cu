@@ -128,6 +128,11 @@ struct SourceTypeBatch {
     size_t refs_bytes, prestep_bytes, impulse_bytes;
     std::vector<int32_t> host_refs;  // retained only for fallback batches (levelisation)
     std::vector<int> device_tbs;
+    // device-side contact update (bepucuda_update_contacts): feature ids of the resident impulses / of the frame being uploaded
+    int32_t* raw_features_old = nullptr;
+    int32_t* raw_features_new = nullptr;
+    size_t feature_bytes = 0;
+    bool resident_impulses = false, redistribute = false;
 };
 
 }  // namespace bepucuda
@@ -156,7 +161,7 @@ struct bepucuda_ctx {
     // constraints
     int W = 8;
     int batch_count = 0;
-    bool constraints_open = false, constraints_ready = false, data_dirty = false;
+    bool constraints_open = false, constraints_ready = false, data_dirty = false, descs_dirty = false;
     std::vector<SourceTypeBatch> sources;
     ChunkArena raw_arena, pinned_arena;
     DeviceBuffer chain32, succ32, next_bundle, dep_counts, df_counters, body_counter, record_table, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
@@ -427,6 +432,42 @@ void compute_frame_params(bepucuda_ctx* ctx, float dt, FrameParams* fp) {
     for (int i = 0; i < 4; ++i) fp->tune[i] = ctx->tune[i];
 }
 
+// Brings the device AOSOA-32 rows up to date with what the host queued since the last solve (bepucuda_update_type_batch / bepucuda_update_contacts):
+// flushes the batched copies, re-uploads the transposition descriptors when a type batch switched to resident impulses, transposes, and
+// redistributes the resident penetration impulses of updated contact type batches from the old to the new feature ids.
+int refresh_device_rows(bepucuda_ctx* ctx) {
+    if (!ctx->data_dirty) return BEPUCUDA_OK;
+    { int rc = flush_chunks(ctx, ctx->pending_h2d); if (rc != BEPUCUDA_OK) return rc; }
+    bool any_redistribute = false;
+    if (ctx->descs_dirty) {
+        for (SourceTypeBatch& s : ctx->sources)
+            for (int tb : s.device_tbs) {
+                TransposeDesc& d = ctx->tdescs[tb];
+                d.flags = (s.resident_impulses ? kDescResidentImpulses : 0) | (s.redistribute ? kDescRedistribute : 0);
+                d.features_old = s.raw_features_old;
+                d.features_new = s.raw_features_new;
+                any_redistribute |= s.redistribute;
+            }
+        CK(cudaMemcpyAsync(ctx->tdesc_table.ptr, ctx->tdescs.data(), ctx->tdescs.size() * sizeof(TransposeDesc), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
+                            kTransposePrestep | kTransposeImpulses, ctx->stream);
+    if (any_redistribute) {
+        launch_redistribute_impulses(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->stream);
+        for (SourceTypeBatch& s : ctx->sources)
+            if (s.redistribute) {
+                std::swap(s.raw_features_old, s.raw_features_new);  // the resident impulses now belong to the new ids
+                s.redistribute = false;
+            }
+        // descriptors still carry kDescRedistribute and the pre-swap pointers: they are rewritten by the next update (descs_dirty stays set)
+    } else {
+        ctx->descs_dirty = false;
+    }
+    CK(cudaGetLastError());
+    ctx->data_dirty = false;
+    return BEPUCUDA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -690,7 +731,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
             d.type_id = s.type_id;
             d.bundle_count = (s.count + 31) / 32;
             d.device_batch = (int)batch_tbs.size() - 1;
-            TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows, source_bundle_base[si], 0};
+            TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows, source_bundle_base[si], 0, nullptr, nullptr};
             s.device_tbs.push_back((int)ctx->tbs.size());
             batch_tbs.back().push_back((int)ctx->tbs.size());
             ctx->tbs.push_back(d);
@@ -771,7 +812,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
                     map_offset.push_back(maps.size());
                     for (size_t q = i; q < j; ++q) maps.push_back(slots[q].constraint);
                     for (int q = n; q < d.bundle_count * 32; ++q) maps.push_back(-1);
-                    TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows, source_bundle_base[source], 0};
+                    TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows, source_bundle_base[source], 0, nullptr, nullptr};
                     s.device_tbs.push_back((int)ctx->tbs.size());
                     batch_tbs.back().push_back((int)ctx->tbs.size());
                     ctx->tbs.push_back(d);
@@ -954,10 +995,100 @@ int32_t bepucuda_update_type_batch(bepucuda_ctx* ctx, int32_t batch_index, int32
             }
             ctx->h2d_accum += (int64_t)(s.prestep_bytes + s.impulse_bytes);
             s.host_impulses = accumulated_impulses;
+            if (s.resident_impulses) { s.resident_impulses = false; s.redistribute = false; ctx->descs_dirty = true; }  // the host took the impulses back
             ctx->data_dirty = true;
             return BEPUCUDA_OK;
         }
     return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "update_type_batch: unknown type batch");
+}
+
+static int contact_count_of_type(int type_id) {
+    if (type_id >= 0 && type_id <= 7) return (type_id & 3) + 1;
+    if (type_id >= 8 && type_id <= 10) return type_id - 6;
+    if (type_id >= 15 && type_id <= 17) return type_id - 13;
+    return 0;
+}
+static SourceTypeBatch* find_source(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index) {
+    for (auto& s : ctx->sources)
+        if (s.batch_index == batch_index && s.type_batch_index == type_batch_index) return &s;
+    return nullptr;
+}
+static int ensure_feature_arrays(bepucuda_ctx* ctx, SourceTypeBatch& s) {
+    if (s.raw_features_old) return BEPUCUDA_OK;
+    s.feature_bytes = (size_t)s.count * contact_count_of_type(s.type_id) * sizeof(int32_t);
+    cudaError_t e = cudaSuccess;
+    s.raw_features_old = (int32_t*)ctx->raw_arena.alloc(s.feature_bytes, &e);
+    s.raw_features_new = (int32_t*)ctx->raw_arena.alloc(s.feature_bytes, &e);
+    if (!s.raw_features_old || !s.raw_features_new) return cuda_fail(ctx, e, "raw arena (contact feature ids)");
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_set_contact_features(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index, const int32_t* feature_ids) {
+    if (!ctx || !feature_ids) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_contact_features: bad arguments");
+    if (!ctx->constraints_open && !ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "set_contact_features before the type batch was uploaded");
+    SourceTypeBatch* s = find_source(ctx, batch_index, type_batch_index);
+    if (!s) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_contact_features: unknown type batch");
+    if (contact_count_of_type(s->type_id) == 0) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "set_contact_features: not a contact constraint type");
+    CK(cudaSetDevice(ctx->device));
+    { int rc = ensure_feature_arrays(ctx, *s); if (rc != BEPUCUDA_OK) return rc; }
+    return copy_in(ctx, s->raw_features_old, feature_ids, s->feature_bytes);
+}
+
+int32_t bepucuda_update_contacts(bepucuda_ctx* ctx, int32_t batch_index, int32_t type_batch_index, const float* prestep, const int32_t* new_feature_ids) {
+    if (!ctx || !prestep || !new_feature_ids) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "update_contacts: bad arguments");
+    if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "update_contacts before end_constraints");
+    SourceTypeBatch* s = find_source(ctx, batch_index, type_batch_index);
+    if (!s) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "update_contacts: unknown type batch");
+    if (!s->raw_features_old) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "update_contacts: bepucuda_set_contact_features was never called for this type batch");
+    if (s->redistribute) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "update_contacts: called twice for the same type batch without a solve in between");
+    CK(cudaSetDevice(ctx->device));
+    open_upload_window(ctx);
+    int rc;
+    if ((rc = copy_in(ctx, s->raw_prestep, prestep, s->prestep_bytes)) != BEPUCUDA_OK) return rc;
+    if ((rc = copy_in(ctx, s->raw_features_new, new_feature_ids, s->feature_bytes)) != BEPUCUDA_OK) return rc;
+    s->resident_impulses = true;
+    s->redistribute = true;
+    ctx->descs_dirty = true;
+    ctx->data_dirty = true;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_upload_body_motion(bepucuda_ctx* ctx, const void* body_dynamics, int32_t body_count) {
+    if (!ctx || !body_dynamics || body_count != ctx->body_count) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "upload_body_motion: bad arguments (the body count must match the last upload_bodies)");
+    if (body_count == 0) return BEPUCUDA_OK;
+    CK(cudaSetDevice(ctx->device));
+    open_upload_window(ctx);
+    const size_t n = (size_t)body_count;
+    if (char* alias = map_host(ctx, body_dynamics, n * 128)) {
+        launch_scatter_body_motion(alias, body_count, ctx->B, ctx->stream);  // 64 of every 128 bytes read straight from the mapped host buffer
+    } else {
+        CK(cudaMemcpy2DAsync(ctx->raw_bodies.ptr, 128, body_dynamics, 128, 64, n, cudaMemcpyHostToDevice, ctx->stream));
+        launch_scatter_body_motion(ctx->raw_bodies.ptr, body_count, ctx->B, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    ctx->h2d_accum += (int64_t)n * 64;
+    ctx->pass_counter = 0;  // the velocity padding words (dataflow versions) were zeroed
+    ctx->versions_dirty = false;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_download_body_motion(bepucuda_ctx* ctx, void* out, int32_t body_count) {
+    if (!ctx || !out || body_count < 0 || body_count > ctx->body_count) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "download_body_motion: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_down_begin, ctx->stream));
+    const size_t n = (size_t)body_count;
+    if (char* alias = map_host(ctx, out, n * 128)) {
+        launch_gather_body_motion(alias, body_count, ctx->B, ctx->stream);
+    } else {
+        launch_gather_body_motion(ctx->raw_bodies.ptr, body_count, ctx->B, ctx->stream);
+        CK(cudaMemcpy2DAsync(out, 128, ctx->raw_bodies.ptr, 128, 64, n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_down_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_down = true;
+    ctx->timings.d2h_bytes = (int64_t)n * 64;
+    return BEPUCUDA_OK;
 }
 
 int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
@@ -971,12 +1102,7 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
         if (rc == BEPUCUDA_OK) rc = bepucuda_end_constraints(ctx);
         if (rc != BEPUCUDA_OK) return rc;
     }
-    if (ctx->data_dirty) {
-        { int rc = flush_chunks(ctx, ctx->pending_h2d); if (rc != BEPUCUDA_OK) return rc; }
-        launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
-                                kTransposePrestep | kTransposeImpulses, ctx->stream);
-        ctx->data_dirty = false;
-    }
+    { int rc = refresh_device_rows(ctx); if (rc != BEPUCUDA_OK) return rc; }
     if (ctx->up_open) {
         cudaEventRecord(ctx->ev_up_end, ctx->stream);
         ctx->up_open = false;
@@ -1172,12 +1298,7 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages: not available in dataflow mode (no per-stage launches)");
     CK(cudaSetDevice(ctx->device));
     std::memset(out, 0, sizeof(*out));
-    if (ctx->data_dirty) {
-        { int rc = flush_chunks(ctx, ctx->pending_h2d); if (rc != BEPUCUDA_OK) return rc; }  // refreshed rows may still be queued (bepucuda_update_type_batch)
-        launch_transpose_in_all(ctx->tb_table.as<DeviceTypeBatch>(), ctx->tdesc_table.as<TransposeDesc>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->W,
-                                kTransposePrestep | kTransposeImpulses, ctx->stream);
-        ctx->data_dirty = false;
-    }
+    { int rc = refresh_device_rows(ctx); if (rc != BEPUCUDA_OK) return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
     compute_frame_params(ctx, dt, ctx->frame_params_host);
     CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));

@@ -95,6 +95,7 @@ C_ABI_SYMBOLS = [
     "bepucuda_set_constrained_kinematics", "bepucuda_end_constraints", "bepucuda_update_type_batch", "bepucuda_solve", "bepucuda_synchronize",
     "bepucuda_download_bodies", "bepucuda_download_impulses", "bepucuda_download_prestep", "bepucuda_get_timings", "bepucuda_set_boundary_bodies",
     "bepucuda_event_record", "bepucuda_event_elapsed_ms", "bepucuda_profile_stages",
+    "bepucuda_set_contact_features", "bepucuda_update_contacts", "bepucuda_upload_body_motion", "bepucuda_download_body_motion",
 ]
 
 
@@ -132,6 +133,10 @@ def load_libraries():
     cuda.bepucuda_set_constrained_kinematics.argtypes = [vp, vp, i32]
     cuda.bepucuda_end_constraints.argtypes = [vp]
     cuda.bepucuda_update_type_batch.argtypes = [vp, i32, i32, vp, vp]
+    cuda.bepucuda_set_contact_features.argtypes = [vp, i32, i32, vp]
+    cuda.bepucuda_update_contacts.argtypes = [vp, i32, i32, vp, vp]
+    cuda.bepucuda_upload_body_motion.argtypes = [vp, vp, i32]
+    cuda.bepucuda_download_body_motion.argtypes = [vp, vp, i32]
     cuda.bepucuda_download_bodies.argtypes = [vp, vp, i32]
     cuda.bepucuda_download_impulses.argtypes = [vp]
     cuda.bepucuda_download_prestep.argtypes = [vp, i32, i32, vp]
@@ -361,6 +366,31 @@ class CudaTimestepper:
 
     def solve(self, dt, download=True):
         self._check(self._host.bepuhost_cuda_solve(self.sim._sim, self._ctx, dt, 1 if download else 0))
+
+    # ---- device-side contact update (first slice): accumulated impulses stay on the device between frames --------------------
+    def set_contact_features(self, features):
+        """features: {(batch_index, type_batch_index): int32[constraints, contacts]} = the feature ids the uploaded impulses belong to."""
+        for (b, t), ids in features.items():
+            ids = np.ascontiguousarray(ids, dtype=np.int32)
+            self._check(self._cuda.bepucuda_set_contact_features(self._ctx, b, t, ids.ctypes.data))
+
+    def update_contacts(self, features):
+        """Per frame, same topology: the host's new prestep data + the new feature ids of every contact type batch; impulses are redistributed on the
+        device (NarrowPhaseConstraintUpdate.cs:L81-135). Type batches not named in `features` keep their device rows."""
+        by_key = {(tb.batch_index, tb.type_batch_index): tb for tb in self.sim.type_batches()}
+        for (b, t), ids in features.items():
+            ids = np.ascontiguousarray(ids, dtype=np.int32)
+            self._check(self._cuda.bepucuda_update_contacts(self._ctx, b, t, by_key[(b, t)].prestep.ctypes.data, ids.ctypes.data))
+
+    def upload_body_motion(self):
+        """Pose + velocity halves of every BodyDynamics record only (64 of 128 bytes per body)."""
+        self._check(self._cuda.bepucuda_upload_body_motion(self._ctx, self.sim.bodies.ctypes.data, self.sim.body_count))
+
+    def download_body_motion(self):
+        self._check(self._cuda.bepucuda_download_body_motion(self._ctx, self.sim.bodies.ctypes.data, self.sim.body_count))
+
+    def download_impulses(self):
+        self._check(self._cuda.bepucuda_download_impulses(self._ctx))
 
     def synchronize(self):
         self._check(self._cuda.bepucuda_synchronize(self._ctx))

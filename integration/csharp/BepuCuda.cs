@@ -52,6 +52,10 @@ namespace BepuCuda
         [DllImport(Lib)] public static extern int bepucuda_set_constrained_kinematics(IntPtr ctx, int* bodyIndices, int count);
         [DllImport(Lib)] public static extern int bepucuda_end_constraints(IntPtr ctx);
         [DllImport(Lib)] public static extern int bepucuda_update_type_batch(IntPtr ctx, int batchIndex, int typeBatchIndex, void* prestep, void* accumulatedImpulses);
+        [DllImport(Lib)] public static extern int bepucuda_set_contact_features(IntPtr ctx, int batchIndex, int typeBatchIndex, int* featureIds);
+        [DllImport(Lib)] public static extern int bepucuda_update_contacts(IntPtr ctx, int batchIndex, int typeBatchIndex, void* prestep, int* newFeatureIds);
+        [DllImport(Lib)] public static extern int bepucuda_upload_body_motion(IntPtr ctx, void* bodyDynamics, int bodyCount);
+        [DllImport(Lib)] public static extern int bepucuda_download_body_motion(IntPtr ctx, void* bodyDynamicsOut, int bodyCount);
         [DllImport(Lib)] public static extern int bepucuda_solve(IntPtr ctx, float dt);
         [DllImport(Lib)] public static extern int bepucuda_synchronize(IntPtr ctx);
         [DllImport(Lib)] public static extern int bepucuda_download_bodies(IntPtr ctx, void* bodyDynamicsOut, int bodyCount);

@@ -825,6 +825,52 @@ extern "C" int32_t oracle_eval_integration(int32_t op, const float* in, float* o
     return 0;
 }
 
+// ---- narrow-phase impulse carry-over for a contact constraint whose type did not change ---------------------------------------------------------
+// NarrowPhase.RedistributeImpulses, CollisionDetection/NarrowPhaseConstraintUpdate.cs:L81-135.
+extern "C" void oracle_redistribute_impulses(int32_t oldContactCount, const int32_t* oldFeatureIds, float* oldImpulses, int32_t newContactCount, const int32_t* newFeatureIds,
+                                             float* newImpulses) {
+    int unmatchedCount = 0;
+    for (int i = 0; i < newContactCount; ++i) {
+        newImpulses[i] = -1;  // accumulated impulses cannot be negative: a negative value flags 'unmatched' (L92-93)
+        for (int j = 0; j < oldContactCount; ++j) {
+            if (oldFeatureIds[j] == newFeatureIds[i]) {
+                newImpulses[i] = oldImpulses[j];
+                oldImpulses[j] = 0;  // will not be distributed to the unmatched contacts (L98-100)
+                break;
+            }
+        }
+        if (newImpulses[i] < 0) ++unmatchedCount;
+    }
+    if (unmatchedCount > 0) {  // L110-131: the remaining impulse is shared evenly by the unmatched contacts
+        float unmatchedImpulse = 0;
+        for (int i = 0; i < oldContactCount; ++i) unmatchedImpulse += oldImpulses[i];
+        float impulsePerUnmatched = unmatchedImpulse / unmatchedCount;
+        for (int i = 0; i < newContactCount; ++i)
+            if (newImpulses[i] < 0) newImpulses[i] = impulsePerUnmatched;
+    }
+}
+// UpdateConstraint, same-type branch (L147-183), for a whole type batch in the reference AOSOA-W layout: GatherOldImpulses / ScatterNewImpulses
+// address the penetration rows of the accumulated impulses (ContactConstraintAccessor.cs:L36-78: after the Vector2Wide tangent for convex types,
+// NonconvexAccumulatedImpulses.Penetration of contact i otherwise).
+extern "C" int32_t oracle_update_contact_impulses(int32_t type_id, int32_t constraint_count, int32_t W, float* accumulated_impulses, const int32_t* old_feature_ids,
+                                                  const int32_t* new_feature_ids) {
+    const bool convex = type_id >= 0 && type_id <= 7;
+    int n;
+    if (convex) n = (type_id & 3) + 1;
+    else if (type_id >= 8 && type_id <= 10) n = type_id - 6;
+    else if (type_id >= 15 && type_id <= 17) n = type_id - 13;
+    else return -1;
+    const int rows = convex ? n + 3 : 3 * n;
+    for (int c = 0; c < constraint_count; ++c) {
+        float* bundle = accumulated_impulses + (size_t)(c / W) * rows * W + (c % W);
+        float oldImpulses[8], newImpulses[8];
+        for (int i = 0; i < n; ++i) oldImpulses[i] = bundle[(convex ? 2 + i : 3 * i + 2) * W];
+        oracle_redistribute_impulses(n, old_feature_ids + (size_t)c * n, oldImpulses, n, new_feature_ids + (size_t)c * n, newImpulses);
+        for (int i = 0; i < n; ++i) bundle[(convex ? 2 + i : 3 * i + 2) * W] = newImpulses[i];
+    }
+    return 0;
+}
+
 extern "C" int32_t oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -51,6 +51,10 @@ int32_t oracle_type_info(int32_t type_id, int32_t* bodies, int32_t* prestep_floa
 /* Single bundle entry points for unit tests: evaluate WarmStart / Solve of `type_id` on `lanes` constraints laid out as
  * one AOSOA bundle of width `lanes`; body state given per slot as SoA-free arrays of 32-float AOS records. */
 int32_t oracle_max_threads(void);
+/* NarrowPhase.RedistributeImpulses (NarrowPhaseConstraintUpdate.cs:L81-135) and its application to a whole contact type batch (same-type update). */
+void oracle_redistribute_impulses(int32_t old_count, const int32_t* old_ids, float* old_impulses, int32_t new_count, const int32_t* new_ids, float* new_impulses);
+int32_t oracle_update_contact_impulses(int32_t type_id, int32_t constraint_count, int32_t bundle_width, float* accumulated_impulses, const int32_t* old_feature_ids,
+                                       const int32_t* new_feature_ids);
 
 #ifdef __cplusplus
 }

@@ -109,3 +109,15 @@ def solve(simulation, dt, threads=1, simd=False):
     rc = lib.oracle_solve(C.byref(sc), dt)
     if rc != 0:
         raise RuntimeError("oracle_solve failed: %d" % rc)
+
+
+def update_contact_impulses(type_batch, old_feature_ids, new_feature_ids):
+    """NarrowPhase.UpdateConstraint, same-type branch, on a host type batch's accumulated impulses in place (NarrowPhaseConstraintUpdate.cs:L81-183)."""
+    lib = load()
+    lib.oracle_update_contact_impulses.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    old = np.ascontiguousarray(old_feature_ids, dtype=np.int32)
+    new = np.ascontiguousarray(new_feature_ids, dtype=np.int32)
+    rc = lib.oracle_update_contact_impulses(type_batch.type_id, type_batch.constraint_count, type_batch.accumulated_impulses.shape[2], type_batch.accumulated_impulses.ctypes.data,
+                                            old.ctypes.data, new.ctypes.data)
+    if rc != 0:
+        raise ValueError("not a contact constraint type: %d" % type_batch.type_id)

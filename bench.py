@@ -396,7 +396,14 @@ def main():
     if rank == 0 and args.scene == "shape_pile":
         frng = np.random.default_rng(11)
         count = lambda tid: (tid & 3) + 1 if tid <= 7 else (tid - 6 if tid <= 10 else tid - 13)
-        feats = {(tb.batch_index, tb.type_batch_index): frng.integers(0, 1 << 20, size=(tb.constraint_count, count(tb.type_id)), dtype=np.int32) for tb in sim.type_batches() if tb.type_id <= 17}
+        contact_tbs = [tb for tb in sim.type_batches() if tb.type_id <= 17]
+        pool = frng.integers(0, 1 << 20, size=sum(tb.constraint_count * count(tb.type_id) for tb in contact_tbs), dtype=np.int32)  # one pinned block, like a BufferPool
+        feats, at = {}, 0
+        for tb in contact_tbs:
+            n = tb.constraint_count * count(tb.type_id)
+            feats[(tb.batch_index, tb.type_batch_index)] = pool[at:at + n].reshape(tb.constraint_count, count(tb.type_id))
+            at += n
+        ts.register_array(pool)
         ts.describe()
         ts.set_contact_features(feats)
         for _ in range(2):

@@ -1043,9 +1043,16 @@ int32_t bepucuda_update_contacts(bepucuda_ctx* ctx, int32_t batch_index, int32_t
     if (s->redistribute) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "update_contacts: called twice for the same type batch without a solve in between");
     CK(cudaSetDevice(ctx->device));
     open_upload_window(ctx);
-    int rc;
-    if ((rc = copy_in(ctx, s->raw_prestep, prestep, s->prestep_bytes)) != BEPUCUDA_OK) return rc;
-    if ((rc = copy_in(ctx, s->raw_features_new, new_feature_ids, s->feature_bytes)) != BEPUCUDA_OK) return rc;
+    // per-frame path: mapped (registered) host buffers go through the batched zero-copy kernel, anything else is copied directly -- never through the
+    // pinned staging arena, which is only recycled by bepucuda_begin_constraints
+    const void* srcs[2] = {prestep, new_feature_ids};
+    void* dsts[2] = {s->raw_prestep, s->raw_features_new};
+    const size_t sizes[2] = {s->prestep_bytes, s->feature_bytes};
+    for (int i = 0; i < 2; ++i) {
+        if (char* alias = map_host(ctx, srcs[i], sizes[i])) queue_chunks(ctx->pending_h2d, dsts[i], alias, sizes[i]);
+        else CK(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_accum += (int64_t)sizes[i];
+    }
     s->resident_impulses = true;
     s->redistribute = true;
     ctx->descs_dirty = true;

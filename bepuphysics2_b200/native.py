@@ -368,6 +368,10 @@ class CudaTimestepper:
         self._check(self._host.bepuhost_cuda_solve(self.sim._sim, self._ctx, dt, 1 if download else 0))
 
     # ---- device-side contact update (first slice): accumulated impulses stay on the device between frames --------------------
+    def register_array(self, array):
+        """Page-locks + maps a host array the per-frame calls read from (contact feature ids), like register_host_buffers does for the simulation's."""
+        self._check(self._cuda.bepucuda_host_register(self._ctx, array.ctypes.data, array.nbytes))
+
     def set_contact_features(self, features):
         """features: {(batch_index, type_batch_index): int32[constraints, contacts]} = the feature ids the uploaded impulses belong to."""
         for (b, t), ids in features.items():

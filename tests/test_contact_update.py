@@ -68,8 +68,8 @@ def _narrow_phase_like_update(sim, features, rng):
         new[key] = ids
         # depth rows: convex prestep rows 4 i + 3; nonconvex contact i = rows 7 i .. 7 i + 6 with the depth at + 3 (Offset xyz, Depth, Normal xyz)
         rows = [4 * i + 3 for i in range(n)] if tb.type_id <= 7 else [7 * i + 3 for i in range(n)]
-        for r in rows:
-            tb.prestep[:, r, :] += rng.uniform(-0.01, 0.01, size=tb.prestep[:, r, :].shape).astype(np.float32)
+        for r in rows:  # the narrow phase writes fresh depths every frame (whatever the solver's incremental updates left in the row)
+            tb.prestep[:, r, :] = rng.uniform(-0.02, 0.05, size=tb.prestep[:, r, :].shape).astype(np.float32)
     return new
 
 

@@ -394,29 +394,19 @@ def main():
     # ---- reads back the motion half of the bodies only
     resident = None
     if rank == 0 and args.scene == "shape_pile":
-        frng = np.random.default_rng(11)
-        count = lambda tid: (tid & 3) + 1 if tid <= 7 else (tid - 6 if tid <= 10 else tid - 13)
-        contact_tbs = [tb for tb in sim.type_batches() if tb.type_id <= 17]
-        pool = frng.integers(0, 1 << 20, size=sum(tb.constraint_count * count(tb.type_id) for tb in contact_tbs), dtype=np.int32)  # one pinned block, like a BufferPool
-        feats, at = {}, 0
-        for tb in contact_tbs:
-            n = tb.constraint_count * count(tb.type_id)
-            feats[(tb.batch_index, tb.type_batch_index)] = pool[at:at + n].reshape(tb.constraint_count, count(tb.type_id))
-            at += n
+        pool, _ = ts.contact_feature_pool(np.random.default_rng(11))  # one pinned block, like a BufferPool
         ts.register_array(pool)
         ts.describe()
-        ts.set_contact_features(feats)
+        ts.set_contact_feature_pool(pool)
         for _ in range(2):
-            ts.upload_body_motion()
-            ts.update_contacts(feats)
+            ts.update_contacts_from_pool(pool)
             ts.solve_device_only(DT)
             ts.download_body_motion()
         ts.synchronize()
         r_steps = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(r_steps):
-            ts.upload_body_motion()
-            ts.update_contacts(feats)
+            ts.update_contacts_from_pool(pool)
             ts.solve_device_only(DT)
             ts.download_body_motion()
         ts.synchronize()

@@ -169,6 +169,7 @@ def load_libraries():
     host.bepuhost_substep_count.argtypes = [vp]
     host.bepuhost_velocity_iterations.argtypes = [vp]
     host.bepuhost_velocity_iterations.restype = C.POINTER(i32)
+    host.bepuhost_cuda_update_contacts.argtypes = [vp, vp, vp, i32]
     for name in ("bepuhost_cuda_describe", "bepuhost_cuda_refresh", "bepuhost_cuda_download_prestep", "bepuhost_cuda_register_buffers", "bepuhost_cuda_unregister_buffers"):
         getattr(host, name).argtypes = [vp, vp]
     host.bepuhost_cuda_solve.argtypes = [vp, vp, f32, i32]
@@ -315,6 +316,9 @@ class CudaTimestepper:
 
     def close(self):
         if getattr(self, "_ctx", None):
+            for array in getattr(self, "_arrays", []):
+                self._cuda.bepucuda_host_unregister(self._ctx, array.ctypes.data)
+            self._arrays = []
             if self._registered:
                 self._host.bepuhost_cuda_unregister_buffers(self.sim._sim, self._ctx)
             self._cuda.bepucuda_destroy(self._ctx)
@@ -369,8 +373,32 @@ class CudaTimestepper:
 
     # ---- device-side contact update (first slice): accumulated impulses stay on the device between frames --------------------
     def register_array(self, array):
-        """Page-locks + maps a host array the per-frame calls read from (contact feature ids), like register_host_buffers does for the simulation's."""
+        """Page-locks + maps a host array the per-frame calls read from (contact feature ids), like register_host_buffers does for the simulation's.
+        The array is kept alive until close()."""
         self._check(self._cuda.bepucuda_host_register(self._ctx, array.ctypes.data, array.nbytes))
+        self._arrays = getattr(self, "_arrays", []) + [array]
+
+    def contact_feature_pool(self, rng=None):
+        """One int32 block with the feature ids of every contact type batch back to back in (batch, type batch) order (the layout
+        bepuhost_cuda_update_contacts walks), plus {(batch, type batch): view}. Filled with random ids when an rng is given."""
+        count = lambda tid: (tid & 3) + 1 if tid <= 7 else (tid - 6 if tid <= 10 else tid - 13)
+        tbs = [tb for tb in self.sim.type_batches() if tb.type_id <= 17]
+        pool = np.zeros(max(1, sum(tb.constraint_count * count(tb.type_id) for tb in tbs)), dtype=np.int32)
+        if rng is not None:
+            pool[:] = rng.integers(0, 1 << 20, size=pool.size, dtype=np.int32)
+        views, at = {}, 0
+        for tb in tbs:
+            n = tb.constraint_count * count(tb.type_id)
+            views[(tb.batch_index, tb.type_batch_index)] = pool[at:at + n].reshape(tb.constraint_count, count(tb.type_id))
+            at += n
+        return pool, views
+
+    def set_contact_feature_pool(self, pool):
+        self._check(self._host.bepuhost_cuda_update_contacts(self.sim._sim, self._ctx, pool.ctypes.data, 1))
+
+    def update_contacts_from_pool(self, pool):
+        """The whole per-frame refresh of the resident path in one native call: body motion + prestep + feature ids of every contact type batch."""
+        self._check(self._host.bepuhost_cuda_update_contacts(self.sim._sim, self._ctx, pool.ctypes.data, 0))
 
     def set_contact_features(self, features):
         """features: {(batch_index, type_batch_index): int32[constraints, contacts]} = the feature ids the uploaded impulses belong to."""

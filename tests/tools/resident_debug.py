@@ -49,6 +49,9 @@ for frame in range(4):
     ob.solve(host, DT)
     ts.solve_device_only(DT)
     ts.download_body_motion()
+    if "--timings" in sys.argv:
+        t = ts.timings()
+        print("d2h", t.d2h_bytes, "h2d", t.h2d_bytes, "solve_ms %.3f" % t.solve_ms)
     bodies_equal("frame %d" % frame)
     if "--downloads" in sys.argv:
         ts.download_impulses(); ts.download_prestep()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call 11: device-side contact update (resident impulses) parity + e2e; default bench.
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_contact_update.py -m gpu -x -q 2>&1 | grep -E "frame|passed|failed" | head -5; timeout 300 python tests/tools/resident_debug.py; timeout 300 python tests/tools/resident_debug.py --downloads; true) > gpurun_out/r2c11_tests.log 2>&1
+(timeout 900 python -m pytest tests/test_contact_update.py -m gpu -x -q 2>&1 | grep -E "AssertionError|passed|failed" | head -5; timeout 300 python tests/tools/resident_debug.py; timeout 300 python tests/tools/resident_debug.py --timings; true) > gpurun_out/r2c11_tests.log 2>&1
 
 cat gpurun_out/r2c11_tests.log
 true "

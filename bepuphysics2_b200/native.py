@@ -418,6 +418,10 @@ class CudaTimestepper:
         """Pose + velocity halves of every BodyDynamics record only (64 of 128 bytes per body)."""
         self._check(self._cuda.bepucuda_upload_body_motion(self._ctx, self.sim.bodies.ctypes.data, self.sim.body_count))
 
+    def download_bodies(self):
+        """Full 128-B records: pose, velocity and world inertia."""
+        self._check(self._cuda.bepucuda_download_bodies(self._ctx, self.sim.bodies.ctypes.data, self.sim.body_count))
+
     def download_body_motion(self):
         self._check(self._cuda.bepucuda_download_body_motion(self._ctx, self.sim.bodies.ctypes.data, self.sim.body_count))
 

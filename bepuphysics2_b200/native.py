@@ -375,7 +375,8 @@ class CudaTimestepper:
     def register_array(self, array):
         """Page-locks + maps a host array the per-frame calls read from (contact feature ids), like register_host_buffers does for the simulation's.
         The array is kept alive until close()."""
-        self._check(self._cuda.bepucuda_host_register(self._ctx, array.ctypes.data, array.nbytes))
+        nbytes = array.nbytes if array.ctypes.data % 4096 else ((array.nbytes + 4095) // 4096) * 4096  # page-aligned blocks are registered in whole pages
+        self._check(self._cuda.bepucuda_host_register(self._ctx, array.ctypes.data, nbytes))
         self._arrays = getattr(self, "_arrays", []) + [array]
 
     def contact_feature_pool(self, rng=None):
@@ -383,7 +384,10 @@ class CudaTimestepper:
         bepuhost_cuda_update_contacts walks), plus {(batch, type batch): view}. Filled with random ids when an rng is given."""
         count = lambda tid: (tid & 3) + 1 if tid <= 7 else (tid - 6 if tid <= 10 else tid - 13)
         tbs = [tb for tb in self.sim.type_batches() if tb.type_id <= 17]
-        pool = np.zeros(max(1, sum(tb.constraint_count * count(tb.type_id) for tb in tbs)), dtype=np.int32)
+        total = max(1, sum(tb.constraint_count * count(tb.type_id) for tb in tbs))
+        backing = np.zeros(total + 2048, dtype=np.int32)  # page-aligned start and a whole number of pages, like a pinned pool block
+        skip = (-backing.ctypes.data % 4096) // 4
+        pool = backing[skip:skip + ((total + 1023) // 1024) * 1024][:total]
         if rng is not None:
             pool[:] = rng.integers(0, 1 << 20, size=pool.size, dtype=np.int32)
         views, at = {}, 0

@@ -66,8 +66,10 @@ def _narrow_phase_like_update(sim, features, rng):
         if n > 1:
             ids[swap] = ids[swap][:, ::-1]
         new[key] = ids
-        # depth rows: convex prestep rows 4 i + 3; nonconvex contact i = rows 7 i .. 7 i + 6 with the depth at + 3 (Offset xyz, Depth, Normal xyz)
-        rows = [4 * i + 3 for i in range(n)] if tb.type_id <= 7 else [7 * i + 3 for i in range(n)]
+        # depth rows: convex prestep rows 4 i + 3; nonconvex: after MaterialProperties (4 rows) [+ OffsetB (3 rows) for two bodies], contact i = 7 rows
+        # (Offset xyz, Depth, Normal xyz) with the depth at + 3 (tests/golden/type_layouts.json)
+        base = 4 if tb.type_id <= 10 else 7
+        rows = [4 * i + 3 for i in range(n)] if tb.type_id <= 7 else [base + 7 * i + 3 for i in range(n)]
         for r in rows:  # the narrow phase writes fresh depths every frame (whatever the solver's incremental updates left in the row)
             tb.prestep[:, r, :] = rng.uniform(-0.02, 0.05, size=tb.prestep[:, r, :].shape).astype(np.float32)
     return new

@@ -62,6 +62,7 @@ struct FrameParams {
     int32_t angular_mode;
     int32_t integrate_velocity_for_kinematics;
     uint32_t pass_base;        // dataflow mode: number of WarmStart/Solve passes executed since the body versions were last reset
+    uint32_t exchange_base;    // peer sharding: number of cross-GPU exchange points executed before this solve (the flag barrier counts them)
     int32_t tune[4];           // development knobs (env BEPUCUDA_TUNE=a,b,c,d; 0 = built-in default), never set in production
 };
 
@@ -115,6 +116,18 @@ struct DataflowTables {
     const int2* dep_counts;     // per bundle: x = (lane, dynamic body) dependencies per pass, y = those that are the first constraint on their body
     unsigned int* counters;     // per bundle: y + notifications received in the current pass (reset to y by the consumer)
 };
+
+// Peer sharding (bepucuda_shard_*): where the other ranks' body arrays and flag blocks are mapped in this process.
+constexpr int kMaxShardRanks = 8;
+struct ShardPeers {
+    float4* pose[kMaxShardRanks];
+    float4* velocity[kMaxShardRanks];
+    float4* inertia_world[kMaxShardRanks];
+    unsigned long long* flags[kMaxShardRanks];  // flags[r][w]: rank r's block, slot written by rank w
+    int32_t rank, rank_count;
+};
+// One entry per (body written by this rank in a batch, destination rank): packed as body | rank << 28 | owner << 31.
+constexpr uint32_t kPushOwnerBit = 1u << 31;
 
 struct TypeInfo {
     int32_t bodies, prestep_rows, impulse_rows, incremental;

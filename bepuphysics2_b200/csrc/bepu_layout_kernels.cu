@@ -403,6 +403,43 @@ void launch_gather_body_motion(void* raw, int body_count, const BodyBuffers& B, 
     if (body_count <= 0) return;
     gather_body_motion_kernel<<<blocks_for((size_t)body_count * 4, 256), 256, 0, s>>>((float4*)raw, body_count, B);
 }
+// ---- peer sharding ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_record(float4* dst, const float4* src, size_t body) {
+    const float4 a = src[2 * body], b = src[2 * body + 1];
+    dst[2 * body] = a;
+    dst[2 * body + 1] = b;
+}
+__global__ void __launch_bounds__(1024, 1)
+shard_exchange_kernel(const uint32_t* __restrict__ pushes, int push_count, int what, BodyBuffers B, ShardPeers peers, const FrameParams* __restrict__ fpp, uint32_t exchange_index,
+                      int32_t* error_flag) {
+    for (int i = threadIdx.x; i < push_count; i += blockDim.x) {
+        const uint32_t e = pushes[i];
+        const size_t body = e & 0x0FFFFFFFu;
+        const int dst = (int)((e >> 28) & 7u);
+        copy_record(peers.velocity[dst], B.velocity, body);
+        if ((e & kPushOwnerBit) && what > 1) {
+            copy_record(peers.inertia_world[dst], B.inertia_world, body);
+            if (what == 3) copy_record(peers.pose[dst], B.pose, body);
+        }
+    }
+    __threadfence_system();  // every thread's peer stores before the signal below
+    __syncthreads();
+    const unsigned long long seq = (unsigned long long)fpp->exchange_base + exchange_index + 1ull;
+    const int p = threadIdx.x;
+    if (p < peers.rank_count && p != peers.rank) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[p] + peers.rank), "l"(seq) : "memory");
+        unsigned long long seen;
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(peers.flags[peers.rank] + p) : "memory");
+        } while (seen < seq && ++spins < 200000000u);
+        if (seen < seq) atomicExch(error_flag, 5);  // a peer never arrived: results are void
+    }
+}
+void launch_shard_exchange(const uint32_t* pushes, int push_count, int what, const BodyBuffers& B, const ShardPeers& peers, const FrameParams* fp, uint32_t exchange_index,
+                           int32_t* error_flag, cudaStream_t s) {
+    shard_exchange_kernel<<<1, 1024, 0, s>>>(pushes, push_count, what, B, peers, fp, exchange_index, error_flag);
+}
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
     if (n == 0) return;
     fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, v);

@@ -59,6 +59,12 @@ void launch_apply_stage(const int32_t* staging, int planes, const BodyBuffers& B
 void launch_widen_u8(const uint8_t* in, int32_t* out, size_t n, cudaStream_t s);
 void launch_narrow_i32(const int32_t* in, uint8_t* out, size_t n, cudaStream_t s);
 
+// Peer sharding: one CTA copies the records this rank's stage wrote for shared bodies into the destination ranks' arrays, then signals every peer
+// and waits for every peer's signal of the same exchange point (flag barrier in peer memory). what: 1 = velocity only (Solve),
+// 3 = + pose and world inertia of integrating entries (WarmStart), 2 = + world inertia only (first substep: poses are not integrated).
+void launch_shard_exchange(const uint32_t* pushes, int push_count, int what, const BodyBuffers& B, const ShardPeers& peers, const FrameParams* fp, uint32_t exchange_index,
+                           int32_t* error_flag, cudaStream_t s);
+
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
 constexpr int kLaunchPdl = 1, kLaunchPrefetchRows = 2;
 struct SolverLaunchers {

@@ -175,6 +175,17 @@ struct bepucuda_ctx {
     bepucuda_exchange_fn exchange = nullptr;    // sharded batches (bepucuda_set_boundary_bodies): all-reduce callback, its user pointer, staging planes
     void* exchange_user = nullptr;
     DeviceBuffer exchange_staging;
+    // peer sharding (bepucuda_shard_*): one constraint graph over several GPUs with NVLink peer stores and a flag barrier per stage
+    bool peer_mode = false;
+    ShardPeers peers{};
+    DeviceBuffer shard_flags, pushes_dev;
+    std::vector<void*> opened_ipc;
+    std::vector<int32_t> global_first_batch;
+    std::vector<uint8_t> global_constrained;
+    std::map<int, std::vector<uint32_t>> pushes_by_batch;          // host batch index -> packed (body | rank << 28 | owner << 31)
+    std::vector<std::pair<size_t, int>> push_range;                // per device batch: (offset, count) into pushes_dev
+    uint32_t exchange_counter = 0;                                  // exchange points executed so far (flag barrier sequence)
+    uint32_t exchanges_per_solve = 0;
     int inc_work_begin = 0, inc_work_count = 0;
     int all_work_count = 0;                     // work[0 .. all_work_count) covers every bundle once
     int sync_batch_count = 0, fallback_levels = 0;
@@ -302,7 +313,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
     // Row prefetch in the PDL prologue (see constraint_stage_kernel): allowed when the kernel launched immediately before neither rewrites this
     // batch's prestep rows (the incremental contact update does) nor its impulses (a stage of the same batch does: single-batch scenes).
     const StageOp* previous = nullptr;  // last launched op
-    uint32_t pass_offset = 0, ws_pass_offset = 0;
+    uint32_t pass_offset = 0, ws_pass_offset = 0, exchange_index = 0;
     bool first_substep = true;
     DataflowTables df{};
     int contacts_only = 1;
@@ -326,6 +337,20 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
             ++pass_offset;
             previous = &op;
             ++n;
+            continue;
+        }
+        if (ctx->peer_mode && op.pad >= 2 && op.stage <= kStageSolve) {
+            // peer sharding: the stage on this rank's constraints of the batch, then records written for shared bodies go to the ranks that
+            // reference them and all ranks meet at the flag barrier
+            if (op.work_count > 0) {
+                ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, pdl ? kLaunchPdl : 0, s);
+                ++n;
+            }
+            const auto& range = ctx->push_range[op.pad - 2];
+            launch_shard_exchange(ctx->pushes_dev.as<uint32_t>() + range.first, range.second, op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2), ctx->B, ctx->peers, fp,
+                                  exchange_index++, ctx->error_dev.as<int32_t>(), s);
+            ++n;
+            previous = nullptr;  // the next stage kernel follows the exchange kernel: no row prefetch assumptions across it
             continue;
         }
         switch (op.stage) {
@@ -364,6 +389,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
         }
     }
     if (launches) *launches = n;
+    ctx->exchanges_per_solve = exchange_index;
 }
 
 // Builds the flat stage program for the current topology + solve description.
@@ -386,11 +412,16 @@ void build_program(bepucuda_ctx* ctx) {
             }
             continue;
         }
-        for (auto& bw : ctx->batch_work)
-            if (bw.second > 0) ctx->program.push_back({s == 0 ? kStageWarmStartFirst : kStageWarmStart, bw.first, bw.second, 0});
+        // pad carries the device batch index + 2 in peer mode (every rank runs the exchange of every batch, also of one it has no constraint in)
+        for (size_t b = 0; b < ctx->batch_work.size(); ++b) {
+            auto& bw = ctx->batch_work[b];
+            if (bw.second > 0 || (ctx->peer_mode && (int)b < ctx->sync_batch_count)) ctx->program.push_back({s == 0 ? kStageWarmStartFirst : kStageWarmStart, bw.first, bw.second, ctx->peer_mode ? (int)b + 2 : 0});
+        }
         for (int it = 0; it < ctx->iterations[s]; ++it)
-            for (auto& bw : ctx->batch_work)
-                if (bw.second > 0) ctx->program.push_back({kStageSolve, bw.first, bw.second, 0});
+            for (size_t b = 0; b < ctx->batch_work.size(); ++b) {
+                auto& bw = ctx->batch_work[b];
+                if (bw.second > 0 || (ctx->peer_mode && (int)b < ctx->sync_batch_count)) ctx->program.push_back({kStageSolve, bw.first, bw.second, ctx->peer_mode ? (int)b + 2 : 0});
+            }
     }
     ctx->program.push_back({kStageFinalPose, 0, ctx->body_count, 0});
 }
@@ -522,7 +553,8 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
-    DeviceBuffer* bufs[] = {&ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
+    for (void* p : ctx->opened_ipc) cudaIpcCloseMemHandle(p);
+    DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
                             &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
@@ -725,21 +757,30 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
             SourceTypeBatch& s = ctx->sources[si];
             s.device_tbs.clear();
             if (s.batch_index >= ctx->fallback_threshold) continue;
-            if (s.batch_index != current_batch) { batch_tbs.emplace_back(); current_batch = s.batch_index; }
+            // device batch index == host batch index (empty batches stay as empty slots): ranks of a sharded graph then agree on batch numbers
+            while ((int)batch_tbs.size() <= s.batch_index) batch_tbs.emplace_back();
+            current_batch = s.batch_index;
             const TypeInfo* t = get_type_info(s.type_id);
             DeviceTypeBatch d{};
             d.type_id = s.type_id;
             d.bundle_count = (s.count + 31) / 32;
-            d.device_batch = (int)batch_tbs.size() - 1;
+            d.device_batch = s.batch_index;
             TransposeDesc td{s.raw_refs, s.raw_prestep, s.raw_impulses, nullptr, s.count, t->bodies, t->prestep_rows, t->impulse_rows, source_bundle_base[si], 0, nullptr, nullptr};
             s.device_tbs.push_back((int)ctx->tbs.size());
-            batch_tbs.back().push_back((int)ctx->tbs.size());
+            batch_tbs[s.batch_index].push_back((int)ctx->tbs.size());
             ctx->tbs.push_back(d);
             ctx->tdescs.push_back(td);
             map_offset.push_back(SIZE_MAX);
             s.live = s.count;
             constraint_count += s.count;
         }
+        if (ctx->peer_mode) {
+            // every rank runs the exchange of every batch, also of batches it has no constraint in
+            while ((int)batch_tbs.size() < std::min(ctx->batch_count, ctx->fallback_threshold)) batch_tbs.emplace_back();
+            for (const SourceTypeBatch& src : ctx->sources)
+                if (src.batch_index >= ctx->fallback_threshold) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "end_constraints: the sequential fallback batch is not supported across ranks");
+        }
+        (void)current_batch;
         ctx->sync_batch_count = (int)batch_tbs.size();
     }
     {
@@ -919,7 +960,12 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     launch_ownership_pass1(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), ctx->sync_batch_count,
                            ctx->body_count, ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (unsigned long long*)ctx->sync_mask.ptr, ctx->error_dev.as<int32_t>(),
                            ctx->stream);
-    if (ctx->exchange && nb > 0) {
+    if (ctx->peer_mode && nb > 0) {
+        // peer sharding: the integration owner of a body is the lowest batch referencing it on ANY rank (computed by the host over the whole graph)
+        if ((int)ctx->global_first_batch.size() != ctx->body_count) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "end_constraints: bepucuda_shard_set_global was not called for this body count");
+        CK(cudaMemcpyAsync(ctx->first_batch.ptr, ctx->global_first_batch.data(), (size_t)ctx->body_count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (ctx->exchange && !ctx->peer_mode && nb > 0) {
         // sharded batches: the integration owner of a body is the lowest batch referencing it on ANY rank
         if (ctx->exchange(ctx->exchange_user, ctx->first_batch.ptr, (int64_t)ctx->body_count, 1, (void*)ctx->stream) != 0)
             return fail(ctx, BEPUCUDA_ERR_CUDA, "end_constraints: the exchange callback failed (first-batch minimum)");
@@ -928,7 +974,21 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
                           ctx->first_batch.as<int32_t>(), ctx->sync_refcount.as<int32_t>(), (const unsigned long long*)ctx->sync_mask.ptr, ctx->constrained.as<uint8_t>(),
                           ctx->kinematics_dev.as<int32_t>(), (int)ctx->kinematics.size(), ctx->error_dev.as<int32_t>(), ctx->tdesc_table.as<TransposeDesc>(), W,
                           ctx->source_bundle_flags.as<int32_t>(), ctx->stream);
-    if (ctx->exchange && nb > 0) {
+    if (ctx->peer_mode && nb > 0) {
+        CK(cudaMemcpyAsync(ctx->constrained.ptr, ctx->global_constrained.data(), (size_t)ctx->body_count, cudaMemcpyHostToDevice, ctx->stream));
+        // the (body, destination rank) lists of every batch, back to back
+        std::vector<uint32_t> all;
+        ctx->push_range.assign(ctx->sync_batch_count, {0, 0});
+        for (int b = 0; b < ctx->sync_batch_count; ++b) {
+            auto it = ctx->pushes_by_batch.find(b);
+            if (it == ctx->pushes_by_batch.end()) continue;
+            ctx->push_range[b] = {all.size(), (int)it->second.size()};
+            all.insert(all.end(), it->second.begin(), it->second.end());
+        }
+        CK(ctx->pushes_dev.reserve(all.size() * 4 + 16));
+        if (!all.empty()) CK(cudaMemcpy(ctx->pushes_dev.ptr, all.data(), all.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (ctx->exchange && !ctx->peer_mode && nb > 0) {
         // ... and a body is "constrained" (final pose pass) if any rank constrains it
         CK(ctx->exchange_staging.reserve((size_t)nb * 24 * 4));
         launch_widen_u8(ctx->constrained.as<uint8_t>(), ctx->exchange_staging.as<int32_t>(), (size_t)ctx->body_count, ctx->stream);
@@ -1126,9 +1186,12 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
         ctx->versions_dirty = false;
     }
     ctx->frame_params_host->pass_base = ctx->pass_counter;
+    ctx->frame_params_host->exchange_base = ctx->exchange_counter;
     CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
 
-    if (ctx->exchange) {
+    if (ctx->peer_mode && ctx->cfg.execution_mode != BEPUCUDA_EXEC_GRAPH && ctx->cfg.execution_mode != BEPUCUDA_EXEC_STREAM)
+        return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "solve: peer sharding needs BEPUCUDA_EXEC_GRAPH or BEPUCUDA_EXEC_STREAM");
+    if (ctx->exchange && !ctx->peer_mode) {
         if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_STREAM) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "solve: sharded batches need BEPUCUDA_EXEC_STREAM");
         if (ctx->integ.angular_integration_mode != 0) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "solve: sharded batches support AngularIntegrationMode.Nonconserving only");
         ctx->exchange_failed = false;
@@ -1179,6 +1242,7 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     CK(cudaEventRecord(ctx->ev_solve_end, ctx->stream));
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW)
         for (int it : ctx->iterations) ctx->pass_counter += (uint32_t)it + 1u;  // body versions keep counting across solves
+    if (ctx->peer_mode) ctx->exchange_counter += ctx->exchanges_per_solve;      // the flag barrier keeps counting across solves
     ctx->have_solve = true;
     ctx->timings.kernel_launches = launches;
 
@@ -1200,6 +1264,12 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
 }
 
 static int check_device_error_flag(bepucuda_ctx* ctx) {
+    if (ctx->peer_mode) {
+        int32_t e = 0;
+        CK(cudaMemcpyAsync(&e, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (e == 5) return fail(ctx, BEPUCUDA_ERR_CUDA, "sharded solve: a peer rank never reached an exchange point (flag barrier timed out); results are invalid");
+    }
     if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_DATAFLOW) return BEPUCUDA_OK;
     int32_t err[8] = {};
     CK(cudaMemcpyAsync(err, ctx->error_dev.ptr, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1355,6 +1425,71 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
         }
         out->algorithmic_bytes[op.stage] += bytes;
     }
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_shard_export(bepucuda_ctx* ctx, bepucuda_ipc_handles* out) {
+    if (!ctx || !out) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_export: bad arguments");
+    if (ctx->body_count <= 0) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "shard_export before upload_bodies");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->shard_flags.reserve(kMaxShardRanks * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->shard_flags.ptr, 0, kMaxShardRanks * sizeof(unsigned long long)));
+    void* ptrs[4] = {ctx->pose.ptr, ctx->velocity.ptr, ctx->inertia_world.ptr, ctx->shard_flags.ptr};
+    for (int i = 0; i < 4; ++i) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ptrs[i]));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(out->bytes[i], &h, 64);
+    }
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_shard_import(bepucuda_ctx* ctx, int32_t rank, int32_t rank_count, const bepucuda_ipc_handles* all) {
+    if (!ctx || !all || rank_count < 1 || rank_count > kMaxShardRanks || rank < 0 || rank >= rank_count) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_import: bad arguments");
+    if (!ctx->shard_flags.ptr) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "shard_import before shard_export");
+    CK(cudaSetDevice(ctx->device));
+    ShardPeers p{};
+    p.rank = rank;
+    p.rank_count = rank_count;
+    for (int r = 0; r < rank_count; ++r) {
+        void* ptrs[4] = {ctx->pose.ptr, ctx->velocity.ptr, ctx->inertia_world.ptr, ctx->shard_flags.ptr};
+        if (r != rank)
+            for (int i = 0; i < 4; ++i) {
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, all[r].bytes[i], 64);
+                CK(cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
+                ctx->opened_ipc.push_back(ptrs[i]);
+            }
+        p.pose[r] = (float4*)ptrs[0];
+        p.velocity[r] = (float4*)ptrs[1];
+        p.inertia_world[r] = (float4*)ptrs[2];
+        p.flags[r] = (unsigned long long*)ptrs[3];
+    }
+    ctx->peers = p;
+    ctx->peer_mode = true;
+    ctx->exchange_counter = 0;
+    if (ctx->constraints_ready) ctx->constraints_ready = false;
+    invalidate_graph(ctx);
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_shard_set_global(bepucuda_ctx* ctx, const int32_t* first_batch, const uint8_t* constrained) {
+    if (!ctx || !first_batch || !constrained) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_set_global: bad arguments");
+    ctx->global_first_batch.assign(first_batch, first_batch + ctx->body_count);
+    ctx->global_constrained.assign(constrained, constrained + ctx->body_count);
+    if (ctx->constraints_ready) ctx->constraints_ready = false;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_shard_set_pushes(bepucuda_ctx* ctx, int32_t batch_index, int32_t count, const int32_t* bodies, const int32_t* ranks, const int32_t* owner_flags) {
+    if (!ctx || batch_index < 0 || count < 0 || (count > 0 && (!bodies || !ranks || !owner_flags))) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_set_pushes: bad arguments");
+    std::vector<uint32_t>& list = ctx->pushes_by_batch[batch_index];
+    list.resize((size_t)count);
+    for (int i = 0; i < count; ++i) {
+        if (bodies[i] < 0 || bodies[i] >= ctx->body_count || ranks[i] < 0 || ranks[i] >= kMaxShardRanks) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_set_pushes: body or rank out of range");
+        list[i] = (uint32_t)bodies[i] | ((uint32_t)ranks[i] << 28) | (owner_flags[i] ? kPushOwnerBit : 0u);
+    }
+    if (ctx->constraints_ready) ctx->constraints_ready = false;
     return BEPUCUDA_OK;
 }
 

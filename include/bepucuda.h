@@ -210,6 +210,31 @@ typedef int32_t (*bepucuda_exchange_fn)(void* user, void* device_words, int64_t 
 int32_t bepucuda_set_boundary_bodies(bepucuda_ctx* ctx, const int32_t* body_indices, int32_t count,
                                      bepucuda_exchange_fn exchange, void* user);
 
+/* Multi-GPU, ONE constraint graph over several GPUs with direct NVLink peer stores (the fast successor of the callback path above).
+ * Bodies are partitioned into owner slabs by the host; every rank (one context per GPU, normally one process per GPU) uploads ALL bodies (only
+ * its own slab and the halo it references are kept current) and ONLY ITS OWN constraints, compacted, under their original batch indices. After
+ * every WarmStart / Solve stage a rank copies the records its stage wrote for bodies other ranks also reference straight into those ranks' body
+ * arrays (peer memory opened from CUDA IPC handles) and all ranks meet at a flag barrier in peer memory: no host round trip, no collective library.
+ * Within a batch no dynamic body is referenced twice, so exactly one rank writes a given body in a given stage, and every rank's copy of a body
+ * it references is bit-identical to the single-GPU solve at every stage.
+ *   bepucuda_shard_export: IPC handles of this context's pose / velocity / world-inertia arrays and of its flag block (call after
+ *     bepucuda_upload_bodies; the arrays must not be re-allocated afterwards, i.e. keep the body count).
+ *   bepucuda_shard_import: this rank's index, the rank count (<= 8) and every rank's exported handles, in rank order.
+ *   bepucuda_shard_set_global: per body, the lowest batch index that references it as a dynamic body on ANY rank (INT32_MAX if none) -- the owner of
+ *     its integration, Solver_Solve.cs:L951-1044 -- and whether any rank constrains it (final pose pass, PoseIntegrator.cs:L537-693).
+ *   bepucuda_shard_set_pushes: for one batch, the (body, destination rank) pairs of the bodies THIS rank's constraints of that batch write and the
+ *     destination rank also references; owner_flags[i] != 0 when this batch integrates the body (pose and world inertia travel too in WarmStart).
+ * Call order: upload_bodies, shard_export, (exchange handles), shard_import, shard_set_global, begin_constraints ... shard_set_pushes ...
+ * end_constraints. The sequential fallback batch is not supported across ranks (BEPUCUDA_ERR_BAD_STATE). BEPUCUDA_EXEC_GRAPH or _STREAM. */
+typedef struct bepucuda_ipc_handles {
+    unsigned char bytes[4][64];
+} bepucuda_ipc_handles;
+int32_t bepucuda_shard_export(bepucuda_ctx* ctx, bepucuda_ipc_handles* out);
+int32_t bepucuda_shard_import(bepucuda_ctx* ctx, int32_t rank, int32_t rank_count, const bepucuda_ipc_handles* all_ranks);
+int32_t bepucuda_shard_set_global(bepucuda_ctx* ctx, const int32_t* first_batch_per_body, const uint8_t* constrained_per_body);
+int32_t bepucuda_shard_set_pushes(bepucuda_ctx* ctx, int32_t batch_index, int32_t count, const int32_t* body_indices, const int32_t* destination_ranks,
+                                  const int32_t* owner_flags);
+
 #ifdef __cplusplus
 }
 #endif

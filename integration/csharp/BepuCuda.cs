@@ -5,6 +5,7 @@ using System.Runtime.InteropServices;
 
 namespace BepuCuda
 {
+    [StructLayout(LayoutKind.Sequential)] public unsafe struct IpcHandles { public fixed byte Bytes[256]; }
     [StructLayout(LayoutKind.Sequential)]
     public unsafe struct Config { public int DeviceOrdinal, StrictFp, ExecutionMode; public fixed int Reserved[5]; }
 
@@ -65,6 +66,10 @@ namespace BepuCuda
         [DllImport(Lib)] public static extern int bepucuda_event_record(IntPtr ctx, int slot);
         [DllImport(Lib)] public static extern int bepucuda_event_elapsed_ms(IntPtr ctx, int slotBegin, int slotEnd, float* ms);
         [DllImport(Lib)] public static extern int bepucuda_profile_stages(IntPtr ctx, float dt, StageProfile* profile);
+        [DllImport(Lib)] public static extern int bepucuda_shard_export(IntPtr ctx, IpcHandles* handles);
+        [DllImport(Lib)] public static extern int bepucuda_shard_import(IntPtr ctx, int rank, int rankCount, IpcHandles* allRanks);
+        [DllImport(Lib)] public static extern int bepucuda_shard_set_global(IntPtr ctx, int* firstBatchPerBody, byte* constrainedPerBody);
+        [DllImport(Lib)] public static extern int bepucuda_shard_set_pushes(IntPtr ctx, int batchIndex, int count, int* bodyIndices, int* destinationRanks, int* ownerFlags);
         [DllImport(Lib)] public static extern int bepucuda_set_boundary_bodies(IntPtr ctx, int* bodyIndices, int count, ExchangeFn exchange, void* user);
     }
 }

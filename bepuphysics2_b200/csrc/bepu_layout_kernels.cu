@@ -409,9 +409,14 @@ __device__ __forceinline__ void copy_record(float4* dst, const float4* src, size
     dst[2 * body] = a;
     dst[2 * body + 1] = b;
 }
-__global__ void __launch_bounds__(1024, 1)
+// Launched with programmatic stream serialization like the stage kernels: it may start while the stage before it is still running, waits for that
+// stage to complete, and only then lets the NEXT stage's grid start its prologue (work record, body references, row prefetch), which overlaps
+// with the pushes and the barrier below.
+__global__ void __launch_bounds__(256, 1)
 shard_exchange_kernel(const uint32_t* __restrict__ pushes, int push_count, int what, BodyBuffers B, ShardPeers peers, const FrameParams* __restrict__ fpp, uint32_t exchange_index,
                       int32_t* error_flag) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     for (int i = threadIdx.x; i < push_count; i += blockDim.x) {
         const uint32_t e = pushes[i];
         const size_t body = e & 0x0FFFFFFFu;
@@ -438,7 +443,16 @@ shard_exchange_kernel(const uint32_t* __restrict__ pushes, int push_count, int w
 }
 void launch_shard_exchange(const uint32_t* pushes, int push_count, int what, const BodyBuffers& B, const ShardPeers& peers, const FrameParams* fp, uint32_t exchange_index,
                            int32_t* error_flag, cudaStream_t s) {
-    shard_exchange_kernel<<<1, 1024, 0, s>>>(pushes, push_count, what, B, peers, fp, exchange_index, error_flag);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, shard_exchange_kernel, pushes, push_count, what, B, peers, fp, exchange_index, error_flag);
 }
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
     if (n == 0) return;

@@ -343,14 +343,16 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
             // peer sharding: the stage on this rank's constraints of the batch, then records written for shared bodies go to the ranks that
             // reference them and all ranks meet at the flag barrier
             if (op.work_count > 0) {
-                ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, pdl ? kLaunchPdl : 0, s);
+                // row prefetch in the prologue: the exchange kernel between two stages writes no rows, so the rule of the single-GPU sequence applies
+                bool prefetch = previous != nullptr && previous->stage != kStageIncremental && !(previous->stage <= kStageSolve && previous->work_begin == op.work_begin && previous->work_count > 0);
+                ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0), s);
                 ++n;
             }
             const auto& range = ctx->push_range[op.pad - 2];
             launch_shard_exchange(ctx->pushes_dev.as<uint32_t>() + range.first, range.second, op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2), ctx->B, ctx->peers, fp,
                                   exchange_index++, ctx->error_dev.as<int32_t>(), s);
             ++n;
-            previous = nullptr;  // the next stage kernel follows the exchange kernel: no row prefetch assumptions across it
+            if (op.work_count > 0) previous = &op;
             continue;
         }
         switch (op.stage) {

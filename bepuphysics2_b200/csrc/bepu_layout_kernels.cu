@@ -417,6 +417,9 @@ shard_exchange_kernel(const uint32_t* __restrict__ pushes, int push_count, int w
                       int32_t* error_flag) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
+    unsigned long long t0 = 0, t1 = 0, t2 = 0;
+    const bool timing = fpp->tune[3] != 0 && threadIdx.x == (peers.rank == 0 ? 1 : 0);  // development knob: phase times of the thread that talks to one peer
+    if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (int i = threadIdx.x; i < push_count; i += blockDim.x) {
         const uint32_t e = pushes[i];
         const size_t body = e & 0x0FFFFFFFu;
@@ -429,16 +432,27 @@ shard_exchange_kernel(const uint32_t* __restrict__ pushes, int push_count, int w
     }
     __threadfence_system();  // every thread's peer stores before the signal below
     __syncthreads();
+    if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     const unsigned long long seq = (unsigned long long)fpp->exchange_base + exchange_index + 1ull;
     const int p = threadIdx.x;
     if (p < peers.rank_count && p != peers.rank) {
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[p] + peers.rank), "l"(seq) : "memory");
+        if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
         unsigned long long seen;
         unsigned int spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(peers.flags[peers.rank] + p) : "memory");
         } while (seen < seq && ++spins < 200000000u);
         if (seen < seq) atomicExch(error_flag, 5);  // a peer never arrived: results are void
+        if (timing) {
+            unsigned long long t3;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3));
+            unsigned long long* acc = peers.flags[peers.rank] + kMaxShardRanks;  // four accumulators behind the flag slots: push, signal, wait (ns), count
+            acc[0] += t1 - t0;
+            acc[1] += t2 - t1;
+            acc[2] += t3 - t2;
+            acc[3] += 1;
+        }
     }
 }
 void launch_shard_exchange(const uint32_t* pushes, int push_count, int what, const BodyBuffers& B, const ShardPeers& peers, const FrameParams* fp, uint32_t exchange_index,

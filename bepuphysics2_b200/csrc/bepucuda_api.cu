@@ -1266,6 +1266,12 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
 }
 
 static int check_device_error_flag(bepucuda_ctx* ctx) {
+    if (ctx->peer_mode && ctx->tune[3]) {
+        unsigned long long acc[4] = {};
+        cudaMemcpy(acc, (unsigned long long*)ctx->shard_flags.ptr + kMaxShardRanks, sizeof(acc), cudaMemcpyDeviceToHost);
+        if (acc[3]) fprintf(stderr, "[bepucuda shard rank %d] exchange phases, mean over %llu: push+fence %.2f us, signal %.2f us, wait %.2f us\n", ctx->peers.rank, acc[3],
+                            acc[0] / 1e3 / acc[3], acc[1] / 1e3 / acc[3], acc[2] / 1e3 / acc[3]);
+    }
     if (ctx->peer_mode) {
         int32_t e = 0;
         CK(cudaMemcpyAsync(&e, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1434,8 +1440,8 @@ int32_t bepucuda_shard_export(bepucuda_ctx* ctx, bepucuda_ipc_handles* out) {
     if (!ctx || !out) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_export: bad arguments");
     if (ctx->body_count <= 0) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "shard_export before upload_bodies");
     CK(cudaSetDevice(ctx->device));
-    CK(ctx->shard_flags.reserve(kMaxShardRanks * sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->shard_flags.ptr, 0, kMaxShardRanks * sizeof(unsigned long long)));
+    CK(ctx->shard_flags.reserve((kMaxShardRanks + 4) * sizeof(unsigned long long)));  // flag slots + four development accumulators
+    CK(cudaMemset(ctx->shard_flags.ptr, 0, (kMaxShardRanks + 4) * sizeof(unsigned long long)));
     void* ptrs[4] = {ctx->pose.ptr, ctx->velocity.ptr, ctx->inertia_world.ptr, ctx->shard_flags.ptr};
     for (int i = 0; i < 4; ++i) {
         cudaIpcMemHandle_t h;

@@ -468,6 +468,18 @@ void launch_shard_exchange(const uint32_t* pushes, int push_count, int what, con
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, shard_exchange_kernel, pushes, push_count, what, B, peers, fp, exchange_index, error_flag);
 }
+__global__ void fill_peer_masks_kernel(const int32_t* __restrict__ refs, uint32_t* __restrict__ peer_masks, size_t count, const uint8_t* __restrict__ body_masks, int rank) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int32_t enc = refs[i];
+    uint32_t m = 0;
+    if (enc >= 0 && !((uint32_t)enc & kRefKinematicBit)) m = (uint32_t)body_masks[(uint32_t)enc & kRefIndexMask] & ~(1u << rank);
+    peer_masks[i] = m;
+}
+void launch_fill_peer_masks(const int32_t* refs, uint32_t* peer_masks, size_t count, const uint8_t* body_masks, int rank, cudaStream_t s) {
+    if (count == 0) return;
+    fill_peer_masks_kernel<<<blocks_for(count, 256), 256, 0, s>>>(refs, peer_masks, count, body_masks, rank);
+}
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
     if (n == 0) return;
     fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, v);

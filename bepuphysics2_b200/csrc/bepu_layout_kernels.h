@@ -65,6 +65,10 @@ void launch_narrow_i32(const int32_t* in, uint8_t* out, size_t n, cudaStream_t s
 void launch_shard_exchange(const uint32_t* pushes, int push_count, int what, const BodyBuffers& B, const ShardPeers& peers, const FrameParams* fp, uint32_t exchange_index,
                            int32_t* error_flag, cudaStream_t s);
 
+// Peer sharding, fused pushes: peer_masks[i] = ranks other than `rank` that reference the dynamic body of device reference refs[i] (0 for empty and
+// kinematic slots); body_masks[b] has bit r set when rank r references body b.
+void launch_fill_peer_masks(const int32_t* refs, uint32_t* peer_masks, size_t count, const uint8_t* body_masks, int rank, cudaStream_t s);
+
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
 constexpr int kLaunchPdl = 1, kLaunchPrefetchRows = 2;
 struct SolverLaunchers {
@@ -83,6 +87,10 @@ struct SolverLaunchers {
     // solve. error_flag is set to 4 if a dependency never arrives. contacts_only selects the instantiation whose type switch holds the contact types only.
     int (*dataflow_pass)(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
                          uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s);
+    // Peer-sharded WarmStartFirst / WarmStart / Solve stage: like constraint_stage, and every written body record also goes to the ranks named by the
+    // per-(lane, slot) destination masks at refs + peer_delta (launch_fill_peer_masks).
+    void (*constraint_stage_sharded)(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
+                                     long long peer_delta, cudaStream_t s);
 };
 const SolverLaunchers* get_launchers_bepu_fast();
 const SolverLaunchers* get_launchers_bepu_strict();

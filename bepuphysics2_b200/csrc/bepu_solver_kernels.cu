@@ -15,6 +15,9 @@ namespace BEPU_NS {
 void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
 void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
 void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
+void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s);
+void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s);
+void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s);
 int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                            unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
 int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
@@ -47,6 +50,35 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
     cfg.numAttrs = (launch_flags & bepucuda::kLaunchPdl) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0);
 }
+template <int STAGE, int MINB>
+static void launch_stage_variant_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
+                                         cudaStream_t s) {
+    static bool carveout_set[64] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    if (!carveout_set[device & 63]) {
+        cudaFuncSetAttribute(constraint_stage_kernel_sharded<STAGE, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set[device & 63] = true;
+    }
+    const unsigned blocks = (unsigned)(((size_t)work_count * 32 + kStageBlockThreads - 1) / kStageBlockThreads);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kStageBlockThreads);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (launch_flags & bepucuda::kLaunchPdl) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, constraint_stage_kernel_sharded<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0, peers,
+                       peer_delta);
+}
+template <int STAGE>
+static void launch_stage_sharded_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
+                                   cudaStream_t s) {
+    if (work_count >= kDeepBatchBundles) launch_stage_variant_sharded<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+    else launch_stage_variant_sharded<STAGE, 1>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+}
 template <int STAGE>
 static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     if (STAGE != kStageIncremental && work_count >= kDeepBatchBundles) launch_stage_variant<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, launch_flags, s);
@@ -58,13 +90,22 @@ static void launch_stage_t(const WorkRecord* records, int work_count, const Body
 void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, s);
 }
+void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s) {
+    launch_stage_sharded_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+}
 #elif BEPU_UNIT == 1
 void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     launch_stage_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, s);
 }
+void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s) {
+    launch_stage_sharded_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+}
 #elif BEPU_UNIT == 2
 void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     launch_stage_t<kStageSolve>(records, work_count, B, fp, launch_flags, s);
+}
+void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s) {
+    launch_stage_sharded_t<kStageSolve>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
 }
 #elif BEPU_UNIT == 3
 static void launch_constraint_stage(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
@@ -74,6 +115,16 @@ static void launch_constraint_stage(int stage, const WorkRecord* records, int wo
         case kStageWarmStart: launch_stage_warm_start(records, work_count, B, fp, launch_flags, s); break;
         case kStageSolve: launch_stage_solve(records, work_count, B, fp, launch_flags, s); break;
         case kStageIncremental: launch_stage_t<kStageIncremental>(records, work_count, B, fp, launch_flags, s); break;
+        default: break;
+    }
+}
+static void launch_constraint_stage_sharded(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
+                                            long long peer_delta, cudaStream_t s) {
+    if (work_count <= 0) return;
+    switch (stage) {
+        case kStageWarmStartFirst: launch_stage_warm_start_first_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, s); break;
+        case kStageWarmStart: launch_stage_warm_start_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, s); break;
+        case kStageSolve: launch_stage_solve_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, s); break;
         default: break;
     }
 }
@@ -87,7 +138,7 @@ static void launch_final_pose(const BodyBuffers& B, const FrameParams* fp, cudaS
     if (B.count <= 0) return;
     final_pose_kernel<<<(unsigned)((B.count + 255) / 256), 256, 0, s>>>(B, fp);
 }
-static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent_unit, &launch_dataflow_unit};
+static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent_unit, &launch_dataflow_unit, &launch_constraint_stage_sharded};
 #elif BEPU_UNIT == 4
 int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                            unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s) {

@@ -134,8 +134,25 @@ template <class T> BEPU_DI void call_incremental(float dt, const Velocity* v, fl
 // One constraint lane of one stage. refs addresses this lane in row 0 of the bundle's body references; enc0/enc1 are the (possibly prefetched)
 // first two body references; p / a are the row accessors (global or staged); p_rw is the lane's raw prestep pointer for the in-place
 // IncrementallyUpdateForSubstep.
-template <class T, int STAGE, class PR, class AR>
-BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+BEPU_DI uint32_t ldg_nc_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// Peer sharding (bepucuda_shard_*): a body another rank references too is also written into that rank's arrays, straight from the registers of
+// the lane that computed it (NVLink peer stores; the per-(lane, slot) destination masks sit next to the body references at refs + peer_delta).
+BEPU_DI void push_record(float4* const* arrays, uint32_t mask, uint32_t idx, float a, float b, float c, float d, float e, float f, float g, float h) {
+    while (mask) {
+        const int q = __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        float4* dst = arrays[q] + 2 * (size_t)idx;
+        dst[0] = make_float4(a, b, c, d);
+        dst[1] = make_float4(e, f, g, h);
+    }
+}
+template <class T, int STAGE, bool kSharded, class PR, class AR>
+BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp, const ShardPeers* peers = nullptr,
+                      long long peer_delta = 0) {
     constexpr int NB = T::kBodies;
     uint32_t enc[NB];
     enc[0] = enc0;
@@ -161,7 +178,13 @@ BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc
         call_solve<T>(b, fp.dt, fp.inverse_dt, p, a, v);
 #pragma unroll
         for (int s = 0; s < NB; ++s)
-            if (!(enc[s] & kRefKinematicBit)) store_velocity(B.velocity, enc[s] & kRefIndexMask, v[s]);
+            if (!(enc[s] & kRefKinematicBit)) {
+                store_velocity(B.velocity, enc[s] & kRefIndexMask, v[s]);
+                if constexpr (kSharded) {
+                    const uint32_t mask = ldg_nc_u32(refs + peer_delta + s * kLanes);
+                    if (mask) push_record(peers->velocity, mask, enc[s] & kRefIndexMask, v[s].lin.x, v[s].lin.y, v[s].lin.z, 0.0f, v[s].ang.x, v[s].ang.y, v[s].ang.z, 0.0f);
+                }
+            }
     } else {
 #pragma unroll
         for (int s = 0; s < NB; ++s) gather_for_warm_start<STAGE, T::kNeedsPose>(enc[s], B, fp, b[s], v[s]);
@@ -169,8 +192,26 @@ BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc
         call_warm_start<T>(b, p, a, v);
 #pragma unroll
         for (int s = 0; s < NB; ++s)
-            if (!(enc[s] & kRefKinematicBit)) store_velocity(B.velocity, enc[s] & kRefIndexMask, v[s]);
+            if (!(enc[s] & kRefKinematicBit)) {
+                const uint32_t idx = enc[s] & kRefIndexMask;
+                store_velocity(B.velocity, idx, v[s]);
+                if constexpr (kSharded) {
+                    const uint32_t mask = ldg_nc_u32(refs + peer_delta + s * kLanes);
+                    if (mask) {
+                        push_record(peers->velocity, mask, idx, v[s].lin.x, v[s].lin.y, v[s].lin.z, 0.0f, v[s].ang.x, v[s].ang.y, v[s].ang.z, 0.0f);
+                        if (enc[s] & kRefIntegrateBit) {  // this lane integrated the body: its new world inertia (and pose) travel too
+                            const Inertia& in = b[s].inertia;
+                            push_record(peers->inertia_world, mask, idx, in.t.xx, in.t.yx, in.t.yy, in.t.zx, in.t.zy, in.t.zz, in.inv_mass, 0.0f);
+                            if (STAGE == kStageWarmStart) push_record(peers->pose, mask, idx, b[s].q.x, b[s].q.y, b[s].q.z, b[s].q.w, b[s].pos.x, b[s].pos.y, b[s].pos.z, 0.0f);
+                        }
+                    }
+                }
+            }
     }
+}
+template <class T, int STAGE, class PR, class AR>
+BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+    run_lane<T, STAGE, false>(refs, p, a, p_rw, enc0, enc1, B, fp);
 }
 
 // Work records and body references are loaded with `asm volatile` so that the loads are ISSUED where the source places them (a whole pipeline
@@ -178,11 +219,6 @@ BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc
 BEPU_DI int4 ldg_nc_v4(const void* p) {
     int4 v;
     asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-BEPU_DI uint32_t ldg_nc_u32(const void* p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 BEPU_DI WorkRecord load_record(const WorkRecord* r) {
@@ -203,19 +239,24 @@ BEPU_DI WorkRecord load_record(const WorkRecord* r) {
     X(8, NonconvexOneBody<2>) X(9, NonconvexOneBody<3>) X(10, NonconvexOneBody<4>)                                                \
     X(15, NonconvexTwoBody<2>) X(16, NonconvexTwoBody<3>) X(17, NonconvexTwoBody<4>)
 
-template <int STAGE, class PR, class AR>
-BEPU_DI void run_bundle_rows(const WorkRecord& rec, int lane, PR p, AR a, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+template <int STAGE, bool kSharded, class PR, class AR>
+BEPU_DI void run_bundle_rows(const WorkRecord& rec, int lane, PR p, AR a, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp, const ShardPeers* peers = nullptr,
+                             long long peer_delta = 0) {
     const int32_t* refs = rec.refs + lane;
     float* p_rw = rec.prestep + lane;
     switch (rec.type_id) {
 #define BEPU_CASE(ID, T) \
-    case ID: run_lane<T, STAGE>(refs, p, a, p_rw, enc0, enc1, B, fp); break;
+    case ID: run_lane<T, STAGE, kSharded>(refs, p, a, p_rw, enc0, enc1, B, fp, peers, peer_delta); break;
         BEPU_CONTACT_TYPES(BEPU_CASE)
         BEPU_JOINT_TYPES(BEPU_CASE)
         BEPU_JOINT_TYPES_MORE(BEPU_CASE)
 #undef BEPU_CASE
         default: break;
     }
+}
+template <int STAGE, class PR, class AR>
+BEPU_DI void run_bundle_rows(const WorkRecord& rec, int lane, PR p, AR a, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
+    run_bundle_rows<STAGE, false>(rec, lane, p, a, enc0, enc1, B, fp);
 }
 // Rows straight from HBM (persistent / dataflow kernels, and the incremental stage everywhere).
 template <int STAGE>
@@ -280,8 +321,9 @@ constexpr int kStageBlockThreads = BEPU_STAGE_BLOCK_THREADS;
 // contact update, which rewrites depth rows, nor a stage of this same batch, which rewrites these impulses) -- the whole row block. That takes the
 // bulk copy's latency off the critical path; after the wait only the body gather, the math and the scatter remain.
 constexpr int kStagePrefetchRows = 1;
-template <int STAGE, int MINB>
-__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags) {
+template <int STAGE, bool kSharded>
+BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int work_count, const BodyBuffers& B, const FrameParams* __restrict__ fpp, int flags, const ShardPeers* peers,
+                                   long long peer_delta) {
     constexpr bool kStaged = STAGE != kStageIncremental;
     constexpr int kWarps = kStageBlockThreads / 32;
     __shared__ __align__(128) float slab[kStaged ? kWarps * kStageSlabRows * kLanes : 1];
@@ -327,10 +369,23 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
             bulk_copy_g2s(slab_addr + prestep_bytes, rec.impulses, impulse_bytes, bar, policy);
         }
         __syncwarp();
-        run_bundle_rows<STAGE>(rec, lane, StagedRows{slab_addr + lane * 4, bar, 0u}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp);
+        run_bundle_rows<STAGE, kSharded>(rec, lane, StagedRows{slab_addr + lane * 4, bar, 0u}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp,
+                                         peers, peer_delta);
     } else {
         run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
     }
+}
+
+template <int STAGE, int MINB>
+__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags) {
+    constraint_stage_body<STAGE, false>(records, work_count, B, fpp, flags, nullptr, 0);
+}
+// Peer-sharded variant (bepucuda_shard_*): the lane that writes a body another rank references stores the record into that rank's arrays too.
+template <int STAGE, int MINB>
+__global__ void __launch_bounds__(kStageBlockThreads, MINB)
+constraint_stage_kernel_sharded(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags, const __grid_constant__ ShardPeers peers,
+                                long long peer_delta) {
+    constraint_stage_body<STAGE, true>(records, work_count, B, fpp, flags, &peers, peer_delta);
 }
 
 // IntegrateKinematicVelocities / IntegrateKinematicPosesAndVelocities (PoseIntegrator.cs:L451-487, L493-535)

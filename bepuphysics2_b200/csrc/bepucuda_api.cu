@@ -178,7 +178,9 @@ struct bepucuda_ctx {
     // peer sharding (bepucuda_shard_*): one constraint graph over several GPUs with NVLink peer stores and a flag barrier per stage
     bool peer_mode = false;
     ShardPeers peers{};
-    DeviceBuffer shard_flags, pushes_dev;
+    DeviceBuffer shard_flags, pushes_dev, peer32, body_masks_dev;
+    std::vector<uint8_t> body_masks;                                // bepucuda_shard_set_body_masks: fused pushes from the stage kernels
+    size_t refs_words = 0;
     std::vector<void*> opened_ipc;
     std::vector<int32_t> global_first_batch;
     std::vector<uint8_t> global_constrained;
@@ -315,6 +317,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
     const StageOp* previous = nullptr;  // last launched op
     uint32_t pass_offset = 0, ws_pass_offset = 0, exchange_index = 0;
     bool first_substep = true;
+    const bool fused_pushes = ctx->peer_mode && !ctx->body_masks.empty();
     DataflowTables df{};
     int contacts_only = 1;
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && ctx->all_work_count > 0) {
@@ -339,17 +342,27 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
             ++n;
             continue;
         }
+        if (ctx->peer_mode && op.pad == -1) {
+            // all ranks meet (nothing to push): before the first stage of a solve, and between the incremental contact update -- which reads the
+            // velocities of shared bodies -- and the WarmStart stages whose results peers store into this rank's arrays
+            launch_shard_exchange(nullptr, 0, 1, ctx->B, ctx->peers, fp, exchange_index++, ctx->error_dev.as<int32_t>(), s);
+            ++n;
+            continue;
+        }
         if (ctx->peer_mode && op.pad >= 2 && op.stage <= kStageSolve) {
             // peer sharding: the stage on this rank's constraints of the batch, then records written for shared bodies go to the ranks that
             // reference them and all ranks meet at the flag barrier
             if (op.work_count > 0) {
                 // row prefetch in the prologue: the exchange kernel between two stages writes no rows, so the rule of the single-GPU sequence applies
                 bool prefetch = previous != nullptr && previous->stage != kStageIncremental && !(previous->stage <= kStageSolve && previous->work_begin == op.work_begin && previous->work_count > 0);
-                ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0), s);
+                const int launch_flags = (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0);
+                if (fused_pushes) ctx->launchers->constraint_stage_sharded(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, ctx->peers,
+                                                                          (long long)(ctx->peer32.as<int32_t>() - ctx->refs32.as<int32_t>()), s);
+                else ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, s);
                 ++n;
             }
             const auto& range = ctx->push_range[op.pad - 2];
-            launch_shard_exchange(ctx->pushes_dev.as<uint32_t>() + range.first, range.second, op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2), ctx->B, ctx->peers, fp,
+            launch_shard_exchange(ctx->pushes_dev.as<uint32_t>() + range.first, fused_pushes ? 0 : range.second, op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2), ctx->B, ctx->peers, fp,
                                   exchange_index++, ctx->error_dev.as<int32_t>(), s);
             ++n;
             if (op.work_count > 0) previous = &op;
@@ -406,6 +419,7 @@ void build_program(bepucuda_ctx* ctx) {
         } else if (ctx->integ.integrate_velocity_for_kinematics && kin > 0) {
             ctx->program.push_back({kStageKinematicFirst, 0, kin, 0});
         }
+        if (ctx->peer_mode) ctx->program.push_back({kStageKinematic, 0, 0, -1});  // rank barrier (see issue_stage_sequence)
         if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
             // one op per PASS over all device batches (pad = 1): the order inside a pass is kept by per-body versions, not by kernel boundaries
             if (ctx->all_work_count > 0) {
@@ -556,7 +570,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
     for (void* p : ctx->opened_ipc) cudaIpcCloseMemHandle(p);
-    DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
+    DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->peer32, &ctx->body_masks_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
                             &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
@@ -878,6 +892,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     }
     CK(ctx->refs32.reserve(refs_floats * 4 + 1024));  // slack: solver warps always read two body-reference rows
     CK(ctx->chain32.reserve(refs_floats * 4 + 1024));
+    ctx->refs_words = refs_floats;
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) CK(ctx->succ32.reserve(refs_floats * 4 + 1024));
     CK(ctx->prestep32.reserve(prestep_floats * 4 + 4));
     CK(ctx->impulses32.reserve(impulse_floats * 4 + 4));
@@ -1020,6 +1035,14 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
         launch_chain_finish(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), chain_delta, succ_delta,
                             ctx->next_bundle.as<int32_t>(), ctx->dep_counts.as<int2>(), ctx->stream);
         ctx->versions_dirty = true;
+    }
+    if (ctx->peer_mode && !ctx->body_masks.empty()) {
+        // fused pushes: per body reference, the other ranks that need what this rank's constraint writes
+        if ((int)ctx->body_masks.size() != ctx->body_count) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "end_constraints: bepucuda_shard_set_body_masks was called for another body count");
+        CK(ctx->peer32.reserve(ctx->refs_words * 4 + 1024));
+        CK(ctx->body_masks_dev.reserve((size_t)ctx->body_count + 16));
+        CK(cudaMemcpyAsync(ctx->body_masks_dev.ptr, ctx->body_masks.data(), (size_t)ctx->body_count, cudaMemcpyHostToDevice, ctx->stream));
+        launch_fill_peer_masks(ctx->refs32.as<int32_t>(), ctx->peer32.as<uint32_t>(), ctx->refs_words, ctx->body_masks_dev.as<uint8_t>(), ctx->peers.rank, ctx->stream);
     }
     CK(cudaGetLastError());
     int32_t err = 0;
@@ -1485,6 +1508,14 @@ int32_t bepucuda_shard_set_global(bepucuda_ctx* ctx, const int32_t* first_batch,
     if (!ctx || !first_batch || !constrained) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_set_global: bad arguments");
     ctx->global_first_batch.assign(first_batch, first_batch + ctx->body_count);
     ctx->global_constrained.assign(constrained, constrained + ctx->body_count);
+    if (ctx->constraints_ready) ctx->constraints_ready = false;
+    return BEPUCUDA_OK;
+}
+
+int32_t bepucuda_shard_set_body_masks(bepucuda_ctx* ctx, const uint8_t* rank_masks) {
+    if (!ctx) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    if (rank_masks) ctx->body_masks.assign(rank_masks, rank_masks + ctx->body_count);
+    else ctx->body_masks.clear();
     if (ctx->constraints_ready) ctx->constraints_ready = false;
     return BEPUCUDA_OK;
 }

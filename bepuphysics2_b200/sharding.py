@@ -4,7 +4,7 @@ The reference splits the constraints of every batch over its worker threads (Sol
 into contiguous index slabs (the active set of a pile is spatially coherent in index order, like the reference's body memory after its
 cache-optimising sorts); a constraint belongs to the rank that owns its first dynamic body. Every rank uploads ALL bodies and only ITS constraints,
 compacted, under their original batch indices, so batch k means the same colour on every rank. What crosses GPUs after a (batch, stage): the records
-the stage wrote for bodies that another rank references too (direct NVLink peer stores from a one-CTA exchange kernel, then a flag barrier).
+the stage wrote for bodies that another rank references too (direct NVLink peer stores from the lanes that computed them, then a flag barrier).
 """
 import ctypes as C
 
@@ -100,12 +100,13 @@ class ShardedSolver:
     """One rank of a sharded solve, straight on the C ABI. `exchange_handles(bytes) -> [bytes per rank]` moves the IPC handles between the ranks
     (torch.distributed.all_gather_object in the tools; a direct call when several contexts live in one process)."""
 
-    def __init__(self, simulation, rank, rank_count, device, strict_fp=False, execution_mode=native.EXEC_GRAPH):
+    def __init__(self, simulation, rank, rank_count, device, strict_fp=False, execution_mode=native.EXEC_GRAPH, fused_pushes=True):
         self._cuda, _ = native.load_libraries()
         for name, args in (("bepucuda_shard_export", [C.c_void_p, C.POINTER(IpcHandles)]), ("bepucuda_shard_import", [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(IpcHandles)]),
-                           ("bepucuda_shard_set_global", [C.c_void_p, C.c_void_p, C.c_void_p]), ("bepucuda_shard_set_pushes", [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p])):
+                           ("bepucuda_shard_set_global", [C.c_void_p, C.c_void_p, C.c_void_p]), ("bepucuda_shard_set_pushes", [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+                           ("bepucuda_shard_set_body_masks", [C.c_void_p, C.c_void_p])):
             getattr(self._cuda, name).argtypes = args
-        self.sim, self.rank, self.rank_count = simulation, rank, rank_count
+        self.sim, self.rank, self.rank_count, self.fused_pushes = simulation, rank, rank_count, fused_pushes
         cfg = native.Config()
         cfg.device_ordinal, cfg.strict_fp, cfg.execution_mode = device, int(bool(strict_fp)), execution_mode
         ctx = C.c_void_p()
@@ -144,8 +145,11 @@ class ShardedSolver:
         for tb in self.shard:
             self._check(self._cuda.bepucuda_upload_type_batch(self._ctx, tb["batch_index"], tb["type_batch_index"], tb["type_id"], tb["count"], tb["refs"].ctypes.data,
                                                               tb["prestep"].ctypes.data, tb["impulses"].ctypes.data))
-        for batch, (b, q, o) in pushes_for_rank(self.shard, self.rank, self.rank_count, self.first_batch, self.masks).items():
-            self._check(self._cuda.bepucuda_shard_set_pushes(self._ctx, batch, b.size, b.ctypes.data, q.ctypes.data, o.ctypes.data))
+        if self.fused_pushes:
+            self._check(self._cuda.bepucuda_shard_set_body_masks(self._ctx, self.masks.ctypes.data))
+        else:
+            for batch, (b, q, o) in pushes_for_rank(self.shard, self.rank, self.rank_count, self.first_batch, self.masks).items():
+                self._check(self._cuda.bepucuda_shard_set_pushes(self._ctx, batch, b.size, b.ctypes.data, q.ctypes.data, o.ctypes.data))
         kin = np.ascontiguousarray(sim.constrained_kinematics, dtype=np.int32)
         self._check(self._cuda.bepucuda_set_constrained_kinematics(self._ctx, kin.ctypes.data if kin.size else None, int(kin.size)))
         self._check(self._cuda.bepucuda_end_constraints(self._ctx))

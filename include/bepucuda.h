@@ -224,8 +224,13 @@ int32_t bepucuda_set_boundary_bodies(bepucuda_ctx* ctx, const int32_t* body_indi
  *     its integration, Solver_Solve.cs:L951-1044 -- and whether any rank constrains it (final pose pass, PoseIntegrator.cs:L537-693).
  *   bepucuda_shard_set_pushes: for one batch, the (body, destination rank) pairs of the bodies THIS rank's constraints of that batch write and the
  *     destination rank also references; owner_flags[i] != 0 when this batch integrates the body (pose and world inertia travel too in WarmStart).
- * Call order: upload_bodies, shard_export, (exchange handles), shard_import, shard_set_global, begin_constraints ... shard_set_pushes ...
- * end_constraints. The sequential fallback batch is not supported across ranks (BEPUCUDA_ERR_BAD_STATE). BEPUCUDA_EXEC_GRAPH or _STREAM. */
+ *     These lists are copied by the one-CTA exchange kernel that follows the stage.
+ *   bepucuda_shard_set_body_masks (preferred, replaces the push lists): rank_masks[body] has bit r set when rank r references the body. The stage
+ *     kernels then store a written record into the other referencing ranks' arrays themselves, from the registers of the lane that computed it,
+ *     and the exchange kernel is only the flag barrier. NULL returns to the push lists.
+ * Call order: upload_bodies, shard_export, (exchange handles), shard_import, shard_set_global, shard_set_body_masks | (begin_constraints ...
+ * shard_set_pushes ...), end_constraints. Every rank must have finished uploading a frame's bodies before any rank's bepucuda_solve can complete
+ * its first stage: the solve starts with a rank barrier, so issuing upload and solve on each rank in that order is enough. The sequential fallback batch is not supported across ranks (BEPUCUDA_ERR_BAD_STATE). BEPUCUDA_EXEC_GRAPH or _STREAM. */
 typedef struct bepucuda_ipc_handles {
     unsigned char bytes[4][64];
 } bepucuda_ipc_handles;
@@ -234,6 +239,7 @@ int32_t bepucuda_shard_import(bepucuda_ctx* ctx, int32_t rank, int32_t rank_coun
 int32_t bepucuda_shard_set_global(bepucuda_ctx* ctx, const int32_t* first_batch_per_body, const uint8_t* constrained_per_body);
 int32_t bepucuda_shard_set_pushes(bepucuda_ctx* ctx, int32_t batch_index, int32_t count, const int32_t* body_indices, const int32_t* destination_ranks,
                                   const int32_t* owner_flags);
+int32_t bepucuda_shard_set_body_masks(bepucuda_ctx* ctx, const uint8_t* rank_masks);
 
 #ifdef __cplusplus
 }

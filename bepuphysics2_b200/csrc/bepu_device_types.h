@@ -126,6 +126,17 @@ struct ShardPeers {
     unsigned long long* flags[kMaxShardRanks];  // flags[r][w]: rank r's block, slot written by rank w
     int32_t rank, rank_count;
 };
+// One sharded stage = one exchange point. Bundles that touch a body another rank references ("boundary" bundles, kRecordBoundaryBit in
+// WorkRecord::live_lanes, sorted to the front of the batch) first wait for every peer's signal of the previous exchange point, and count themselves
+// off on `counter` when their peer stores are out; the last one signals this exchange point to every peer. Interior bundles neither wait nor count,
+// so the NVLink round trip hides behind them.
+struct ShardStage {
+    unsigned int* counter;
+    int32_t boundary_count;
+    uint32_t exchange_index;
+    int32_t* error_flag;
+};
+constexpr int32_t kRecordBoundaryBit = 1 << 30;
 // One entry per (body written by this rank in a batch, destination rank): packed as body | rank << 28 | owner << 31.
 constexpr uint32_t kPushOwnerBit = 1u << 31;
 

@@ -480,6 +480,19 @@ void launch_fill_peer_masks(const int32_t* refs, uint32_t* peer_masks, size_t co
     if (count == 0) return;
     fill_peer_masks_kernel<<<blocks_for(count, 256), 256, 0, s>>>(refs, peer_masks, count, body_masks, rank);
 }
+__global__ void boundary_flags_kernel(const WorkRecord* __restrict__ records, int count, const int32_t* __restrict__ bodies_per_type, long long peer_delta, uint8_t* __restrict__ flags) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    const WorkRecord r = records[warp];
+    uint32_t m = 0;
+    for (int s = 0; s < bodies_per_type[r.type_id]; ++s) m |= (uint32_t)r.refs[peer_delta + s * 32 + lane];
+    const bool any = __any_sync(0xFFFFFFFFu, m != 0);
+    if (lane == 0) flags[warp] = any ? 1 : 0;
+}
+void launch_boundary_flags(const WorkRecord* records, int count, const int32_t* bodies_per_type, long long peer_delta, uint8_t* flags, cudaStream_t s) {
+    if (count <= 0) return;
+    boundary_flags_kernel<<<blocks_for((size_t)count * 32, 128), 128, 0, s>>>(records, count, bodies_per_type, peer_delta, flags);
+}
 void launch_fill_i32(int32_t* p, size_t n, int32_t v, cudaStream_t s) {
     if (n == 0) return;
     fill_i32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, n, v);

@@ -68,6 +68,8 @@ void launch_shard_exchange(const uint32_t* pushes, int push_count, int what, con
 // Peer sharding, fused pushes: peer_masks[i] = ranks other than `rank` that reference the dynamic body of device reference refs[i] (0 for empty and
 // kinematic slots); body_masks[b] has bit r set when rank r references body b.
 void launch_fill_peer_masks(const int32_t* refs, uint32_t* peer_masks, size_t count, const uint8_t* body_masks, int rank, cudaStream_t s);
+// flags[i] = 1 when any lane of work record i has a non-empty destination mask (a "boundary" bundle, see ShardStage).
+void launch_boundary_flags(const WorkRecord* records, int count, const int32_t* bodies_per_type, long long peer_delta, uint8_t* flags, cudaStream_t s);
 
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
 constexpr int kLaunchPdl = 1, kLaunchPrefetchRows = 2;
@@ -90,7 +92,7 @@ struct SolverLaunchers {
     // Peer-sharded WarmStartFirst / WarmStart / Solve stage: like constraint_stage, and every written body record also goes to the ranks named by the
     // per-(lane, slot) destination masks at refs + peer_delta (launch_fill_peer_masks).
     void (*constraint_stage_sharded)(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
-                                     long long peer_delta, cudaStream_t s);
+                                     long long peer_delta, const ShardStage& shard, cudaStream_t s);
 };
 const SolverLaunchers* get_launchers_bepu_fast();
 const SolverLaunchers* get_launchers_bepu_strict();

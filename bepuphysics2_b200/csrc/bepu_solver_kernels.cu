@@ -15,9 +15,9 @@ namespace BEPU_NS {
 void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
 void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
 void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
-void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s);
-void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s);
-void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s);
+void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
+void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
+void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
 int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                            unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
 int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
@@ -52,7 +52,7 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
 }
 template <int STAGE, int MINB>
 static void launch_stage_variant_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
-                                         cudaStream_t s) {
+                                         const ShardStage& shard, cudaStream_t s) {
     static bool carveout_set[64] = {};
     int device = 0;
     cudaGetDevice(&device);
@@ -71,13 +71,13 @@ static void launch_stage_variant_sharded(const WorkRecord* records, int work_cou
     cfg.attrs = attr;
     cfg.numAttrs = (launch_flags & bepucuda::kLaunchPdl) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, constraint_stage_kernel_sharded<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0, peers,
-                       peer_delta);
+                       peer_delta, shard);
 }
 template <int STAGE>
 static void launch_stage_sharded_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
-                                   cudaStream_t s) {
-    if (work_count >= kDeepBatchBundles) launch_stage_variant_sharded<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
-    else launch_stage_variant_sharded<STAGE, 1>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+                                   const ShardStage& shard, cudaStream_t s) {
+    if (work_count >= kDeepBatchBundles) launch_stage_variant_sharded<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
+    else launch_stage_variant_sharded<STAGE, 1>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 template <int STAGE>
 static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
@@ -90,22 +90,22 @@ static void launch_stage_t(const WorkRecord* records, int work_count, const Body
 void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, s);
 }
-void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s) {
-    launch_stage_sharded_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
+    launch_stage_sharded_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 #elif BEPU_UNIT == 1
 void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     launch_stage_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, s);
 }
-void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s) {
-    launch_stage_sharded_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
+    launch_stage_sharded_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 #elif BEPU_UNIT == 2
 void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     launch_stage_t<kStageSolve>(records, work_count, B, fp, launch_flags, s);
 }
-void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, cudaStream_t s) {
-    launch_stage_sharded_t<kStageSolve>(records, work_count, B, fp, launch_flags, peers, peer_delta, s);
+void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
+    launch_stage_sharded_t<kStageSolve>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 #elif BEPU_UNIT == 3
 static void launch_constraint_stage(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
@@ -119,12 +119,12 @@ static void launch_constraint_stage(int stage, const WorkRecord* records, int wo
     }
 }
 static void launch_constraint_stage_sharded(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
-                                            long long peer_delta, cudaStream_t s) {
+                                            long long peer_delta, const ShardStage& shard, cudaStream_t s) {
     if (work_count <= 0) return;
     switch (stage) {
-        case kStageWarmStartFirst: launch_stage_warm_start_first_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, s); break;
-        case kStageWarmStart: launch_stage_warm_start_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, s); break;
-        case kStageSolve: launch_stage_solve_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, s); break;
+        case kStageWarmStartFirst: launch_stage_warm_start_first_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
+        case kStageWarmStart: launch_stage_warm_start_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
+        case kStageSolve: launch_stage_solve_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
         default: break;
     }
 }

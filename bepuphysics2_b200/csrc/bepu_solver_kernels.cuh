@@ -321,9 +321,24 @@ constexpr int kStageBlockThreads = BEPU_STAGE_BLOCK_THREADS;
 // contact update, which rewrites depth rows, nor a stage of this same batch, which rewrites these impulses) -- the whole row block. That takes the
 // bulk copy's latency off the critical path; after the wait only the body gather, the math and the scatter remain.
 constexpr int kStagePrefetchRows = 1;
+// Flag barrier pieces of the sharded stages (ShardStage). Lanes 0..rank_count-1 of one warp each talk to one peer.
+BEPU_DI void shard_signal(const ShardPeers& peers, int lane, unsigned long long seq) {
+    if (lane < peers.rank_count && lane != peers.rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[lane] + peers.rank), "l"(seq) : "memory");
+}
+BEPU_DI void shard_wait(const ShardPeers& peers, int lane, unsigned long long seq, int32_t* error_flag) {
+    if (lane < peers.rank_count && lane != peers.rank) {
+        unsigned long long seen;
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(peers.flags[peers.rank] + lane) : "memory");
+        } while (seen < seq && ++spins < 100000000u);
+        if (seen < seq) atomicExch(error_flag, 5);  // a peer never arrived: results are void
+    }
+    __syncwarp();
+}
 template <int STAGE, bool kSharded>
 BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int work_count, const BodyBuffers& B, const FrameParams* __restrict__ fpp, int flags, const ShardPeers* peers,
-                                   long long peer_delta) {
+                                   long long peer_delta, const ShardStage* shard = nullptr) {
     constexpr bool kStaged = STAGE != kStageIncremental;
     constexpr int kWarps = kStageBlockThreads / 32;
     __shared__ __align__(128) float slab[kStaged ? kWarps * kStageSlabRows * kLanes : 1];
@@ -360,6 +375,13 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
     const FrameParams fp = *fpp;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
+    bool boundary = false;
+    if constexpr (kSharded) {
+        if (shard->boundary_count == 0 && global_warp == 0) shard_signal(*peers, lane, (unsigned long long)fp.exchange_base + shard->exchange_index + 1ull);  // nothing to push here
+        boundary = active && (rec.live_lanes & kRecordBoundaryBit) != 0;
+        // records other ranks pushed in the previous exchange point are read below: all of them must have arrived
+        if (boundary && shard->exchange_index > 0) shard_wait(*peers, lane, (unsigned long long)fp.exchange_base + shard->exchange_index, shard->error_flag);
+    }
     if (!active) return;
     if constexpr (kStaged) {
         if (!early_rows && lane == 0) {
@@ -371,6 +393,19 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
         __syncwarp();
         run_bundle_rows<STAGE, kSharded>(rec, lane, StagedRows{slab_addr + lane * 4, bar, 0u}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp,
                                          peers, peer_delta);
+        if constexpr (kSharded) {
+            if (boundary) {
+                __threadfence_system();  // this warp's peer stores have landed ...
+                __syncwarp();
+                unsigned int arrived = 0;
+                if (lane == 0) arrived = atomicAdd(shard->counter, 1u) + 1u;  // ... before it counts itself off
+                arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
+                if (arrived == (unsigned int)shard->boundary_count) {
+                    __threadfence();  // the other boundary warps' count-offs (and the stores fenced before them) are ordered before the signal
+                    shard_signal(*peers, lane, (unsigned long long)fp.exchange_base + shard->exchange_index + 1ull);
+                }
+            }
+        }
     } else {
         run_bundle<STAGE>(rec, lane, enc0, enc1, B, fp);
     }
@@ -384,8 +419,8 @@ __global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_ker
 template <int STAGE, int MINB>
 __global__ void __launch_bounds__(kStageBlockThreads, MINB)
 constraint_stage_kernel_sharded(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags, const __grid_constant__ ShardPeers peers,
-                                long long peer_delta) {
-    constraint_stage_body<STAGE, true>(records, work_count, B, fpp, flags, &peers, peer_delta);
+                                long long peer_delta, const __grid_constant__ ShardStage shard) {
+    constraint_stage_body<STAGE, true>(records, work_count, B, fpp, flags, &peers, peer_delta, &shard);
 }
 
 // IntegrateKinematicVelocities / IntegrateKinematicPosesAndVelocities (PoseIntegrator.cs:L451-487, L493-535)

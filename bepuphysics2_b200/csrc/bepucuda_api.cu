@@ -178,7 +178,8 @@ struct bepucuda_ctx {
     // peer sharding (bepucuda_shard_*): one constraint graph over several GPUs with NVLink peer stores and a flag barrier per stage
     bool peer_mode = false;
     ShardPeers peers{};
-    DeviceBuffer shard_flags, pushes_dev, peer32, body_masks_dev;
+    DeviceBuffer shard_flags, pushes_dev, peer32, body_masks_dev, shard_counters, boundary_flags_dev;
+    std::vector<int> boundary_count;                                // per device batch: bundles that touch a body another rank references
     std::vector<uint8_t> body_masks;                                // bepucuda_shard_set_body_masks: fused pushes from the stage kernels
     size_t refs_words = 0;
     std::vector<void*> opened_ipc;
@@ -330,6 +331,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
         cudaMemsetAsync(ctx->error_dev.ptr, 0, 32, s);  // stall report of this solve (see report_stall)
         ++n;
     }
+    if (fused_pushes) { cudaMemsetAsync(ctx->shard_counters.ptr, 0, ctx->program.size() * 4 + 4, s); ++n; }  // count-off counters of this solve's exchange points
     for (const StageOp& op : ctx->program) {
         if (op.pad == 1 && op.stage <= kStageSolve) {
             // dataflow pass (BEPUCUDA_EXEC_DATAFLOW)
@@ -356,9 +358,17 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
                 // row prefetch in the prologue: the exchange kernel between two stages writes no rows, so the rule of the single-GPU sequence applies
                 bool prefetch = previous != nullptr && previous->stage != kStageIncremental && !(previous->stage <= kStageSolve && previous->work_begin == op.work_begin && previous->work_count > 0);
                 const int launch_flags = (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0);
-                if (fused_pushes) ctx->launchers->constraint_stage_sharded(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, ctx->peers,
-                                                                          (long long)(ctx->peer32.as<int32_t>() - ctx->refs32.as<int32_t>()), s);
-                else ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, s);
+                if (fused_pushes) {
+                    // the stage pushes, signals and (in its boundary bundles) waits itself: no exchange kernel
+                    const ShardStage shard{ctx->shard_counters.as<unsigned int>() + exchange_index, ctx->boundary_count[(size_t)(op.pad - 2)], exchange_index, ctx->error_dev.as<int32_t>()};
+                    ctx->launchers->constraint_stage_sharded(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, ctx->peers,
+                                                             (long long)(ctx->peer32.as<int32_t>() - ctx->refs32.as<int32_t>()), shard, s);
+                    ++exchange_index;
+                    ++n;
+                    previous = &op;
+                    continue;
+                }
+                ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, s);
                 ++n;
             }
             const auto& range = ctx->push_range[op.pad - 2];
@@ -444,6 +454,7 @@ void build_program(bepucuda_ctx* ctx) {
 
 int upload_program(bepucuda_ctx* ctx) {
     build_program(ctx);
+    if (ctx->peer_mode) CK(ctx->shard_counters.reserve(ctx->program.size() * 4 + 16));
     CK(ctx->program_dev.reserve(ctx->program.size() * sizeof(StageOp)));
     CK(cudaMemcpyAsync(ctx->program_dev.ptr, ctx->program.data(), ctx->program.size() * sizeof(StageOp), cudaMemcpyHostToDevice, ctx->stream));
     // The copy source is a std::vector: make sure the DMA read it before anyone mutates it.
@@ -570,7 +581,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
     for (void* p : ctx->opened_ipc) cudaIpcCloseMemHandle(p);
-    DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->peer32, &ctx->body_masks_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
+    DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->peer32, &ctx->body_masks_dev, &ctx->shard_counters, &ctx->boundary_flags_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
                             &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
@@ -1043,6 +1054,31 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
         CK(ctx->body_masks_dev.reserve((size_t)ctx->body_count + 16));
         CK(cudaMemcpyAsync(ctx->body_masks_dev.ptr, ctx->body_masks.data(), (size_t)ctx->body_count, cudaMemcpyHostToDevice, ctx->stream));
         launch_fill_peer_masks(ctx->refs32.as<int32_t>(), ctx->peer32.as<uint32_t>(), ctx->refs_words, ctx->body_masks_dev.as<uint8_t>(), ctx->peers.rank, ctx->stream);
+        // boundary bundles (any lane writes a shared body) go to the front of their batch and carry kRecordBoundaryBit: they are scheduled first, and
+        // the flag barrier of the stage involves only them (ShardStage)
+        const int n_rec = ctx->all_work_count;
+        CK(ctx->boundary_flags_dev.reserve((size_t)n_rec + 16));
+        launch_boundary_flags(ctx->record_table.as<WorkRecord>(), n_rec, ctx->bodies_per_type.as<int32_t>(), (long long)(ctx->peer32.as<int32_t>() - ctx->refs32.as<int32_t>()),
+                              ctx->boundary_flags_dev.as<uint8_t>(), ctx->stream);
+        std::vector<uint8_t> is_boundary((size_t)n_rec);
+        if (n_rec > 0) CK(cudaMemcpyAsync(is_boundary.data(), ctx->boundary_flags_dev.ptr, (size_t)n_rec, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->boundary_count.assign(ctx->batch_work.size(), 0);
+        std::vector<WorkRecord> sorted;
+        for (size_t b = 0; b < ctx->batch_work.size(); ++b) {
+            const int begin = ctx->batch_work[b].first, count = ctx->batch_work[b].second;
+            sorted.clear();
+            for (int pass = 0; pass < 2; ++pass)
+                for (int i = begin; i < begin + count; ++i)
+                    if ((is_boundary[(size_t)i] != 0) == (pass == 0)) {
+                        WorkRecord r = ctx->records[(size_t)i];
+                        r.live_lanes = (r.live_lanes & ~kRecordBoundaryBit) | (pass == 0 ? kRecordBoundaryBit : 0);
+                        sorted.push_back(r);
+                        ctx->boundary_count[b] += pass == 0;
+                    }
+            std::copy(sorted.begin(), sorted.end(), ctx->records.begin() + begin);
+        }
+        if (n_rec > 0) CK(cudaMemcpyAsync(ctx->record_table.ptr, ctx->records.data(), (size_t)n_rec * sizeof(WorkRecord), cudaMemcpyHostToDevice, ctx->stream));
     }
     CK(cudaGetLastError());
     int32_t err = 0;

@@ -159,6 +159,11 @@ BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc
     if constexpr (NB > 1) enc[1] = enc1;
 #pragma unroll
     for (int s = 2; s < NB; ++s) enc[s] = (uint32_t)__ldg(refs + s * kLanes);
+    uint32_t push_to[kSharded ? NB : 1];  // ranks that need what this lane writes to body slot s; interior bundles (peer_delta == 0) have none
+    if constexpr (kSharded) {
+#pragma unroll
+        for (int s = 0; s < NB; ++s) push_to[s] = peer_delta != 0 ? ldg_nc_u32(refs + peer_delta + s * kLanes) : 0u;
+    }
     if ((int32_t)enc[0] == kRefEmpty) return;  // trailing lane of the last bundle, or a hole in a fallback bundle
     BodyState b[NB];
     Velocity v[NB];
@@ -181,7 +186,7 @@ BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc
             if (!(enc[s] & kRefKinematicBit)) {
                 store_velocity(B.velocity, enc[s] & kRefIndexMask, v[s]);
                 if constexpr (kSharded) {
-                    const uint32_t mask = ldg_nc_u32(refs + peer_delta + s * kLanes);
+                    const uint32_t mask = push_to[s];
                     if (mask) push_record(peers->velocity, mask, enc[s] & kRefIndexMask, v[s].lin.x, v[s].lin.y, v[s].lin.z, 0.0f, v[s].ang.x, v[s].ang.y, v[s].ang.z, 0.0f);
                 }
             }
@@ -196,7 +201,7 @@ BEPU_DI void run_lane(const int32_t* refs, PR p, AR a, float* p_rw, uint32_t enc
                 const uint32_t idx = enc[s] & kRefIndexMask;
                 store_velocity(B.velocity, idx, v[s]);
                 if constexpr (kSharded) {
-                    const uint32_t mask = ldg_nc_u32(refs + peer_delta + s * kLanes);
+                    const uint32_t mask = push_to[s];
                     if (mask) {
                         push_record(peers->velocity, mask, idx, v[s].lin.x, v[s].lin.y, v[s].lin.z, 0.0f, v[s].ang.x, v[s].ang.y, v[s].ang.z, 0.0f);
                         if (enc[s] & kRefIntegrateBit) {  // this lane integrated the body: its new world inertia (and pose) travel too
@@ -392,7 +397,7 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
         }
         __syncwarp();
         run_bundle_rows<STAGE, kSharded>(rec, lane, StagedRows{slab_addr + lane * 4, bar, 0u}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp,
-                                         peers, peer_delta);
+                                         peers, boundary ? peer_delta : 0);
         if constexpr (kSharded) {
             if (boundary) {
                 __threadfence_system();  // this warp's peer stores have landed ...

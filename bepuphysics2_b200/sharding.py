@@ -59,6 +59,10 @@ def partition(simulation, rank_count):
             mine = np.flatnonzero(owner == r)
             if mine.size == 0:
                 continue
+            # constraints that write a body another rank references go first: they fill few bundles, which the device schedules ahead of the rest
+            # and which alone take part in the stage's flag barrier (ShardStage in bepu_device_types.h)
+            boundary = (((masks[idx[mine]] & ~np.uint8(1 << r)) != 0) & dynamic[mine]).any(axis=1)
+            mine = np.concatenate([mine[boundary], mine[~boundary]])
             m = mine.size
             bundles = (m + W - 1) // W
 

@@ -11,9 +11,9 @@ timeout 900 $T --bodies 100000 --substeps 8 --iterations 2 --frames 2 --check >>
 echo "== check 20k push lists" >> $L
 timeout 600 $T --bodies 20000 --check --push-lists >> $L 2>&1
 echo "== bench 1M 4x2, 2 GPUs fused" >> $L
-BEPUCUDA_TUNE=0,0,0,1 timeout 600 $T --bodies 1000000 --substeps 4 --iterations 2 --steps 10 >> $L 2>&1
-echo "== bench 1M 4x2, 2 GPUs push lists" >> $L
-timeout 600 $T --bodies 1000000 --substeps 4 --iterations 2 --steps 10 --push-lists >> $L 2>&1
+timeout 600 $T --bodies 1000000 --substeps 4 --iterations 2 --steps 10 >> $L 2>&1
+echo "== bench 1M 8x2, 2 GPUs fused" >> $L
+timeout 600 $T --bodies 1000000 --substeps 8 --iterations 2 --steps 10 >> $L 2>&1
 echo "== bench 1M 4x2, 1 GPU peer mode" >> $L
 timeout 600 $T1 --bodies 1000000 --substeps 4 --iterations 2 --steps 10 >> $L 2>&1
 echo "== bench 100k 8x2, 2 GPUs fused" >> $L

@@ -63,6 +63,7 @@ struct FrameParams {
     int32_t integrate_velocity_for_kinematics;
     uint32_t pass_base;        // dataflow mode: number of WarmStart/Solve passes executed since the body versions were last reset
     uint32_t exchange_base;    // peer sharding: number of cross-GPU exchange points executed before this solve (the flag barrier counts them)
+    uint32_t shard_solve_index;  // peer sharding: solves since the arrival targets were last published (the arrival counters keep counting)
     int32_t tune[4];           // development knobs (env BEPUCUDA_TUNE=a,b,c,d; 0 = built-in default), never set in production
 };
 
@@ -127,15 +128,21 @@ struct ShardPeers {
     int32_t rank, rank_count;
 };
 // One sharded stage = one exchange point. Bundles that touch a body another rank references ("boundary" bundles, kRecordBoundaryBit in
-// WorkRecord::live_lanes, sorted to the front of the batch) first wait for every peer's signal of the previous exchange point, and count themselves
-// off on `counter` when their peer stores are out; the last one signals this exchange point to every peer. Interior bundles neither wait nor count,
-// so the NVLink round trip hides behind them.
+// WorkRecord::live_lanes, sorted to the front of the batch) first wait until every peer's boundary bundles of all earlier exchange points have
+// arrived, and announce their own arrival to every peer (one fire-and-forget red.add over NVLink) once their peer stores are out. Interior bundles
+// neither wait nor announce, so the NVLink round trip hides behind them. A rank's flag block (u64 slots):
+//   [0, 8)  barrier flags, slot w written by rank w (shard_exchange_kernel)      [8, 12) development accumulators
+//   [16, 24) arrival counters, slot w incremented by rank w's boundary bundles
+//   [32 + w * kShardMaxExchanges ...) rank w's arrival targets: slot e = its boundary bundles through exchange point e of one solve, cumulative;
+//                                     the last slot holds the per-solve total
 struct ShardStage {
-    unsigned int* counter;
-    int32_t boundary_count;
     uint32_t exchange_index;
     int32_t* error_flag;
 };
+constexpr int kShardCounterSlot = 16;
+constexpr int kShardTargetSlot = 32;
+constexpr int kShardMaxExchanges = 4096;
+constexpr size_t kShardFlagBlockWords = kShardTargetSlot + (size_t)kMaxShardRanks * kShardMaxExchanges;
 constexpr int32_t kRecordBoundaryBit = 1 << 30;
 // One entry per (body written by this rank in a batch, destination rank): packed as body | rank << 28 | owner << 31.
 constexpr uint32_t kPushOwnerBit = 1u << 31;

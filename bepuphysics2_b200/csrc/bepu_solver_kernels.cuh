@@ -326,18 +326,22 @@ constexpr int kStageBlockThreads = BEPU_STAGE_BLOCK_THREADS;
 // contact update, which rewrites depth rows, nor a stage of this same batch, which rewrites these impulses) -- the whole row block. That takes the
 // bulk copy's latency off the critical path; after the wait only the body gather, the math and the scatter remain.
 constexpr int kStagePrefetchRows = 1;
-// Flag barrier pieces of the sharded stages (ShardStage). Lanes 0..rank_count-1 of one warp each talk to one peer.
-BEPU_DI void shard_signal(const ShardPeers& peers, int lane, unsigned long long seq) {
-    if (lane < peers.rank_count && lane != peers.rank) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.flags[lane] + peers.rank), "l"(seq) : "memory");
+// Arrival counting of the sharded stages (ShardStage). Lanes 0..rank_count-1 of a boundary warp each talk to one peer.
+BEPU_DI void shard_announce(const ShardPeers& peers, int lane) {
+    if (lane < peers.rank_count && lane != peers.rank)
+        asm volatile("red.relaxed.sys.global.add.u64 [%0], 1;" ::"l"(peers.flags[lane] + kShardCounterSlot + peers.rank) : "memory");
 }
-BEPU_DI void shard_wait(const ShardPeers& peers, int lane, unsigned long long seq, int32_t* error_flag) {
+BEPU_DI void shard_wait(const ShardPeers& peers, int lane, uint32_t solve_index, uint32_t exchange_point, int32_t* error_flag) {
     if (lane < peers.rank_count && lane != peers.rank) {
+        const unsigned long long* mine = peers.flags[peers.rank];
+        const unsigned long long* targets = mine + kShardTargetSlot + (size_t)lane * kShardMaxExchanges;
+        const unsigned long long want = (unsigned long long)solve_index * targets[kShardMaxExchanges - 1] + targets[exchange_point];
         unsigned long long seen;
         unsigned int spins = 0;
         do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(peers.flags[peers.rank] + lane) : "memory");
-        } while (seen < seq && ++spins < 100000000u);
-        if (seen < seq) atomicExch(error_flag, 5);  // a peer never arrived: results are void
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine + kShardCounterSlot + lane) : "memory");
+        } while (seen < want && ++spins < 100000000u);
+        if (seen < want) atomicExch(error_flag, 5);  // a peer never arrived: results are void
     }
     __syncwarp();
 }
@@ -382,10 +386,9 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
     asm volatile("griddepcontrol.launch_dependents;");
     bool boundary = false;
     if constexpr (kSharded) {
-        if (shard->boundary_count == 0 && global_warp == 0) shard_signal(*peers, lane, (unsigned long long)fp.exchange_base + shard->exchange_index + 1ull);  // nothing to push here
         boundary = active && (rec.live_lanes & kRecordBoundaryBit) != 0;
         // records other ranks pushed in the previous exchange point are read below: all of them must have arrived
-        if (boundary && shard->exchange_index > 0) shard_wait(*peers, lane, (unsigned long long)fp.exchange_base + shard->exchange_index, shard->error_flag);
+        if (boundary && shard->exchange_index > 0 && !(fp.tune[0] & 1)) shard_wait(*peers, lane, fp.shard_solve_index, shard->exchange_index - 1u, shard->error_flag);
     }
     if (!active) return;
     if constexpr (kStaged) {
@@ -397,18 +400,12 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
         }
         __syncwarp();
         run_bundle_rows<STAGE, kSharded>(rec, lane, StagedRows{slab_addr + lane * 4, bar, 0u}, StagedAcc{slab_addr + prestep_bytes + lane * 4, rec.impulses + lane}, enc0, enc1, B, fp,
-                                         peers, boundary ? peer_delta : 0);
+                                         peers, boundary && !(fp.tune[0] & 4) ? peer_delta : 0);
         if constexpr (kSharded) {
-            if (boundary) {
-                __threadfence_system();  // this warp's peer stores have landed ...
+            if (boundary && !(fp.tune[0] & 2)) {  // (tune[0]: development knob for A/B timing -- 1 no waits, 2 no announcements, 4 no peer stores; results are void)
+                __threadfence_system();  // every lane's peer stores have landed ...
                 __syncwarp();
-                unsigned int arrived = 0;
-                if (lane == 0) arrived = atomicAdd(shard->counter, 1u) + 1u;  // ... before it counts itself off
-                arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
-                if (arrived == (unsigned int)shard->boundary_count) {
-                    __threadfence();  // the other boundary warps' count-offs (and the stores fenced before them) are ordered before the signal
-                    shard_signal(*peers, lane, (unsigned long long)fp.exchange_base + shard->exchange_index + 1ull);
-                }
+                shard_announce(*peers, lane);  // ... before the warp counts as arrived
             }
         }
     } else {

@@ -178,7 +178,8 @@ struct bepucuda_ctx {
     // peer sharding (bepucuda_shard_*): one constraint graph over several GPUs with NVLink peer stores and a flag barrier per stage
     bool peer_mode = false;
     ShardPeers peers{};
-    DeviceBuffer shard_flags, pushes_dev, peer32, body_masks_dev, shard_counters, boundary_flags_dev;
+    DeviceBuffer shard_flags, pushes_dev, peer32, body_masks_dev, boundary_flags_dev;
+    uint32_t shard_solve_index = 0;                                 // solves since the arrival targets were last published
     std::vector<int> boundary_count;                                // per device batch: bundles that touch a body another rank references
     std::vector<uint8_t> body_masks;                                // bepucuda_shard_set_body_masks: fused pushes from the stage kernels
     size_t refs_words = 0;
@@ -331,7 +332,6 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
         cudaMemsetAsync(ctx->error_dev.ptr, 0, 32, s);  // stall report of this solve (see report_stall)
         ++n;
     }
-    if (fused_pushes) { cudaMemsetAsync(ctx->shard_counters.ptr, 0, ctx->program.size() * 4 + 4, s); ++n; }  // count-off counters of this solve's exchange points
     for (const StageOp& op : ctx->program) {
         if (op.pad == 1 && op.stage <= kStageSolve) {
             // dataflow pass (BEPUCUDA_EXEC_DATAFLOW)
@@ -360,7 +360,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
                 const int launch_flags = (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0);
                 if (fused_pushes) {
                     // the stage pushes, signals and (in its boundary bundles) waits itself: no exchange kernel
-                    const ShardStage shard{ctx->shard_counters.as<unsigned int>() + exchange_index, ctx->boundary_count[(size_t)(op.pad - 2)], exchange_index, ctx->error_dev.as<int32_t>()};
+                    const ShardStage shard{exchange_index, ctx->error_dev.as<int32_t>()};
                     ctx->launchers->constraint_stage_sharded(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, ctx->peers,
                                                              (long long)(ctx->peer32.as<int32_t>() - ctx->refs32.as<int32_t>()), shard, s);
                     ++exchange_index;
@@ -371,8 +371,9 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
                 ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, s);
                 ++n;
             }
+            if (fused_pushes) { ++exchange_index; continue; }  // no constraint of this batch here: nothing arrives from this rank, its targets say so
             const auto& range = ctx->push_range[op.pad - 2];
-            launch_shard_exchange(ctx->pushes_dev.as<uint32_t>() + range.first, fused_pushes ? 0 : range.second, op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2), ctx->B, ctx->peers, fp,
+            launch_shard_exchange(ctx->pushes_dev.as<uint32_t>() + range.first, range.second, op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2), ctx->B, ctx->peers, fp,
                                   exchange_index++, ctx->error_dev.as<int32_t>(), s);
             ++n;
             if (op.work_count > 0) previous = &op;
@@ -454,7 +455,26 @@ void build_program(bepucuda_ctx* ctx) {
 
 int upload_program(bepucuda_ctx* ctx) {
     build_program(ctx);
-    if (ctx->peer_mode) CK(ctx->shard_counters.reserve(ctx->program.size() * 4 + 16));
+    if (ctx->peer_mode && !ctx->body_masks.empty() && ctx->boundary_count.size() == ctx->batch_work.size()) {
+        // fused pushes: publish, to every peer, how many boundary bundles of this rank arrive through each exchange point of one solve (ShardStage),
+        // and restart the arrival counters other ranks increment here. Every rank does this for the same program, between solves.
+        std::vector<unsigned long long> targets((size_t)kShardMaxExchanges, 0ull);
+        unsigned long long arrived = 0;
+        size_t e = 0;
+        for (const StageOp& op : ctx->program) {
+            if (op.pad != -1 && !(op.pad >= 2 && op.stage <= kStageSolve)) continue;
+            if (e + 1 >= (size_t)kShardMaxExchanges) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "peer sharding: more than 4095 exchange points per solve");
+            if (op.pad >= 2 && op.work_count > 0) arrived += (unsigned long long)ctx->boundary_count[(size_t)(op.pad - 2)];
+            targets[e++] = arrived;
+        }
+        targets[(size_t)kShardMaxExchanges - 1] = arrived;
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int q = 0; q < ctx->peers.rank_count; ++q)
+            if (q != ctx->peers.rank)
+                CK(cudaMemcpy(ctx->peers.flags[q] + kShardTargetSlot + (size_t)ctx->peers.rank * kShardMaxExchanges, targets.data(), targets.size() * 8, cudaMemcpyDefault));
+        CK(cudaMemset((unsigned long long*)ctx->shard_flags.ptr + kShardCounterSlot, 0, kMaxShardRanks * 8));
+        ctx->shard_solve_index = 0;
+    }
     CK(ctx->program_dev.reserve(ctx->program.size() * sizeof(StageOp)));
     CK(cudaMemcpyAsync(ctx->program_dev.ptr, ctx->program.data(), ctx->program.size() * sizeof(StageOp), cudaMemcpyHostToDevice, ctx->stream));
     // The copy source is a std::vector: make sure the DMA read it before anyone mutates it.
@@ -581,7 +601,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     invalidate_graph(ctx);
     for (void* p : ctx->opened_ipc) cudaIpcCloseMemHandle(p);
-    DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->peer32, &ctx->body_masks_dev, &ctx->shard_counters, &ctx->boundary_flags_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
+    DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->peer32, &ctx->body_masks_dev, &ctx->boundary_flags_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
                             &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
@@ -1248,6 +1268,7 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     }
     ctx->frame_params_host->pass_base = ctx->pass_counter;
     ctx->frame_params_host->exchange_base = ctx->exchange_counter;
+    ctx->frame_params_host->shard_solve_index = ctx->shard_solve_index;
     CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
 
     if (ctx->peer_mode && ctx->cfg.execution_mode != BEPUCUDA_EXEC_GRAPH && ctx->cfg.execution_mode != BEPUCUDA_EXEC_STREAM)
@@ -1303,7 +1324,7 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     CK(cudaEventRecord(ctx->ev_solve_end, ctx->stream));
     if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW)
         for (int it : ctx->iterations) ctx->pass_counter += (uint32_t)it + 1u;  // body versions keep counting across solves
-    if (ctx->peer_mode) ctx->exchange_counter += ctx->exchanges_per_solve;      // the flag barrier keeps counting across solves
+    if (ctx->peer_mode) { ctx->exchange_counter += ctx->exchanges_per_solve; ++ctx->shard_solve_index; }  // the flag barrier and the arrival counters keep counting across solves
     ctx->have_solve = true;
     ctx->timings.kernel_launches = launches;
 
@@ -1499,8 +1520,8 @@ int32_t bepucuda_shard_export(bepucuda_ctx* ctx, bepucuda_ipc_handles* out) {
     if (!ctx || !out) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_export: bad arguments");
     if (ctx->body_count <= 0) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "shard_export before upload_bodies");
     CK(cudaSetDevice(ctx->device));
-    CK(ctx->shard_flags.reserve((kMaxShardRanks + 4) * sizeof(unsigned long long)));  // flag slots + four development accumulators
-    CK(cudaMemset(ctx->shard_flags.ptr, 0, (kMaxShardRanks + 4) * sizeof(unsigned long long)));
+    CK(ctx->shard_flags.reserve(kShardFlagBlockWords * sizeof(unsigned long long)));  // barrier flags, arrival counters and targets (ShardStage)
+    CK(cudaMemset(ctx->shard_flags.ptr, 0, kShardFlagBlockWords * sizeof(unsigned long long)));
     void* ptrs[4] = {ctx->pose.ptr, ctx->velocity.ptr, ctx->inertia_world.ptr, ctx->shard_flags.ptr};
     for (int i = 0; i < 4; ++i) {
         cudaIpcMemHandle_t h;

@@ -329,7 +329,7 @@ constexpr int kStagePrefetchRows = 1;
 // Arrival counting of the sharded stages (ShardStage). Lanes 0..rank_count-1 of a boundary warp each talk to one peer.
 BEPU_DI void shard_announce(const ShardPeers& peers, int lane) {
     if (lane < peers.rank_count && lane != peers.rank)
-        asm volatile("red.relaxed.sys.global.add.u64 [%0], 1;" ::"l"(peers.flags[lane] + kShardCounterSlot + peers.rank) : "memory");
+        asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(peers.flags[lane] + kShardCounterSlot + peers.rank) : "memory");
 }
 BEPU_DI void shard_wait(const ShardPeers& peers, int lane, uint32_t solve_index, uint32_t exchange_point, int32_t* error_flag) {
     if (lane < peers.rank_count && lane != peers.rank) {
@@ -403,9 +403,8 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
                                          peers, boundary && !(fp.tune[0] & 4) ? peer_delta : 0);
         if constexpr (kSharded) {
             if (boundary && !(fp.tune[0] & 2)) {  // (tune[0]: development knob for A/B timing -- 1 no waits, 2 no announcements, 4 no peer stores; results are void)
-                __threadfence_system();  // every lane's peer stores have landed ...
-                __syncwarp();
-                shard_announce(*peers, lane);  // ... before the warp counts as arrived
+                __syncwarp();                  // every lane's peer stores are ordered before ...
+                shard_announce(*peers, lane);  // ... the release that counts the warp as arrived
             }
         }
     } else {

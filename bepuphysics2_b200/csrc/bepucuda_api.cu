@@ -345,8 +345,9 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
             continue;
         }
         if (ctx->peer_mode && op.pad == -1) {
-            // all ranks meet (nothing to push): before the first stage of a solve, and between the incremental contact update -- which reads the
-            // velocities of shared bodies -- and the WarmStart stages whose results peers store into this rank's arrays
+            // all ranks meet (nothing to push): before the first stage of a solve; around the incremental contact update, which reads the velocities
+            // of shared bodies -- after every peer's last Solve stage has completed, before any peer's WarmStart stage stores into this rank's
+            // arrays; and before the final pose pass
             launch_shard_exchange(nullptr, 0, 1, ctx->B, ctx->peers, fp, exchange_index++, ctx->error_dev.as<int32_t>(), s);
             ++n;
             continue;
@@ -425,6 +426,8 @@ void build_program(bepucuda_ctx* ctx) {
     const int kin = (int)ctx->kinematics.size();
     for (int s = 0; s < substeps; ++s) {
         if (s > 0) {
+            // peer sharding: what peers pushed in the last Solve stages must have arrived before the contact update reads velocities (rank barrier)
+            if (ctx->peer_mode) ctx->program.push_back({kStageKinematic, 0, 0, -1});
             if (ctx->inc_work_count > 0) ctx->program.push_back({kStageIncremental, ctx->inc_work_begin, ctx->inc_work_count, 0});
             if (kin > 0) ctx->program.push_back({kStageKinematic, 0, kin, 0});
         } else if (ctx->integ.integrate_velocity_for_kinematics && kin > 0) {
@@ -450,6 +453,7 @@ void build_program(bepucuda_ctx* ctx) {
                 if (bw.second > 0 || (ctx->peer_mode && (int)b < ctx->sync_batch_count)) ctx->program.push_back({kStageSolve, bw.first, bw.second, ctx->peer_mode ? (int)b + 2 : 0});
             }
     }
+    if (ctx->peer_mode) ctx->program.push_back({kStageKinematic, 0, 0, -1});  // ... and before the final pose pass reads them
     ctx->program.push_back({kStageFinalPose, 0, ctx->body_count, 0});
 }
 

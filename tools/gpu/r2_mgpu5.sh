@@ -5,7 +5,7 @@ T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 1
 echo "== check 20k fused" > $L
 timeout 600 $T --bodies 20000 --check >> $L 2>&1
 echo "== check 100k 8x2 fused" >> $L
-timeout 900 $T --bodies 100000 --substeps 8 --iterations 2 --frames 2 --check >> $L 2>&1
+timeout 900 $T --bodies 100000 --substeps 8 --iterations 2 --frames 3 --check >> $L 2>&1
 for tune in 0 1 3; do
   for cfg in "1000000 4" "100000 8"; do
     set -- $cfg

@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--large-bodies", type=int, default=1_000_000, help="body count of the large pile in the configs block (the scene size BASELINE.json's north_star targets); 0 = skip it")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the one-graph-over-N-GPUs block")
+    ap.add_argument("--sharded-bodies", type=int, default=1_000_000, help="N > 1: body count of the pile whose single constraint graph is split over the N GPUs")
     return ap.parse_args()
 
 
@@ -216,6 +218,64 @@ def measure_config(args, overrides, torch, bp, modes, flush, peak, steps, with_c
         frames = 1 if cfg.bodies > 300_000 else 2
         cb = cpu_reference_run(cfg, steps=frames, warmup=0 if cfg.bodies > 300_000 else 1, threads=args.cpu_threads)
         out["cpu_baseline"] = {"value": cb["value"], "ms_per_step": cb["ms_per_step"], "cores": cb["cores"], "kind": "port", "sample": "%d frame(s) of this workload" % frames}
+    return out
+
+
+def measure_sharded(args, torch, dist, bp, rank, world, local_rank, flush):
+    """One pile's constraint graph over all ranks. Device time per step = max over ranks of the CUDA-event time around each rank's solve."""
+    from bepuphysics2_b200 import scenes, sharding
+
+    bodies, substeps, iterations = args.sharded_bodies, 4, 2
+    scene = scenes.shape_pile(bodies, seed=5)
+    sim = bp.Simulation(bundle_width=8, substeps=substeps, velocity_iterations=iterations)
+    scenes.build(scene, sim)
+    solver = sharding.ShardedSolver(sim, rank, world, local_rank, strict_fp=args.strict)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, solver.export_handles())
+    solver.import_handles(gathered)
+    solver.describe()
+    solver.synchronize()
+    dist.barrier()
+    steps = max(3, min(args.steps, 10))
+
+    def step():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        solver.solve(DT)
+        return solver.timings().solve_ms
+
+    for _ in range(3):
+        step()
+    ms = sum(step() for _ in range(steps)) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mine = torch.tensor([float(sum(tb["count"] for tb in solver.shard))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+    shared = int(((solver.masks & (solver.masks - 1)) != 0).sum())
+    solver.close()
+    dist.barrier()
+    out = {"workload": "shape_pile bodies=%d substeps=%d velocity_iterations=%d, one constraint graph" % (bodies, substeps, iterations), "n_gpus": world, "scaling": "strong",
+           "constraints": int(sim.constraint_count), "constraints_uploaded_over_ranks": int(mine.item()), "bodies_shared_between_ranks": shared,
+           "ms_per_step": t.item(), "value": sim.constraint_count * substeps * iterations / (t.item() * 1e-3), "unit": "constraint-iterations/s", "steps": steps,
+           "timing": "CUDA events around each rank's solve, max over ranks; L2 flushed and ranks aligned (barrier) before every step"}
+    if rank == 0:
+        # the same pile on this GPU alone, same numerics, for the strong-scaling denominator
+        ts = bp.CudaTimestepper(sim, device=local_rank, strict_fp=args.strict, execution_mode=bp.native.EXEC_GRAPH)
+        ts.describe()
+        ts.synchronize()
+
+        def single():
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            ts.solve_device_only(DT)
+            return ts.timings().solve_ms
+
+        for _ in range(3):
+            single()
+        out["single_gpu_ms_per_step"] = sum(single() for _ in range(steps)) / steps
+        ts.close()
+    dist.barrier()
     return out
 
 
@@ -425,6 +485,12 @@ def main():
         for key, overrides in side_configs(args):
             configs[key] = measure_config(args, overrides, torch, bp, modes, flush, peak_for_configs, args.config_steps, with_cpu=not args.no_cpu_baseline)
 
+    # ---- N > 1: ONE constraint graph over the N GPUs, next to the N independent islands above: the 1M-body pile of configs[4],
+    # ---- constraints split by body slab, shared body records pushed over NVLink by the stage kernels (bepucuda_shard_*); strong scaling
+    sharded = None
+    if dist is not None and not args.no_sharded and args.scene == "shape_pile":
+        sharded = measure_sharded(args, torch, dist, bp, rank, world, local_rank, flush)
+
     per_rank_ms = [total_ms / args.steps]
     if dist is not None:
         gathered = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
@@ -486,6 +552,8 @@ def main():
             line["e2e_resident_impulses"] = resident
         if configs is not None:
             line["configs"] = configs
+        if sharded is not None:
+            line["one_graph_sharded"] = sharded
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             cb = cpu_reference_run(args, steps=3, warmup=1, threads=args.cpu_threads)
             c1 = cpu_reference_run(args, steps=1, warmup=0, threads=1)  # the reference's own benchmarks run single-threaded (ShapePileBenchmark.cs:L228)

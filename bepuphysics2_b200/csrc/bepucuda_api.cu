@@ -1565,6 +1565,37 @@ int32_t bepucuda_shard_import(bepucuda_ctx* ctx, int32_t rank, int32_t rank_coun
     return BEPUCUDA_OK;
 }
 
+int32_t bepucuda_shard_import_contexts(bepucuda_ctx* ctx, int32_t rank, int32_t rank_count, bepucuda_ctx* const* all) {
+    if (!ctx || !all || rank_count < 1 || rank_count > kMaxShardRanks || rank < 0 || rank >= rank_count || all[rank] != ctx)
+        return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_import_contexts: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    ShardPeers p{};
+    p.rank = rank;
+    p.rank_count = rank_count;
+    for (int r = 0; r < rank_count; ++r) {
+        bepucuda_ctx* o = all[r];
+        if (!o || !o->shard_flags.ptr || o->body_count != ctx->body_count) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "shard_import_contexts: every context needs the same bodies and a shard_export");
+        if (o->device != ctx->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->device, o->device));
+            if (!can) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "shard_import_contexts: no peer access between the devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            (void)cudaGetLastError();
+        }
+        p.pose[r] = o->pose.as<float4>();
+        p.velocity[r] = o->velocity.as<float4>();
+        p.inertia_world[r] = o->inertia_world.as<float4>();
+        p.flags[r] = (unsigned long long*)o->shard_flags.ptr;
+    }
+    ctx->peers = p;
+    ctx->peer_mode = true;
+    ctx->exchange_counter = 0;
+    if (ctx->constraints_ready) ctx->constraints_ready = false;
+    invalidate_graph(ctx);
+    return BEPUCUDA_OK;
+}
+
 int32_t bepucuda_shard_set_global(bepucuda_ctx* ctx, const int32_t* first_batch, const uint8_t* constrained) {
     if (!ctx || !first_batch || !constrained) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "shard_set_global: bad arguments");
     ctx->global_first_batch.assign(first_batch, first_batch + ctx->body_count);

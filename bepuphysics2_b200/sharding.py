@@ -108,7 +108,7 @@ class ShardedSolver:
         self._cuda, _ = native.load_libraries()
         for name, args in (("bepucuda_shard_export", [C.c_void_p, C.POINTER(IpcHandles)]), ("bepucuda_shard_import", [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(IpcHandles)]),
                            ("bepucuda_shard_set_global", [C.c_void_p, C.c_void_p, C.c_void_p]), ("bepucuda_shard_set_pushes", [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-                           ("bepucuda_shard_set_body_masks", [C.c_void_p, C.c_void_p])):
+                           ("bepucuda_shard_set_body_masks", [C.c_void_p, C.c_void_p]), ("bepucuda_shard_import_contexts", [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)])):
             getattr(self._cuda, name).argtypes = args
         self.sim, self.rank, self.rank_count, self.fused_pushes = simulation, rank, rank_count, fused_pushes
         cfg = native.Config()
@@ -141,6 +141,11 @@ class ShardedSolver:
         for r, raw in enumerate(all_handles):
             C.memmove(C.byref(arr[r]), raw, C.sizeof(IpcHandles))
         self._check(self._cuda.bepucuda_shard_import(self._ctx, self.rank, self.rank_count, arr))
+
+    def import_contexts(self, solvers):
+        """All ranks in this process: `solvers` in rank order (each after export_handles)."""
+        arr = (C.c_void_p * self.rank_count)(*[s._ctx for s in solvers])
+        self._check(self._cuda.bepucuda_shard_import_contexts(self._ctx, self.rank, self.rank_count, arr))
 
     def describe(self):
         sim = self.sim

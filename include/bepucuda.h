@@ -236,6 +236,9 @@ typedef struct bepucuda_ipc_handles {
 } bepucuda_ipc_handles;
 int32_t bepucuda_shard_export(bepucuda_ctx* ctx, bepucuda_ipc_handles* out);
 int32_t bepucuda_shard_import(bepucuda_ctx* ctx, int32_t rank, int32_t rank_count, const bepucuda_ipc_handles* all_ranks);
+/* The same for ranks that live in ONE process (one host thread per context): the other ranks' arrays are taken from their contexts directly
+ * (peer access is enabled between different devices) instead of through IPC handles. all_ranks[rank] must be ctx itself. */
+int32_t bepucuda_shard_import_contexts(bepucuda_ctx* ctx, int32_t rank, int32_t rank_count, bepucuda_ctx* const* all_ranks);
 int32_t bepucuda_shard_set_global(bepucuda_ctx* ctx, const int32_t* first_batch_per_body, const uint8_t* constrained_per_body);
 int32_t bepucuda_shard_set_pushes(bepucuda_ctx* ctx, int32_t batch_index, int32_t count, const int32_t* body_indices, const int32_t* destination_ranks,
                                   const int32_t* owner_flags);

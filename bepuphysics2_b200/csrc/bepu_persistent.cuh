@@ -95,14 +95,19 @@ persistent_solve_kernel(const StageOp* __restrict__ program, int op_count, const
 
 static int launch_persistent(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                              unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s) {
-    static int sms = 0, max_per_sm = 0;
-    if (sms == 0) {
+    // Queried once per process (thread-safe static initialisation); every device of a node is the same part, so one answer serves all contexts.
+    struct Occupancy { int sms = 0, max_per_sm = 0, error = 0; };
+    static const Occupancy occ = [] {
+        Occupancy o;
         int device = 0;
         cudaError_t e = cudaGetDevice(&device);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, persistent_solve_kernel, kPersistentThreads, 0);
-        if (e != cudaSuccess) return (int)e;
-    }
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&o.sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o.max_per_sm, persistent_solve_kernel, kPersistentThreads, 0);
+        o.error = (int)e;
+        return o;
+    }();
+    if (occ.error != 0) return occ.error;
+    const int sms = occ.sms, max_per_sm = occ.max_per_sm;
     if (max_per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
     int per_sm = blocks_per_sm <= 0 ? 1 : blocks_per_sm;
     if (per_sm > max_per_sm) per_sm = max_per_sm;

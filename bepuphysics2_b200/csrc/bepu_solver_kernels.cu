@@ -2,6 +2,7 @@
 // so that the big per-type switch of each kernel gets its own translation unit and the build parallelises:
 //   0 WarmStartFirst stage   1 WarmStart stage   2 Solve stage   3 Incremental stage + kinematic + final pose + launcher table
 //   4 persistent kernel      5 dataflow pass kernels
+#include <atomic>
 #include "bepu_solver_kernels.cuh"
 #if BEPU_UNIT == 4
 #include "bepu_persistent.cuh"
@@ -30,7 +31,7 @@ int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, c
 constexpr int kDeepBatchBundles = 2400;  // more bundles than the uncapped build keeps resident at once (148 SMs x 16 warps)
 template <int STAGE, int MINB>
 static void launch_stage_variant(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
-    static bool carveout_set[64] = {};  // function attributes are per device: a process may hold contexts on several
+    static std::atomic<bool> carveout_set[64] = {};  // function attributes are per device: a process may hold contexts on several
     int device = 0;
     cudaGetDevice(&device);
     if (!carveout_set[device & 63]) {  // the staged stages keep one 6 KB slab per resident warp in shared memory
@@ -53,7 +54,7 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
 template <int STAGE, int MINB>
 static void launch_stage_variant_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
                                          const ShardStage& shard, cudaStream_t s) {
-    static bool carveout_set[64] = {};
+    static std::atomic<bool> carveout_set[64] = {};
     int device = 0;
     cudaGetDevice(&device);
     if (!carveout_set[device & 63]) {

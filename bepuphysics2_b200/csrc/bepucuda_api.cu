@@ -831,6 +831,12 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
             for (const SourceTypeBatch& src : ctx->sources)
                 if (src.batch_index >= ctx->fallback_threshold) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "end_constraints: the sequential fallback batch is not supported across ranks");
         }
+        if (ctx->exchange && !ctx->peer_mode) {
+            // sharded batches through the exchange callback: levels computed from one rank's constraints differ between ranks, so would the number of
+            // collectives per step (a hang), and level indices are not comparable across ranks
+            for (const SourceTypeBatch& src : ctx->sources)
+                if (src.batch_index >= ctx->fallback_threshold) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "end_constraints: the sequential fallback batch is not supported with an exchange callback");
+        }
         (void)current_batch;
         ctx->sync_batch_count = (int)batch_tbs.size();
     }
@@ -876,6 +882,19 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
                         const int32_t enc = s.host_refs[((size_t)k * nb + b) * W + l];
                         if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
                         last_level[(uint32_t)enc & kRefIndexMask] = lane_level[l];
+                    }
+                    // TypeProcessor.cs:L338-359: a fallback bundle never holds a dynamic body twice (two lanes of one level would race on its record)
+                    for (int l2 = 0; l2 < l; ++l2) {
+                        if (lane_level[l2] == 0) continue;
+                        for (int b = 0; b < nb; ++b) {
+                            const int32_t e1 = s.host_refs[((size_t)k * nb + b) * W + l];
+                            if (e1 < 0 || ((uint32_t)e1 & kRefKinematicBit)) continue;
+                            for (int b2 = 0; b2 < nb; ++b2) {
+                                const int32_t e2 = s.host_refs[((size_t)k * nb + b2) * W + l2];
+                                if (e2 >= 0 && !((uint32_t)e2 & kRefKinematicBit) && (((uint32_t)e1 ^ (uint32_t)e2) & kRefIndexMask) == 0)
+                                    return fail(ctx, BEPUCUDA_ERR_BATCH_INVARIANT, "end_constraints: a fallback bundle references the same dynamic body more than once");
+                            }
+                        }
                     }
                     slots.push_back({lane_level[l], (int)si, k * W + l});
                     ++s.live;

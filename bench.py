@@ -476,6 +476,29 @@ def main():
                     "h2d_bytes_per_step": int(tr.h2d_bytes), "d2h_bytes_per_step": int(tr.d2h_bytes),
                     "what": "every step: upload the motion half of the bodies (64 B / body) + prestep + contact feature ids, redistribute the resident impulses on the device, solve, download the motion half of the bodies"}
 
+    # ---- device-side batch colouring of this workload's constraint list: bepucuda_color_constraints vs the host mirror's
+    # ---- sequential Solver.Add batch search (C++, one thread), wall clock including the reference upload and the batch-index download
+    colouring = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        from bepuphysics2_b200 import coloring
+
+        scene_for_refs = make_scene(args, 5)
+        refs = coloring.scene_references(scene_for_refs)
+        colouring = {"constraints": int(refs.shape[0]), "what": "batch index per constraint, identical to sequential first fit in the stated order (tests/test_coloring.py)"}
+        for order, name in ((1, "hashed_order"), (0, "insertion_order")):
+            ts.color_constraints(refs, sim.body_count, 64, order=order)
+            t0 = time.perf_counter()
+            _, n_batches, rounds = ts.color_constraints(refs, sim.body_count, 64, order=order)
+            colouring[name] = {"ms": (time.perf_counter() - t0) * 1e3, "batches": int(n_batches), "device_rounds": int(rounds)}
+        from bepuphysics2_b200 import scenes as scenes_mod
+
+        host_sim = bp.Simulation(bundle_width=8, fallback_batch_threshold=64, substeps=args.substeps, velocity_iterations=args.iterations)
+        t0 = time.perf_counter()
+        scenes_mod.build(scene_for_refs, host_sim)
+        colouring["host_solver_add_ms"] = (time.perf_counter() - t0) * 1e3
+        colouring["host_solver_add_what"] = "Bodies.Add + Solver.Add of every constraint in the C++ host mirror, one thread (batch search AND writing the type batches)"
+        del host_sim
+
     configs = None
     if rank == 0 and world == 1 and not args.no_configs and args.scene == "shape_pile":
         ts.close()
@@ -550,6 +573,8 @@ def main():
             line["e2e_topology_change"] = topo
         if resident is not None:
             line["e2e_resident_impulses"] = resident
+        if colouring is not None:
+            line["device_colouring"] = colouring
         if configs is not None:
             line["configs"] = configs
         if sharded is not None:

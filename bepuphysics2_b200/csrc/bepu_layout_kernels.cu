@@ -489,6 +489,16 @@ __global__ void boundary_flags_kernel(const WorkRecord* __restrict__ records, in
     const bool any = __any_sync(0xFFFFFFFFu, m != 0);
     if (lane == 0) flags[warp] = any ? 1 : 0;
 }
+__global__ void pack_ref_rows_kernel(const WorkRecord* __restrict__ records, int count, int32_t* __restrict__ rows) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)count * 64) return;
+    // the reference arena is padded: the second row of a one-body type batch is in bounds (and ignored by the kernels)
+    rows[i] = records[i >> 6].refs[i & 63];
+}
+void launch_pack_ref_rows(const WorkRecord* records, int count, int32_t* rows, cudaStream_t s) {
+    if (count <= 0) return;
+    pack_ref_rows_kernel<<<blocks_for((size_t)count * 64, 256), 256, 0, s>>>(records, count, rows);
+}
 void launch_boundary_flags(const WorkRecord* records, int count, const int32_t* bodies_per_type, long long peer_delta, uint8_t* flags, cudaStream_t s) {
     if (count <= 0) return;
     boundary_flags_kernel<<<blocks_for((size_t)count * 32, 128), 128, 0, s>>>(records, count, bodies_per_type, peer_delta, flags);

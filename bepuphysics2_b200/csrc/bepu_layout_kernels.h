@@ -71,13 +71,18 @@ void launch_fill_peer_masks(const int32_t* refs, uint32_t* peer_masks, size_t co
 // flags[i] = 1 when any lane of work record i has a non-empty destination mask (a "boundary" bundle, see ShardStage).
 void launch_boundary_flags(const WorkRecord* records, int count, const int32_t* bodies_per_type, long long peer_delta, uint8_t* flags, cudaStream_t s);
 
+// Reference rows next to the work list: rows[i][0..1][lane] = the first two body-reference rows of work record i (64 words per record), so that a
+// solver warp fetches its work record and its body references with independent loads (one DRAM round trip instead of two).
+void launch_pack_ref_rows(const WorkRecord* records, int count, int32_t* rows, cudaStream_t s);
+
 // Numerics flavours (bepu_solver_kernels.cu, compiled twice).
 constexpr int kLaunchPdl = 1, kLaunchPrefetchRows = 2;
 struct SolverLaunchers {
     // Launches one constraint stage (kStageWarmStartFirst / kStageWarmStart / kStageSolve / kStageIncremental) over `work_count` bundles.
     // launch_flags: kLaunchPdl = launch with programmatic stream serialization (the kernel overlaps its prologue with the previous stage);
     // kLaunchPrefetchRows = the kernel launched just before this one writes neither this batch's prestep nor its impulses, so the prologue may fetch them.
-    void (*constraint_stage)(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
+    // ref_rows: the packed reference rows of records[0 .. work_count) (launch_pack_ref_rows).
+    void (*constraint_stage)(int stage, const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
     void (*kinematic_stage)(int stage, const int32_t* kinematics, int count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
     void (*final_pose)(const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
     // Persistent cooperative kernel: runs a whole stage program with a grid barrier between ops. Returns a cudaError_t.
@@ -91,7 +96,7 @@ struct SolverLaunchers {
                          uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s);
     // Peer-sharded WarmStartFirst / WarmStart / Solve stage: like constraint_stage, and every written body record also goes to the ranks named by the
     // per-(lane, slot) destination masks at refs + peer_delta (launch_fill_peer_masks).
-    void (*constraint_stage_sharded)(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
+    void (*constraint_stage_sharded)(int stage, const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
                                      long long peer_delta, const ShardStage& shard, cudaStream_t s);
 };
 const SolverLaunchers* get_launchers_bepu_fast();

@@ -13,12 +13,12 @@
 
 namespace BEPU_NS {
 
-void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
-void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
-void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
-void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
-void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
-void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
+void launch_stage_warm_start_first(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
+void launch_stage_warm_start(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
+void launch_stage_solve(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
+void launch_stage_warm_start_first_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
+void launch_stage_warm_start_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
+void launch_stage_solve_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
 int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
                            unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
 int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
@@ -30,7 +30,7 @@ int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, c
 #endif
 constexpr int kDeepBatchBundles = 2400;  // more bundles than the uncapped build keeps resident at once (148 SMs x 16 warps)
 template <int STAGE, int MINB>
-static void launch_stage_variant(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+static void launch_stage_variant(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     static std::atomic<bool> carveout_set[64] = {};  // function attributes are per device: a process may hold contexts on several
     int device = 0;
     cudaGetDevice(&device);
@@ -49,10 +49,10 @@ static void launch_stage_variant(const WorkRecord* records, int work_count, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (launch_flags & bepucuda::kLaunchPdl) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0);
+    cudaLaunchKernelEx(&cfg, constraint_stage_kernel<STAGE, MINB>, records, ref_rows, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0);
 }
 template <int STAGE, int MINB>
-static void launch_stage_variant_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
+static void launch_stage_variant_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
                                          const ShardStage& shard, cudaStream_t s) {
     static std::atomic<bool> carveout_set[64] = {};
     int device = 0;
@@ -71,61 +71,61 @@ static void launch_stage_variant_sharded(const WorkRecord* records, int work_cou
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (launch_flags & bepucuda::kLaunchPdl) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, constraint_stage_kernel_sharded<STAGE, MINB>, records, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0, peers,
+    cudaLaunchKernelEx(&cfg, constraint_stage_kernel_sharded<STAGE, MINB>, records, ref_rows, work_count, B, fp, (launch_flags & bepucuda::kLaunchPrefetchRows) ? kStagePrefetchRows : 0, peers,
                        peer_delta, shard);
 }
 template <int STAGE>
-static void launch_stage_sharded_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
+static void launch_stage_sharded_t(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta,
                                    const ShardStage& shard, cudaStream_t s) {
-    if (work_count >= kDeepBatchBundles) launch_stage_variant_sharded<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
-    else launch_stage_variant_sharded<STAGE, 1>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
+    if (work_count >= kDeepBatchBundles) launch_stage_variant_sharded<STAGE, BEPU_DEEP_MINB>(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
+    else launch_stage_variant_sharded<STAGE, 1>(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 template <int STAGE>
-static void launch_stage_t(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
-    if (STAGE != kStageIncremental && work_count >= kDeepBatchBundles) launch_stage_variant<STAGE, BEPU_DEEP_MINB>(records, work_count, B, fp, launch_flags, s);
-    else launch_stage_variant<STAGE, 1>(records, work_count, B, fp, launch_flags, s);
+static void launch_stage_t(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    if (STAGE != kStageIncremental && work_count >= kDeepBatchBundles) launch_stage_variant<STAGE, BEPU_DEEP_MINB>(records, ref_rows, work_count, B, fp, launch_flags, s);
+    else launch_stage_variant<STAGE, 1>(records, ref_rows, work_count, B, fp, launch_flags, s);
 }
 #endif
 
 #if BEPU_UNIT == 0
-void launch_stage_warm_start_first(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
-    launch_stage_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, s);
+void launch_stage_warm_start_first(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    launch_stage_t<kStageWarmStartFirst>(records, ref_rows, work_count, B, fp, launch_flags, s);
 }
-void launch_stage_warm_start_first_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
-    launch_stage_sharded_t<kStageWarmStartFirst>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
+void launch_stage_warm_start_first_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
+    launch_stage_sharded_t<kStageWarmStartFirst>(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 #elif BEPU_UNIT == 1
-void launch_stage_warm_start(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
-    launch_stage_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, s);
+void launch_stage_warm_start(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    launch_stage_t<kStageWarmStart>(records, ref_rows, work_count, B, fp, launch_flags, s);
 }
-void launch_stage_warm_start_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
-    launch_stage_sharded_t<kStageWarmStart>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
+void launch_stage_warm_start_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
+    launch_stage_sharded_t<kStageWarmStart>(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 #elif BEPU_UNIT == 2
-void launch_stage_solve(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
-    launch_stage_t<kStageSolve>(records, work_count, B, fp, launch_flags, s);
+void launch_stage_solve(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+    launch_stage_t<kStageSolve>(records, ref_rows, work_count, B, fp, launch_flags, s);
 }
-void launch_stage_solve_sharded(const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
-    launch_stage_sharded_t<kStageSolve>(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
+void launch_stage_solve_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s) {
+    launch_stage_sharded_t<kStageSolve>(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s);
 }
 #elif BEPU_UNIT == 3
-static void launch_constraint_stage(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
+static void launch_constraint_stage(int stage, const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
     if (work_count <= 0) return;
     switch (stage) {
-        case kStageWarmStartFirst: launch_stage_warm_start_first(records, work_count, B, fp, launch_flags, s); break;
-        case kStageWarmStart: launch_stage_warm_start(records, work_count, B, fp, launch_flags, s); break;
-        case kStageSolve: launch_stage_solve(records, work_count, B, fp, launch_flags, s); break;
-        case kStageIncremental: launch_stage_t<kStageIncremental>(records, work_count, B, fp, launch_flags, s); break;
+        case kStageWarmStartFirst: launch_stage_warm_start_first(records, ref_rows, work_count, B, fp, launch_flags, s); break;
+        case kStageWarmStart: launch_stage_warm_start(records, ref_rows, work_count, B, fp, launch_flags, s); break;
+        case kStageSolve: launch_stage_solve(records, ref_rows, work_count, B, fp, launch_flags, s); break;
+        case kStageIncremental: launch_stage_t<kStageIncremental>(records, ref_rows, work_count, B, fp, launch_flags, s); break;
         default: break;
     }
 }
-static void launch_constraint_stage_sharded(int stage, const WorkRecord* records, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
+static void launch_constraint_stage_sharded(int stage, const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,
                                             long long peer_delta, const ShardStage& shard, cudaStream_t s) {
     if (work_count <= 0) return;
     switch (stage) {
-        case kStageWarmStartFirst: launch_stage_warm_start_first_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
-        case kStageWarmStart: launch_stage_warm_start_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
-        case kStageSolve: launch_stage_solve_sharded(records, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
+        case kStageWarmStartFirst: launch_stage_warm_start_first_sharded(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
+        case kStageWarmStart: launch_stage_warm_start_sharded(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
+        case kStageSolve: launch_stage_solve_sharded(records, ref_rows, work_count, B, fp, launch_flags, peers, peer_delta, shard, s); break;
         default: break;
     }
 }

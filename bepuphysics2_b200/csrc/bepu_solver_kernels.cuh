@@ -346,7 +346,7 @@ BEPU_DI void shard_wait(const ShardPeers& peers, int lane, uint32_t solve_index,
     __syncwarp();
 }
 template <int STAGE, bool kSharded>
-BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int work_count, const BodyBuffers& B, const FrameParams* __restrict__ fpp, int flags, const ShardPeers* peers,
+BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, const int32_t* __restrict__ ref_rows, int work_count, const BodyBuffers& B, const FrameParams* __restrict__ fpp, int flags, const ShardPeers* peers,
                                    long long peer_delta, const ShardStage* shard = nullptr) {
     constexpr bool kStaged = STAGE != kStageIncremental;
     constexpr int kWarps = kStageBlockThreads / 32;
@@ -378,8 +378,9 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
                 }
             }
         }
-        enc0 = ldg_nc_u32(rec.refs + lane);
-        enc1 = ldg_nc_u32(rec.refs + kLanes + lane);
+        // the first two reference rows come from the packed copy next to the work list: their address does not depend on the record (no second round trip)
+        enc0 = ldg_nc_u32(ref_rows + (size_t)warp * (2 * kLanes) + lane);
+        enc1 = ldg_nc_u32(ref_rows + (size_t)warp * (2 * kLanes) + kLanes + lane);
     }
     const FrameParams fp = *fpp;
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -413,15 +414,15 @@ BEPU_DI void constraint_stage_body(const WorkRecord* __restrict__ records, int w
 }
 
 template <int STAGE, int MINB>
-__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags) {
-    constraint_stage_body<STAGE, false>(records, work_count, B, fpp, flags, nullptr, 0);
+__global__ void __launch_bounds__(kStageBlockThreads, MINB) constraint_stage_kernel(const WorkRecord* __restrict__ records, const int32_t* __restrict__ ref_rows, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags) {
+    constraint_stage_body<STAGE, false>(records, ref_rows, work_count, B, fpp, flags, nullptr, 0);
 }
 // Peer-sharded variant (bepucuda_shard_*): the lane that writes a body another rank references stores the record into that rank's arrays too.
 template <int STAGE, int MINB>
 __global__ void __launch_bounds__(kStageBlockThreads, MINB)
-constraint_stage_kernel_sharded(const WorkRecord* __restrict__ records, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags, const __grid_constant__ ShardPeers peers,
+constraint_stage_kernel_sharded(const WorkRecord* __restrict__ records, const int32_t* __restrict__ ref_rows, int work_count, BodyBuffers B, const FrameParams* __restrict__ fpp, int flags, const __grid_constant__ ShardPeers peers,
                                 long long peer_delta, const __grid_constant__ ShardStage shard) {
-    constraint_stage_body<STAGE, true>(records, work_count, B, fpp, flags, &peers, peer_delta, &shard);
+    constraint_stage_body<STAGE, true>(records, ref_rows, work_count, B, fpp, flags, &peers, peer_delta, &shard);
 }
 
 // IntegrateKinematicVelocities / IntegrateKinematicPosesAndVelocities (PoseIntegrator.cs:L451-487, L493-535)

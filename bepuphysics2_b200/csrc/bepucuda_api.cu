@@ -11,6 +11,7 @@
 
 #include "../../include/bepucuda.h"
 #include "bepu_layout_kernels.h"
+#include "bepu_coloring.h"
 
 using namespace bepucuda;
 
@@ -164,7 +165,7 @@ struct bepucuda_ctx {
     bool constraints_open = false, constraints_ready = false, data_dirty = false, descs_dirty = false;
     std::vector<SourceTypeBatch> sources;
     ChunkArena raw_arena, pinned_arena;
-    DeviceBuffer chain32, succ32, next_bundle, dep_counts, df_counters, body_counter, record_table, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
+    DeviceBuffer chain32, succ32, next_bundle, dep_counts, df_counters, body_counter, record_table, ref_rows, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
     std::vector<DeviceTypeBatch> tbs;
     std::vector<TransposeDesc> tdescs;
     std::vector<WorkItem> work;                 // grouped by device batch, then the incremental list
@@ -214,6 +215,7 @@ struct bepucuda_ctx {
     uint32_t pass_counter = 0;      // dataflow mode: WarmStart/Solve passes since the body versions were reset
     bool versions_dirty = true;     // velocity-record padding words do not hold valid versions
     cudaEvent_t user_events[16] = {};
+    DeviceBuffer color_refs, color_priorities, color_body_min, color_body_mask, color_out, color_lists, color_counts;  // bepucuda_color_constraints
     std::vector<cudaEvent_t> profile_events;
 };
 
@@ -310,6 +312,7 @@ void invalidate_graph(bepucuda_ctx* ctx) {
 // capture in GRAPH mode). Order: Solver_Solve.cs:L1419-1479, then PoseIntegrator.IntegrateAfterSubstepping.
 void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) {
     const WorkRecord* records = ctx->record_table.as<WorkRecord>();
+    const int32_t* ref_rows = ctx->ref_rows.as<int32_t>();
     const FrameParams* fp = ctx->frame_params_dev.as<FrameParams>();
     const int32_t* kin = ctx->kinematics_dev.as<int32_t>();
     int64_t n = 0;
@@ -362,14 +365,14 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
                 if (fused_pushes) {
                     // the stage pushes, signals and (in its boundary bundles) waits itself: no exchange kernel
                     const ShardStage shard{exchange_index, ctx->error_dev.as<int32_t>()};
-                    ctx->launchers->constraint_stage_sharded(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, ctx->peers,
+                    ctx->launchers->constraint_stage_sharded(op.stage, records + op.work_begin, ref_rows + (size_t)op.work_begin * 64, op.work_count, ctx->B, fp, launch_flags, ctx->peers,
                                                              (long long)(ctx->peer32.as<int32_t>() - ctx->refs32.as<int32_t>()), shard, s);
                     ++exchange_index;
                     ++n;
                     previous = &op;
                     continue;
                 }
-                ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, launch_flags, s);
+                ctx->launchers->constraint_stage(op.stage, records + op.work_begin, ref_rows + (size_t)op.work_begin * 64, op.work_count, ctx->B, fp, launch_flags, s);
                 ++n;
             }
             if (fused_pushes) { ++exchange_index; continue; }  // no constraint of this batch here: nothing arrives from this rank, its targets say so
@@ -387,7 +390,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
                     if (prefetch && previous->stage <= kStageSolve && previous->work_begin == op.work_begin) prefetch = false;
                     if (ctx->exchange) {
                         // sharded batches: plain launches, then all ranks learn what this rank's constraints wrote in this stage
-                        ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, 0, s);
+                        ctx->launchers->constraint_stage(op.stage, records + op.work_begin, ref_rows + (size_t)op.work_begin * 64, op.work_count, ctx->B, fp, 0, s);
                         ++n;
                         if (op.stage != kStageIncremental) {
                             const int planes = op.stage == kStageSolve ? 1 : (op.stage == kStageWarmStart ? 3 : 2);
@@ -402,7 +405,7 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
                         previous = &op;
                         break;
                     }
-                    ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0), s);
+                    ctx->launchers->constraint_stage(op.stage, records + op.work_begin, ref_rows + (size_t)op.work_begin * 64, op.work_count, ctx->B, fp, (pdl ? kLaunchPdl : 0) | (prefetch ? kLaunchPrefetchRows : 0), s);
                     previous = &op;
                     ++n;
                 }
@@ -606,7 +609,7 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     invalidate_graph(ctx);
     for (void* p : ctx->opened_ipc) cudaIpcCloseMemHandle(p);
     DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->peer32, &ctx->body_masks_dev, &ctx->boundary_flags_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
-                            &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
+                            &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->ref_rows, &ctx->color_refs, &ctx->color_priorities, &ctx->color_body_min, &ctx->color_body_mask, &ctx->color_out, &ctx->color_lists, &ctx->color_counts, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
                             &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
     ctx->raw_arena.release();
@@ -1123,6 +1126,9 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
         }
         if (n_rec > 0) CK(cudaMemcpyAsync(ctx->record_table.ptr, ctx->records.data(), (size_t)n_rec * sizeof(WorkRecord), cudaMemcpyHostToDevice, ctx->stream));
     }
+    // the first two body-reference rows of every work record, packed in work-list order (they carry the ownership bits set above)
+    CK(ctx->ref_rows.reserve((size_t)std::max<size_t>(ctx->records.size(), 1) * 64 * 4));
+    launch_pack_ref_rows(ctx->record_table.as<WorkRecord>(), (int)ctx->records.size(), ctx->ref_rows.as<int32_t>(), ctx->stream);
     CK(cudaGetLastError());
     int32_t err = 0;
     CK(cudaMemcpyAsync(&err, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1497,6 +1503,7 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
         ctx->profile_events.push_back(ev);
     }
     const WorkRecord* records = ctx->record_table.as<WorkRecord>();
+    const int32_t* ref_rows = ctx->ref_rows.as<int32_t>();
     const FrameParams* fp = ctx->frame_params_dev.as<FrameParams>();
     const int32_t* kin = ctx->kinematics_dev.as<int32_t>();
     std::vector<int> launched(ctx->program.size(), 0);
@@ -1505,7 +1512,7 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
         const bool has_work = op.stage == kStageFinalPose ? ctx->B.count > 0 : op.work_count > 0;
         if (!has_work) continue;
         CK(cudaEventRecord(ctx->profile_events[2 * i], ctx->stream));
-        if (op.stage <= kStageIncremental) ctx->launchers->constraint_stage(op.stage, records + op.work_begin, op.work_count, ctx->B, fp, 0, ctx->stream);
+        if (op.stage <= kStageIncremental) ctx->launchers->constraint_stage(op.stage, records + op.work_begin, ref_rows + (size_t)op.work_begin * 64, op.work_count, ctx->B, fp, 0, ctx->stream);
         else if (op.stage <= kStageKinematic) ctx->launchers->kinematic_stage(op.stage, kin, op.work_count, ctx->B, fp, ctx->stream);
         else ctx->launchers->final_pose(ctx->B, fp, ctx->stream);
         CK(cudaEventRecord(ctx->profile_events[2 * i + 1], ctx->stream));
@@ -1536,6 +1543,82 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
         }
         out->algorithmic_bytes[op.stage] += bytes;
     }
+    return BEPUCUDA_OK;
+}
+
+uint32_t bepucuda_color_hash(uint32_t constraint_index) { return color_hash(constraint_index); }
+
+int32_t bepucuda_color_constraints(bepucuda_ctx* ctx, int32_t constraint_count, int32_t bodies_per_constraint, const int32_t* encoded_body_references, int32_t body_count,
+                                   int32_t fallback_batch_threshold, int32_t order, const uint32_t* priorities, int32_t* batch_indices_out, int32_t* batch_count_out,
+                                   int32_t* rounds_out) {
+    if (!ctx) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    if (constraint_count < 0 || bodies_per_constraint < 1 || bodies_per_constraint > 4 || body_count < 0 || fallback_batch_threshold < 1 || fallback_batch_threshold > 64)
+        return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "color_constraints: counts out of range (1..4 body slots, fallback threshold 1..64)");
+    if (order < BEPUCUDA_COLOR_INSERTION_ORDER || order > BEPUCUDA_COLOR_BY_PRIORITY || (order == BEPUCUDA_COLOR_BY_PRIORITY && !priorities))
+        return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "color_constraints: unknown order, or BEPUCUDA_COLOR_BY_PRIORITY without priorities");
+    if (constraint_count > 0 && (!encoded_body_references || !batch_indices_out)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "color_constraints: null buffer");
+    if (batch_count_out) *batch_count_out = 0;
+    if (rounds_out) *rounds_out = 0;
+    if (constraint_count == 0) return BEPUCUDA_OK;
+    CK(cudaSetDevice(ctx->device));
+    // body references are validated on the host while they are being staged (one pass over memory the copy touches anyway)
+    const size_t words = (size_t)constraint_count * bodies_per_constraint;
+    for (size_t i = 0; i < words; ++i) {
+        const int32_t enc = encoded_body_references[i];
+        if (enc >= 0 && (int32_t)((uint32_t)enc & ((1u << 30) - 1u)) >= body_count) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "color_constraints: body reference out of range");
+    }
+    constexpr int kRoundsPerChunk = 32;  // even: the ping-pong lists return to their starting roles after every chunk
+    const size_t nb = (size_t)std::max(body_count, 1), nc = (size_t)constraint_count;
+    CK(ctx->color_refs.reserve(words * 4));
+    CK(ctx->color_priorities.reserve(nc * 4));
+    CK(ctx->color_body_min.reserve(nb * 8));
+    CK(ctx->color_body_mask.reserve(nb * 8));
+    CK(ctx->color_out.reserve(nc * 4));
+    CK(ctx->color_lists.reserve(nc * 8));
+    CK(ctx->color_counts.reserve((kRoundsPerChunk + 1) * 4));
+    CK(cudaMemcpyAsync(ctx->color_refs.ptr, encoded_body_references, words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (order == BEPUCUDA_COLOR_BY_PRIORITY) CK(cudaMemcpyAsync(ctx->color_priorities.ptr, priorities, nc * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ColoringBuffers cb{};
+    cb.refs = ctx->color_refs.as<int32_t>();
+    cb.priorities = ctx->color_priorities.as<uint32_t>();
+    cb.body_min = ctx->color_body_min.as<unsigned long long>();
+    cb.body_mask = ctx->color_body_mask.as<unsigned long long>();
+    cb.batch_out = ctx->color_out.as<int32_t>();
+    cb.list[0] = ctx->color_lists.as<int32_t>();
+    cb.list[1] = ctx->color_lists.as<int32_t>() + nc;
+    cb.counts = ctx->color_counts.as<unsigned int>();
+    cb.constraint_count = constraint_count;
+    cb.bodies_per_constraint = bodies_per_constraint;
+    cb.body_count = body_count;
+    cb.fallback_threshold = fallback_batch_threshold;
+    cb.order = order;
+    CK(cudaMemsetAsync(ctx->color_counts.ptr, 0, (kRoundsPerChunk + 1) * 4, ctx->stream));
+    launch_color_init(cb, ctx->stream);
+    unsigned int counts[kRoundsPerChunk + 1];
+    int64_t rounds = 0;
+    for (;;) {
+        for (int r = 0; r < kRoundsPerChunk; ++r) launch_color_round(cb, r, ctx->stream);
+        CK(cudaMemcpyAsync(counts, ctx->color_counts.ptr, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+        int used = kRoundsPerChunk;
+        for (int r = 0; r < kRoundsPerChunk; ++r)
+            if (counts[r + 1] == 0) { used = r + 1; break; }
+        rounds += used;
+        if (counts[used] == 0) break;
+        // every round assigns at least the constraint with the globally lowest key, so the list shrinks: the loop ends after at most constraint_count rounds
+        if (counts[kRoundsPerChunk] >= counts[0]) return fail(ctx, BEPUCUDA_ERR_CUDA, "color_constraints: no progress (internal error)");
+        counts[0] = counts[kRoundsPerChunk];
+        for (int r = 1; r <= kRoundsPerChunk; ++r) counts[r] = 0;
+        CK(cudaMemcpyAsync(ctx->color_counts.ptr, counts, sizeof(counts), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // `counts` is a stack array: the copy must have read it before the next chunk's download overwrites it
+    }
+    CK(cudaMemcpyAsync(batch_indices_out, ctx->color_out.ptr, nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int32_t highest = -1;
+    for (size_t i = 0; i < nc; ++i) highest = std::max(highest, batch_indices_out[i]);
+    if (batch_count_out) *batch_count_out = highest + 1;
+    if (rounds_out) *rounds_out = (int32_t)std::min<int64_t>(rounds, 0x7fffffff);
     return BEPUCUDA_OK;
 }
 

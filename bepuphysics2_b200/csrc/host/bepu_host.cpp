@@ -202,20 +202,45 @@ int allocate_in_type_batch_for_fallback(Simulation& sim, TypeBatch& t, int handl
     return index;
 }
 
-// Solver.Add (Solver.cs:L1182-1199): greedy first fit over batches; kinematics never block (GetBlockingBodyHandles L1058-1078);
-// batch index == FallbackBatchThreshold is the fallback batch and accepts everything (TryAllocateInBatch L1093-1140).
-int solver_add(Simulation& sim, int type_id, const int32_t* body_handles, const float* prestep) {
+// GetBlockingBodyHandles (Solver.cs:L1058-1078): encodes the body references (kinematic flag in bit 30) and lists the dynamic handles, the only
+// ones that take part in batch membership.
+int encode_references(Simulation& sim, int type_id, const int32_t* body_handles, int32_t* encoded, int32_t* blocking, int* blocking_count, int* body_count_out) {
     int32_t nb = 0;
     if (bepucuda_type_info(type_id, &nb, nullptr, nullptr) != BEPUCUDA_OK) { sim.error = "unsupported constraint type"; return -1; }
-    int32_t encoded[4];
-    int32_t blocking[4];
-    int blocking_count = 0;
+    *blocking_count = 0;
     for (int i = 0; i < nb; ++i) {
         const int h = body_handles[i];
         if (h < 0 || h >= sim.body_count) { sim.error = "body handle out of range"; return -1; }
         if (is_kinematic(sim.dynamics.data + (size_t)h * 32)) encoded[i] = h | (int32_t)kKinematicMask;
-        else { encoded[i] = h; blocking[blocking_count++] = h; }
+        else { encoded[i] = h; blocking[(*blocking_count)++] = h; }
     }
+    *body_count_out = nb;
+    return 0;
+}
+
+// AllocateInBatch (Solver.cs:L1016-1056) into a batch that is known to fit.
+int allocate_in_batch(Simulation& sim, int target, int type_id, int nb, const int32_t* encoded, const int32_t* blocking, int blocking_count, const float* prestep) {
+    const int handle = (int)sim.handle_to_constraint.size();
+    for (int i = 0; i < nb; ++i)
+        if ((uint32_t)encoded[i] & kKinematicMask) {
+            const int h = encoded[i] & ~(int32_t)kKinematicMask;
+            if (!sim.constrained_kinematic_set.contains(h)) { sim.constrained_kinematic_set.set(h); sim.constrained_kinematic_handles.push_back(h); }
+        }
+    TypeBatch* tb = get_or_create_type_batch(sim, *sim.batches[target], type_id);
+    if (!tb) { sim.error = "unsupported constraint type"; return -1; }
+    int index = target == sim.fallback_batch_threshold ? allocate_in_type_batch_for_fallback(sim, *tb, handle, encoded) : allocate_in_type_batch(sim, *tb, handle);
+    write_lane(sim, *tb, index, encoded, prestep);
+    for (int i = 0; i < blocking_count; ++i) sim.batch_referenced_handles[target].set(blocking[i]);
+    sim.handle_to_constraint.push_back({target, type_id, index});
+    return handle;
+}
+
+// Solver.Add (Solver.cs:L1182-1199): greedy first fit over batches; kinematics never block (GetBlockingBodyHandles L1058-1078);
+// batch index == FallbackBatchThreshold is the fallback batch and accepts everything (TryAllocateInBatch L1093-1140).
+int solver_add(Simulation& sim, int type_id, const int32_t* body_handles, const float* prestep) {
+    int32_t encoded[4], blocking[4];
+    int blocking_count = 0, nb = 0;
+    if (encode_references(sim, type_id, body_handles, encoded, blocking, &blocking_count, &nb) != 0) return -1;
     for (int target = 0; target <= (int)sim.batches.size(); ++target) {
         if (target == (int)sim.batches.size()) {
             sim.batches.push_back(new ConstraintBatch());
@@ -225,23 +250,27 @@ int solver_add(Simulation& sim, int type_id, const int32_t* body_handles, const 
             for (int i = 0; i < blocking_count; ++i) fits = fits && !sim.batch_referenced_handles[target].contains(blocking[i]);
             if (!fits) continue;
         }
-        // AllocateInBatch (Solver.cs:L1016-1056)
-        const int handle = (int)sim.handle_to_constraint.size();
-        for (int i = 0; i < nb; ++i)
-            if ((uint32_t)encoded[i] & kKinematicMask) {
-                const int h = encoded[i] & ~(int32_t)kKinematicMask;
-                if (!sim.constrained_kinematic_set.contains(h)) { sim.constrained_kinematic_set.set(h); sim.constrained_kinematic_handles.push_back(h); }
-            }
-        TypeBatch* tb = get_or_create_type_batch(sim, *sim.batches[target], type_id);
-        if (!tb) { sim.error = "unsupported constraint type"; return -1; }
-        int index = target == sim.fallback_batch_threshold ? allocate_in_type_batch_for_fallback(sim, *tb, handle, encoded) : allocate_in_type_batch(sim, *tb, handle);
-        write_lane(sim, *tb, index, encoded, prestep);
-        for (int i = 0; i < blocking_count; ++i) sim.batch_referenced_handles[target].set(blocking[i]);
-        sim.handle_to_constraint.push_back({target, type_id, index});
-        return handle;
+        return allocate_in_batch(sim, target, type_id, nb, encoded, blocking, blocking_count, prestep);
     }
     sim.error = "constraint add failed";
     return -1;
+}
+
+// The add path of callers that already know the batch (the narrow phase: FindCandidateBatch, then TryAllocateInBatch at that index,
+// Solver.cs:L984-1014, L1093-1140; here: a batch index computed by bepucuda_color_constraints). Fails if the batch cannot hold the constraint.
+int solver_add_in_batch(Simulation& sim, int target, int type_id, const int32_t* body_handles, const float* prestep) {
+    int32_t encoded[4], blocking[4];
+    int blocking_count = 0, nb = 0;
+    if (encode_references(sim, type_id, body_handles, encoded, blocking, &blocking_count, &nb) != 0) return -1;
+    if (target < 0 || target > sim.fallback_batch_threshold) { sim.error = "batch index out of range"; return -1; }
+    while ((int)sim.batches.size() <= target) {  // empty batches may sit between occupied ones (the reference tolerates them too, Solver_Solve.cs:L794-796)
+        sim.batches.push_back(new ConstraintBatch());
+        sim.batch_referenced_handles.emplace_back();
+    }
+    if (target < sim.fallback_batch_threshold)
+        for (int i = 0; i < blocking_count; ++i)
+            if (sim.batch_referenced_handles[target].contains(blocking[i])) { sim.error = "the batch already references one of the constraint's dynamic bodies"; return -1; }
+    return allocate_in_batch(sim, target, type_id, nb, encoded, blocking, blocking_count, prestep);
 }
 
 }  // namespace
@@ -306,6 +335,34 @@ int32_t bepuhost_add_constraints(void* simp, int32_t type_id, int32_t count, con
         if (i == 0) first = h;
     }
     return first;
+}
+// Like bepuhost_add_constraints with the batch of every constraint given (computed by bepucuda_color_constraints).
+int32_t bepuhost_add_constraints_in_batches(void* simp, int32_t type_id, int32_t count, const int32_t* body_handles, const float* prestep, const int32_t* batch_indices) {
+    Simulation& sim = *(Simulation*)simp;
+    int32_t nb = 0, p = 0;
+    if (bepucuda_type_info(type_id, &nb, &p, nullptr) != BEPUCUDA_OK) { sim.error = "unsupported constraint type"; return -1; }
+    int32_t first = -1;
+    for (int i = 0; i < count; ++i) {
+        const int h = solver_add_in_batch(sim, batch_indices[i], type_id, body_handles + (size_t)i * nb, prestep + (size_t)i * p);
+        if (h < 0) return -1;
+        if (i == 0) first = h;
+    }
+    return first;
+}
+// In handle (= add) order: the encoded body references of every constraint, 4 slots each (-1 = unused), and its batch index.
+int32_t bepuhost_export_constraint_references(void* simp, int32_t* references_out, int32_t* batch_indices_out) {
+    Simulation& sim = *(Simulation*)simp;
+    const int W = sim.W;
+    for (size_t h = 0; h < sim.handle_to_constraint.size(); ++h) {
+        const ConstraintLocation& loc = sim.handle_to_constraint[h];
+        ConstraintBatch& batch = *sim.batches[loc.batch];
+        TypeBatch& t = *batch.type_batches[batch.type_index_to_type_batch_index[loc.type_id]];
+        const int bundle = loc.index_in_type_batch / W, inner = loc.index_in_type_batch % W;
+        const int32_t* refs = t.body_references.data + (size_t)bundle * t.bodies * W;
+        for (int b = 0; b < 4; ++b) references_out[h * 4 + b] = b < t.bodies ? refs[b * W + inner] : -1;
+        if (batch_indices_out) batch_indices_out[h] = loc.batch;
+    }
+    return (int32_t)sim.handle_to_constraint.size();
 }
 int32_t bepuhost_constraint_location(void* simp, int32_t handle, int32_t* batch, int32_t* type_id, int32_t* index_in_type_batch) {
     Simulation& sim = *(Simulation*)simp;

@@ -97,6 +97,7 @@ C_ABI_SYMBOLS = [
     "bepucuda_event_record", "bepucuda_event_elapsed_ms", "bepucuda_profile_stages",
     "bepucuda_set_contact_features", "bepucuda_update_contacts", "bepucuda_upload_body_motion", "bepucuda_download_body_motion",
     "bepucuda_shard_export", "bepucuda_shard_import", "bepucuda_shard_set_global", "bepucuda_shard_set_pushes", "bepucuda_shard_set_body_masks", "bepucuda_shard_import_contexts",
+    "bepucuda_color_constraints", "bepucuda_color_hash",
 ]
 
 
@@ -146,6 +147,9 @@ def load_libraries():
     cuda.bepucuda_profile_stages.argtypes = [vp, f32, C.POINTER(StageProfile)]
     cuda.bepucuda_host_register.argtypes = [vp, vp, C.c_int64]
     cuda.bepucuda_host_unregister.argtypes = [vp, vp]
+    cuda.bepucuda_color_constraints.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, C.POINTER(i32), C.POINTER(i32)]
+    cuda.bepucuda_color_hash.argtypes = [C.c_uint32]
+    cuda.bepucuda_color_hash.restype = C.c_uint32
 
     host.bepuhost_create.restype = vp
     host.bepuhost_create.argtypes = [i32, i32]
@@ -159,6 +163,8 @@ def load_libraries():
     host.bepuhost_body_dynamics.restype = C.POINTER(C.c_float)
     host.bepuhost_body_count.argtypes = [vp]
     host.bepuhost_add_constraints.argtypes = [vp, i32, i32, vp, vp]
+    host.bepuhost_add_constraints_in_batches.argtypes = [vp, i32, i32, vp, vp, vp]
+    host.bepuhost_export_constraint_references.argtypes = [vp, vp, vp]
     host.bepuhost_constraint_location.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     host.bepuhost_constraint_count.argtypes = [vp]
     host.bepuhost_batch_count.argtypes = [vp]
@@ -267,6 +273,29 @@ class Simulation:
             raise ValueError(self._host.bepuhost_last_error(self._sim).decode())
         return first
 
+    def add_constraints_in_batches(self, type_id, body_handles, prestep, batch_indices):
+        """Solver.Add for callers that already know each constraint's batch (computed by CudaTimestepper.color_constraints): the narrow phase's
+        FindCandidateBatch -> TryAllocateInBatch path (Solver.cs:L984-1014, L1093-1140). Raises if a batch cannot hold its constraint."""
+        nb, p, _ = type_info(type_id)
+        h = np.ascontiguousarray(body_handles, dtype=np.int32).reshape(-1, nb)
+        pre = np.ascontiguousarray(prestep, dtype=np.float32).reshape(-1, p)
+        b = np.ascontiguousarray(batch_indices, dtype=np.int32).reshape(-1)
+        assert h.shape[0] == pre.shape[0] == b.shape[0]
+        if h.shape[0] == 0:
+            return -1
+        first = self._host.bepuhost_add_constraints_in_batches(self._sim, type_id, h.shape[0], h.ctypes.data, pre.ctypes.data, b.ctypes.data)
+        if first < 0:
+            raise ValueError(self._host.bepuhost_last_error(self._sim).decode())
+        return first
+
+    def constraint_references(self):
+        """(references[n, 4], batch[n]) in handle (= add) order: encoded body references (kinematic flag in bit 30, -1 = unused slot) and batch indices."""
+        n = self.constraint_count
+        refs = np.full((max(n, 1), 4), -1, dtype=np.int32)
+        batches = np.zeros(max(n, 1), dtype=np.int32)
+        self._host.bepuhost_export_constraint_references(self._sim, refs.ctypes.data, batches.ctypes.data)
+        return refs[:n], batches[:n]
+
     @property
     def constraint_count(self):
         return self._host.bepuhost_constraint_count(self._sim)
@@ -334,6 +363,17 @@ class CudaTimestepper:
     def _check(self, rc):
         if rc != 0:
             raise BepuCudaError(rc, self._cuda.bepucuda_last_error(self._ctx).decode())
+
+    def color_constraints(self, references, body_count, fallback_batch_threshold=64, order=0, priorities=None):
+        """bepucuda_color_constraints: batch index per constraint for references[n, slots] (encoded body references). Returns (batches, batch_count, rounds)."""
+        refs = np.ascontiguousarray(references, dtype=np.int32)
+        n, slots = refs.shape
+        out = np.full(max(n, 1), -1, dtype=np.int32)
+        pr = None if priorities is None else np.ascontiguousarray(priorities, dtype=np.uint32)
+        count, rounds = C.c_int32(), C.c_int32()
+        self._check(self._cuda.bepucuda_color_constraints(self._ctx, n, slots, refs.ctypes.data, body_count, fallback_batch_threshold, order, None if pr is None else pr.ctypes.data,
+                                                          out.ctypes.data, C.byref(count), C.byref(rounds)))
+        return out[:n], count.value, rounds.value
 
     def register_host_buffers(self):
         """Page-locks the simulation's buffers (a C# host would register its BufferPool blocks once)."""

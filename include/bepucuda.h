@@ -192,6 +192,30 @@ typedef struct bepucuda_stage_profile {
 } bepucuda_stage_profile;
 int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_profile* out);
 
+/* Device-side batch colouring. Replaces, for a whole constraint set at once, the batch search Solver.Add runs per constraint
+ * (Solver.cs:L1182-1199: the first batch whose referenced-handle set holds none of the constraint's dynamic bodies; kinematic references never
+ * block, GetBlockingBodyHandles L1058-1078; index == fallback_batch_threshold is the fallback batch and accepts everything, TryAllocateInBatch
+ * L1093-1140; the narrow phase's FindCandidateBatch L984-1014 is the same search). The result is IDENTICAL to running that first-fit search
+ * sequentially over the constraints in ascending key order:
+ *   BEPUCUDA_COLOR_INSERTION_ORDER  key = constraint index: the batches the reference's Solver.Add sequence produces from an empty solver;
+ *   BEPUCUDA_COLOR_HASHED_ORDER     key = (bepucuda_color_hash(index) << 32) | index: a fixed pseudo-random order, which bounds the number of
+ *                                   dependent device rounds by O(log n) on bounded-degree constraint graphs (insertion order can chain);
+ *   BEPUCUDA_COLOR_BY_PRIORITY      key = (priorities[index] << 32) | index. With priorities = the constraints' CURRENT batch indices no
+ *                                   constraint moves to a higher batch and none could move lower afterwards: the fixed point the reference's
+ *                                   BatchCompressor (BatchCompressor.cs:L233) approaches a few constraints per frame.
+ * encoded_body_references: [constraint][slot] with `bodies_per_constraint` (1..4) slots per constraint: active-set body index, bit 30 set for a
+ * kinematic body (Bodies_GatherScatter.cs:L107-139), -1 for an unused slot. body_count bounds the indices. batch_indices_out[i] receives the batch
+ * of constraint i (0 .. fallback_batch_threshold), *batch_count_out the number of batches, *rounds_out the dependent device rounds it took
+ * (both optional). Host buffers are caller-owned and only used during the call, which blocks until the result is written. */
+#define BEPUCUDA_COLOR_INSERTION_ORDER 0
+#define BEPUCUDA_COLOR_HASHED_ORDER 1
+#define BEPUCUDA_COLOR_BY_PRIORITY 2
+int32_t bepucuda_color_constraints(bepucuda_ctx* ctx, int32_t constraint_count, int32_t bodies_per_constraint, const int32_t* encoded_body_references,
+                                   int32_t body_count, int32_t fallback_batch_threshold, int32_t order, const uint32_t* priorities,
+                                   int32_t* batch_indices_out, int32_t* batch_count_out, int32_t* rounds_out);
+/* The hash behind BEPUCUDA_COLOR_HASHED_ORDER: h = i * 0x9E3779B1; h ^= h >> 15; h *= 0x85EBCA77; h ^= h >> 13; h *= 0xC2B2AE3D; h ^= h >> 16 (uint32). */
+uint32_t bepucuda_color_hash(uint32_t constraint_index);
+
 /* Multi-GPU, one constraint graph over several contexts (replaces the reference's multithreaded batch dispatch,
  * Solver_Solve.cs:L458-654, where workers split the constraints of a batch). Every participating context ("rank": one per GPU, normally one per
  * process) is given the WHOLE body set and the same batch layout, but only its share of the constraints (lanes of other ranks are empty, body

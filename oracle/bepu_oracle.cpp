@@ -871,6 +871,52 @@ extern "C" int32_t oracle_update_contact_impulses(int32_t type_id, int32_t const
     return 0;
 }
 
+// Batch assignment of Solver.Add (Solver.cs:L1182-1199) for a whole constraint list: every constraint, in ascending key order, goes to the first
+// batch whose referenced-handle set holds none of its dynamic bodies (GetBlockingBodyHandles L1058-1078: kinematic references never block); batch
+// index == fallback_threshold is the fallback batch and takes whatever no synchronized batch could (TryAllocateInBatch L1093-1140). The key is the
+// one include/bepucuda.h documents for bepucuda_color_constraints: order 0 = index (the reference's own add sequence), 1 = hashed, 2 = priorities.
+static uint32_t oracle_color_hash(uint32_t c) {
+    uint32_t h = c * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    h *= 0xC2B2AE3Du;
+    h ^= h >> 16;
+    return h;
+}
+extern "C" int32_t oracle_first_fit_batches(int32_t constraint_count, int32_t bodies_per_constraint, const int32_t* encoded_body_references, int32_t body_count,
+                                            int32_t fallback_threshold, int32_t order, const uint32_t* priorities, int32_t* batch_indices_out) {
+    if (constraint_count < 0 || bodies_per_constraint < 1 || bodies_per_constraint > 4 || order < 0 || order > 2 || (order == 2 && !priorities)) return -1;
+    std::vector<uint64_t> keys((size_t)constraint_count);
+    for (int c = 0; c < constraint_count; ++c) keys[c] = ((uint64_t)(order == 0 ? 0u : (order == 1 ? oracle_color_hash((uint32_t)c) : priorities[c])) << 32) | (uint32_t)c;
+    std::sort(keys.begin(), keys.end());
+    const size_t words = ((size_t)body_count + 63) / 64;
+    std::vector<std::vector<uint64_t>> batchReferencedHandles;  // Solver.cs:L33, one IndexSet per batch
+    for (uint64_t key : keys) {
+        const int c = (int)(uint32_t)key;
+        int blocking[4], blockingCount = 0;
+        for (int s = 0; s < bodies_per_constraint; ++s) {
+            const int32_t enc = encoded_body_references[(size_t)c * bodies_per_constraint + s];
+            if (enc < 0 || ((uint32_t)enc & 0x40000000u)) continue;
+            if (enc >= body_count) return -2;
+            blocking[blockingCount++] = enc;
+        }
+        for (int target = 0;; ++target) {
+            if (target == (int)batchReferencedHandles.size()) batchReferencedHandles.emplace_back(words, 0ull);
+            else if (target < fallback_threshold) {
+                bool fits = true;
+                for (int i = 0; i < blockingCount; ++i) fits = fits && !((batchReferencedHandles[target][blocking[i] >> 6] >> (blocking[i] & 63)) & 1);
+                if (!fits) continue;
+            }
+            if (target < fallback_threshold)
+                for (int i = 0; i < blockingCount; ++i) batchReferencedHandles[target][blocking[i] >> 6] |= 1ull << (blocking[i] & 63);
+            batch_indices_out[c] = target;
+            break;
+        }
+    }
+    return (int32_t)batchReferencedHandles.size();
+}
+
 extern "C" int32_t oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

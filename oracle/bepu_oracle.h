@@ -56,6 +56,11 @@ void oracle_redistribute_impulses(int32_t old_count, const int32_t* old_ids, flo
 int32_t oracle_update_contact_impulses(int32_t type_id, int32_t constraint_count, int32_t bundle_width, float* accumulated_impulses, const int32_t* old_feature_ids,
                                        const int32_t* new_feature_ids);
 
+/* Solver.Add's first-fit batch search (Solver.cs:L1182-1199) over a whole constraint list in ascending key order (keys as documented for
+ * bepucuda_color_constraints in include/bepucuda.h). Returns the number of batches, negative on bad arguments. */
+int32_t oracle_first_fit_batches(int32_t constraint_count, int32_t bodies_per_constraint, const int32_t* encoded_body_references, int32_t body_count,
+                                 int32_t fallback_threshold, int32_t order, const uint32_t* priorities, int32_t* batch_indices_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,3 +121,17 @@ def update_contact_impulses(type_batch, old_feature_ids, new_feature_ids):
                                             old.ctypes.data, new.ctypes.data)
     if rc != 0:
         raise ValueError("not a contact constraint type: %d" % type_batch.type_id)
+
+
+def first_fit_batches(refs, body_count, fallback_threshold=64, order=0, priorities=None):
+    """Sequential restatement of Solver.Add's batch search (Solver.cs:L1182-1199) over refs[n, slots] (encoded body references, -1 = unused slot)."""
+    lib = load()
+    refs = np.ascontiguousarray(refs, dtype=np.int32)
+    n, slots = refs.shape
+    out = np.full(n, -1, dtype=np.int32)
+    pr = None if priorities is None else np.ascontiguousarray(priorities, dtype=np.uint32)
+    lib.oracle_first_fit_batches.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    count = lib.oracle_first_fit_batches(n, slots, refs.ctypes.data, body_count, fallback_threshold, order, None if pr is None else pr.ctypes.data, out.ctypes.data)
+    if count < 0:
+        raise ValueError("oracle_first_fit_batches failed: %d" % count)
+    return out, count

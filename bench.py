@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--substeps", type=int, default=8)
     ap.add_argument("--iterations", type=int, default=2)
     ap.add_argument("--scene", default="shape_pile", choices=["shape_pile", "ragdolls", "fallback_stress"])
-    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent", "stream", "dataflow"], help="auto = the execution mode that measured fastest for the scene (DESIGN.md §8)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "stream"], help="auto = the execution mode that measured fastest for the scene (DESIGN.md §8)")
     ap.add_argument("--no-configs", action="store_true", help="skip the side block with the other BASELINE configs (C3 ragdolls x2, C5 fallback stress, 1 M-body pile 4 x 2)")
     ap.add_argument("--config-steps", type=int, default=20)
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false build")
@@ -346,7 +346,7 @@ def main():
     import torch
 
     import bepuphysics2_b200 as bp
-    from bepuphysics2_b200.native import EXEC_DATAFLOW, EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
+    from bepuphysics2_b200.native import EXEC_GRAPH, EXEC_STREAM
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -364,7 +364,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    modes = {"graph": EXEC_GRAPH, "persistent": EXEC_PERSISTENT, "stream": EXEC_STREAM, "dataflow": EXEC_DATAFLOW}
+    modes = {"graph": EXEC_GRAPH, "stream": EXEC_STREAM}
     args.mode = resolve_mode(args)
     mode = modes[args.mode]
 
@@ -441,7 +441,7 @@ def main():
 
     # ---- per-stage device time (event pair around every launch) for the roofline of the dominant kernel ----
     prof = None
-    if rank == 0 and args.mode != "dataflow":
+    if rank == 0:
         flush.fill_(1)
         torch.cuda.synchronize()
         ts.profile_stages(DT)
@@ -453,7 +453,7 @@ def main():
     # ---- the old to the new feature ids; per step the host sends the motion half of the bodies, the new prestep data and the new feature ids, and
     # ---- reads back the motion half of the bodies only
     resident = None
-    if rank == 0 and args.scene == "shape_pile":
+    if args.scene == "shape_pile":  # every rank (its own island), like the full-refresh leg
         pool, _ = ts.contact_feature_pool(np.random.default_rng(11))  # one pinned block, like a BufferPool
         ts.register_array(pool)
         ts.describe()
@@ -463,6 +463,7 @@ def main():
             ts.solve_device_only(DT)
             ts.download_body_motion()
         ts.synchronize()
+        barrier()
         r_steps = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(r_steps):
@@ -519,12 +520,15 @@ def main():
         gathered = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
         dist.all_gather(gathered, torch.tensor([total_ms / args.steps], dtype=torch.float64, device="cuda"))
         per_rank_ms = [float(g.item()) for g in gathered]
-    times = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    times = torch.tensor([total_ms, e2e_s * 1e3, (resident["ms_per_step"] * resident["steps"]) if resident is not None else 0.0], dtype=torch.float64, device="cuda")
     counts = torch.tensor([float(ci_per_step)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_ms_max = times.tolist()
+    total_ms_max, e2e_ms_max, resident_ms_max = times.tolist()
+    if resident is not None:  # whole job: all ranks' constraint-iterations over the slowest rank's time
+        resident["ms_per_step"] = resident_ms_max / resident["steps"]
+        resident["value"] = counts.item() * resident["steps"] / (resident_ms_max * 1e-3)
     ci_all = counts.item()
 
     if rank == 0:
@@ -532,20 +536,15 @@ def main():
         value = ci_all * args.steps / (total_ms_max * 1e-3)
         e2e_value = ci_all * e2e_steps / (e2e_ms_max * 1e-3)
         roof_extra = {}
-        if args.mode in ("persistent", "dataflow"):
-            # one kernel per step: the whole stage program
-            roof_bytes, roof_ms, roof_kernel = alg_bytes_per_step, total_ms / args.steps, "persistent_solve_kernel (whole step)"
-            launches = 1
-        else:
-            # Dominant kernel: constraint_stage_kernel<Solve>. Its launches sit inside a CUDA graph with programmatic-dependent-launch edges, so its time
-            # inside the timed region = (its share of the per-launch event-timed stage profile, taken right after the timed region on the same
-            # stream) x (the event-timed step). The fully serialised event-per-launch figure is reported next to it.
-            launches = prof["solve"]["launches"]
-            share = prof["solve"]["ms"] / sum(v["ms"] for v in prof.values())
-            roof_bytes, roof_ms = prof["solve"]["algorithmic_bytes"], share * total_ms / args.steps
-            roof_kernel = "constraint_stage_kernel<Solve> (%d launches per step, %.0f%% of the step)" % (launches, 100 * share)
-            roof_extra = {"share_of_step": share, "achieved_serialised_launches": prof["solve"]["algorithmic_bytes"] / (prof["solve"]["ms"] * 1e-3) / 1e9,
-                          "whole_step_achieved": alg_bytes_per_step / (total_ms / args.steps * 1e-3) / 1e9}
+        # Dominant kernel: constraint_stage_kernel<Solve>. Its launches sit inside a CUDA graph with programmatic-dependent-launch edges, so its time
+        # inside the timed region = (its share of the per-launch event-timed stage profile, taken right after the timed region on the same
+        # stream) x (the event-timed step). The fully serialised event-per-launch figure is reported next to it.
+        launches = prof["solve"]["launches"]
+        share = prof["solve"]["ms"] / sum(v["ms"] for v in prof.values())
+        roof_bytes, roof_ms = prof["solve"]["algorithmic_bytes"], share * total_ms / args.steps
+        roof_kernel = "constraint_stage_kernel<Solve> (%d launches per step, %.0f%% of the step)" % (launches, 100 * share)
+        roof_extra = {"share_of_step": share, "achieved_serialised_launches": prof["solve"]["algorithmic_bytes"] / (prof["solve"]["ms"] * 1e-3) / 1e9,
+                      "whole_step_achieved": alg_bytes_per_step / (total_ms / args.steps * 1e-3) / 1e9}
         achieved = roof_bytes / (roof_ms * 1e-3) / 1e9
         traffic_row = load_traffic(args.bodies, "constraint_stage_kernel<Solve>") if args.scene == "shape_pile" else None
         traffic = None
@@ -569,6 +568,15 @@ def main():
             "stage_profile_ms": {k: round(v["ms"], 4) for k, v in (prof or {}).items()},
         }
         line["ms_per_step_per_rank"] = per_rank_ms
+        if resident is not None:
+            # Headline end-to-end figure = the frame a host with the device-side contact update runs: per step it uploads the motion
+            # half of the bodies, the new prestep data and the new contact feature ids, and downloads the motion half of the bodies; accumulated
+            # impulses never cross the bus. The full-refresh frame (everything up, everything down) stays next to it.
+            line["e2e_full_refresh"] = line["e2e"]
+            line["e2e"] = {"value": resident["value"], "unit": resident["unit"], "h2d_bytes_per_step": resident["h2d_bytes_per_step"], "d2h_bytes_per_step": resident["d2h_bytes_per_step"],
+                           "ms_per_step": resident["ms_per_step"], "steps": resident["steps"],
+                           "path": "bepucuda_upload_body_motion + bepucuda_update_contacts (prestep + feature ids; impulses resident, redistributed on the device) + bepucuda_solve + bepucuda_download_body_motion",
+                           "topology": "unchanged between steps"}
         if topo is not None:
             line["e2e_topology_change"] = topo
         if resident is not None:

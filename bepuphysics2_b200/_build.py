@@ -67,8 +67,8 @@ def build(force=False, verbose=False, variant=None, defines=()):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "bepucuda.h"))
     flavours = [("fast", ["-DBEPU_NS=bepu_fast", "-prec-div=false", "-prec-sqrt=false"]), ("strict", ["-DBEPU_NS=bepu_strict", "-fmad=false"])]
-    # (object, source, extra flags); the heaviest units (dataflow, persistent) first so the pool starts them early
-    units = [("solver_%s_%d.o" % (name, unit), "bepu_solver_kernels.cu", flags + ["-DBEPU_UNIT=%d" % unit]) for unit in (5, 4, 1, 0, 2, 3) for name, flags in flavours]
+    # (object, source, extra flags)
+    units = [("solver_%s_%d.o" % (name, unit), "bepu_solver_kernels.cu", flags + ["-DBEPU_UNIT=%d" % unit]) for unit in (1, 0, 2, 3) for name, flags in flavours]
     units += [("layout.o", "bepu_layout_kernels.cu", []), ("coloring.o", "bepu_coloring.cu", []), ("api.o", "bepucuda_api.cu", [])]
     all_sources = [os.path.join(CSRC, f) for f in ("bepu_solver_kernels.cu", "bepu_layout_kernels.cu", "bepu_coloring.cu", "bepucuda_api.cu")] + headers
     # Nothing to compile when the library was built from exactly these sources (content stamp written after a build: survives a snapshot that

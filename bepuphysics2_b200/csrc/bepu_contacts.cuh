@@ -15,7 +15,7 @@ constexpr int kLanes = 32;
 
 // Row accessors. A constraint function sees its prestep rows through `P` and its accumulated impulses through `A`:
 //   GlobalRows / GlobalAcc : straight from the AOSOA-32 arrays in HBM. Prestep rows are read once per stage: load through L2 only
-//                            (ld.global.cg), which also keeps the persistent kernel coherent across grid barriers, where an L1 line filled
+//                            (ld.global.cg): an L1 line filled
 //                            before IncrementallyUpdateForSubstep rewrote a depth row would be stale.
 //   StagedRows / StagedAcc : the bundle's prestep + impulse block was bulk-copied (cp.async.bulk, one transaction per block) into this
 //                            warp's shared-memory slab; reads are conflict-free LDS (lane stride 4 B, row stride 128 B), impulse writes go

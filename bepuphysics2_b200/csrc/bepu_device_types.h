@@ -61,7 +61,6 @@ struct FrameParams {
     int32_t final_steps;       // integration steps for unconstrained bodies in the final pass
     int32_t angular_mode;
     int32_t integrate_velocity_for_kinematics;
-    uint32_t pass_base;        // dataflow mode: number of WarmStart/Solve passes executed since the body versions were last reset
     uint32_t exchange_base;    // peer sharding: number of cross-GPU exchange points executed before this solve (the flag barrier counts them)
     uint32_t shard_solve_index;  // peer sharding: solves since the arrival targets were last published (the arrival counters keep counting)
     int32_t tune[4];           // development knobs (env BEPUCUDA_TUNE=a,b,c,d; 0 = built-in default), never set in production
@@ -75,9 +74,6 @@ enum Stage : int32_t {
     kStageKinematicFirst = 4,
     kStageKinematic = 5,
     kStageFinalPose = 6,
-    // Dataflow mode: one substep's WarmStart pass + all Solve passes with per-body version dependencies instead of barriers.
-    // work_count = bundles of the whole active set, pad = (solve passes << 1) | (first substep ? 1 : 0).
-    kStageRegion = 7,
 };
 
 // One entry per warp of a stage launch: which bundle of which device type batch.
@@ -96,26 +92,12 @@ struct alignas(32) WorkRecord {
     int32_t live_lanes;
 };
 
-// Persistent-kernel stage program entry.
+// Stage program entry (built by bepucuda_end_constraints, walked by the host when it issues or captures a frame).
 struct StageOp {
     int32_t stage;
     int32_t work_begin;   // into the work item array (constraint stages) / unused
     int32_t work_count;   // warps of work (constraint stages), bodies (final pose), kinematics (kinematic stages)
     int32_t pad;
-};
-
-// Dataflow chain word per (constraint, body slot), same shape as the body reference arena: (degree of the body << 16) | rank of this constraint among
-// the body's constraints in device batch order. A lane writing body X at pass P expects version P * degree + rank and publishes version + 1.
-constexpr int kChainDegreeShift = 16;
-constexpr uint32_t kChainRankMask = 0xFFFFu;
-
-// Dataflow mode tables (built at bepucuda_end_constraints, see bepu_dataflow.cuh). Arrays parallel to the body reference arena are addressed as
-// refs + delta (in int32 elements).
-struct DataflowTables {
-    long long chain_delta;      // chain words
-    long long succ_delta;       // per (lane, body slot): work index of the bundle holding the NEXT constraint on that body, -1 after the last
-    const int2* dep_counts;     // per bundle: x = (lane, dynamic body) dependencies per pass, y = those that are the first constraint on their body
-    unsigned int* counters;     // per bundle: y + notifications received in the current pass (reset to y by the consumer)
 };
 
 // Peer sharding (bepucuda_shard_*): where the other ranks' body arrays and flag blocks are mapped in this process.

@@ -217,93 +217,6 @@ __global__ void bundle_flags_pass_kernel(const DeviceTypeBatch* __restrict__ tbs
         }
     }
 }
-// Dataflow chain words. Phase 0 (one launch per device batch, in order): rank = how many earlier device batches reference the body as dynamic.
-// Phase 1 (one launch): or in the body's total degree. Also resets nothing else; version words are reset by reset_versions_kernel.
-__global__ void chain_rank_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
-                                  long long chain_delta, int32_t* body_counter) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= work_count) return;
-    const WorkItem w = work[warp];
-    const DeviceTypeBatch tb = tbs[w.type_batch];
-    const int nb = bodies_per_type[tb.type_id];
-    for (int s = 0; s < nb; ++s) {
-        int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
-        uint32_t* c = reinterpret_cast<uint32_t*>(r + chain_delta);
-        const int32_t enc = *r;
-        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) { *c = 0; continue; }
-        const int idx = enc & kRefIndexMask;
-        const int rank = body_counter[idx];  // a dynamic body appears at most once per device batch: no race inside a launch
-        body_counter[idx] = rank + 1;
-        *c = (uint32_t)rank & kChainRankMask;
-    }
-}
-__global__ void chain_degree_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
-                                    long long chain_delta, const int32_t* __restrict__ body_counter, int32_t* error_flag) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= work_count) return;
-    const WorkItem w = work[warp];
-    const DeviceTypeBatch tb = tbs[w.type_batch];
-    const int nb = bodies_per_type[tb.type_id];
-    for (int s = 0; s < nb; ++s) {
-        const int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
-        uint32_t* c = reinterpret_cast<uint32_t*>(const_cast<int32_t*>(r) + chain_delta);
-        const int32_t enc = *r;
-        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
-        const int degree = body_counter[enc & kRefIndexMask];
-        if (degree > 0xFFFF) atomicExch(error_flag, 3);
-        *c |= (uint32_t)degree << kChainDegreeShift;
-    }
-}
-// Dataflow successor table. Phase 0 (one launch per device batch, LAST batch first): succ = work index of the bundle that holds the next constraint
-// on the body (-1 for the body's last constraint: passes are separated by kernel boundaries, nobody waits for it). Phase 1 (one launch): the
-// per-bundle dependency counts.
-__global__ void chain_succ_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, int work_base, const int32_t* __restrict__ bodies_per_type,
-                                  long long succ_delta, int32_t* next_bundle) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= work_count) return;
-    const WorkItem w = work[warp];
-    const DeviceTypeBatch tb = tbs[w.type_batch];
-    const int nb = bodies_per_type[tb.type_id];
-    for (int s = 0; s < nb; ++s) {
-        int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
-        const int32_t enc = *r;
-        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) { r[succ_delta] = -1; continue; }
-        const int idx = enc & kRefIndexMask;
-        r[succ_delta] = next_bundle[idx];  // a dynamic body appears at most once per device batch: no race inside a launch
-        next_bundle[idx] = work_base + warp;
-    }
-}
-__global__ void chain_finish_kernel(const DeviceTypeBatch* __restrict__ tbs, const WorkItem* __restrict__ work, int work_count, const int32_t* __restrict__ bodies_per_type,
-                                    long long chain_delta, long long succ_delta, const int32_t* __restrict__ next_bundle, int2* dep_counts) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= work_count) return;
-    const WorkItem w = work[warp];
-    const DeviceTypeBatch tb = tbs[w.type_batch];
-    const int nb = bodies_per_type[tb.type_id];
-    int deps = 0, first = 0;
-    for (int s = 0; s < nb; ++s) {
-        int32_t* r = tb.refs + ((size_t)w.bundle * nb + s) * 32 + lane;
-        const int32_t enc = *r;
-        if (enc < 0 || ((uint32_t)enc & kRefKinematicBit)) continue;
-        ++deps;
-        first += ((uint32_t)r[chain_delta] & kChainRankMask) == 0u;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        deps += __shfl_xor_sync(0xffffffffu, deps, o);
-        first += __shfl_xor_sync(0xffffffffu, first, o);
-    }
-    if (lane == 0) dep_counts[warp] = make_int2(deps, first);
-}
-__global__ void reset_counters_kernel(const int2* __restrict__ dep_counts, unsigned int* counters, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) counters[i] = (unsigned int)dep_counts[i].y;
-}
-__global__ void reset_versions_kernel(float4* velocity, int body_count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= body_count) return;
-    velocity[2 * (size_t)i].w = 0.0f;
-    velocity[2 * (size_t)i + 1].w = 0.0f;
-}
 __global__ void check_invariant_kernel(int body_count, const int32_t* __restrict__ sync_refcount, const unsigned long long* __restrict__ sync_mask, int32_t* error_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= body_count) return;
@@ -363,33 +276,6 @@ void launch_transpose_in_all(const DeviceTypeBatch* tbs, const TransposeDesc* de
 void launch_transpose_out_all(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, int W, int what, cudaStream_t s) {
     if (work_count <= 0) return;
     transpose_out_all_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, descs, work, work_count, W, what);
-}
-void launch_chain_rank(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, int32_t* body_counter, cudaStream_t s) {
-    if (work_count <= 0) return;
-    chain_rank_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, chain_delta, body_counter);
-}
-void launch_chain_degree(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, const int32_t* body_counter,
-                         int32_t* error_flag, cudaStream_t s) {
-    if (work_count <= 0) return;
-    chain_degree_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, chain_delta, body_counter, error_flag);
-}
-void launch_chain_succ(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, int work_base, const int32_t* bodies_per_type, long long succ_delta, int32_t* next_bundle,
-                       cudaStream_t s) {
-    if (work_count <= 0) return;
-    chain_succ_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, work_base, bodies_per_type, succ_delta, next_bundle);
-}
-void launch_chain_finish(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, long long succ_delta,
-                         const int32_t* next_bundle, int2* dep_counts, cudaStream_t s) {
-    if (work_count <= 0) return;
-    chain_finish_kernel<<<blocks_for((size_t)work_count * 32, 128), 128, 0, s>>>(tbs, work, work_count, bodies_per_type, chain_delta, succ_delta, next_bundle, dep_counts);
-}
-void launch_reset_counters(const int2* dep_counts, unsigned int* counters, int n, cudaStream_t s) {
-    if (n <= 0) return;
-    reset_counters_kernel<<<blocks_for((size_t)n, 256), 256, 0, s>>>(dep_counts, counters, n);
-}
-void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s) {
-    if (body_count <= 0) return;
-    reset_versions_kernel<<<blocks_for(body_count, 256), 256, 0, s>>>(velocity, body_count);
 }
 void launch_redistribute_impulses(const DeviceTypeBatch* tbs, const TransposeDesc* descs, const WorkItem* work, int work_count, cudaStream_t s) {
     if (work_count <= 0) return;

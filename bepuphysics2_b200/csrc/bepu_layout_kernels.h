@@ -36,17 +36,6 @@ struct CopyChunk {
     size_t bytes;
 };
 void launch_batched_copy(const CopyChunk* chunks, int chunk_count, cudaStream_t s);
-// Dataflow chain words (see kChainDegreeShift): chain array = refs array + chain_delta (in int32 elements).
-void launch_chain_rank(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, int32_t* body_counter, cudaStream_t s);
-void launch_chain_degree(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, const int32_t* body_counter,
-                         int32_t* error_flag, cudaStream_t s);
-// Dataflow successor table and per-bundle dependency counts (see DataflowTables).
-void launch_chain_succ(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, int work_base, const int32_t* bodies_per_type, long long succ_delta, int32_t* next_bundle,
-                       cudaStream_t s);
-void launch_chain_finish(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, long long chain_delta, long long succ_delta,
-                         const int32_t* next_bundle, int2* dep_counts, cudaStream_t s);
-void launch_reset_counters(const int2* dep_counts, unsigned int* counters, int n, cudaStream_t s);
-void launch_reset_versions(float4* velocity, int body_count, cudaStream_t s);
 void launch_ownership_pass1(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int sync_batch_count, int body_count,
                             int32_t* first_batch, int32_t* sync_refcount, unsigned long long* sync_mask, int32_t* error_flag, cudaStream_t s);
 void launch_ownership_rest(const DeviceTypeBatch* tbs, const WorkItem* work, int work_count, const int32_t* bodies_per_type, int body_count, const int32_t* first_batch,
@@ -85,15 +74,6 @@ struct SolverLaunchers {
     void (*constraint_stage)(int stage, const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s);
     void (*kinematic_stage)(int stage, const int32_t* kinematics, int count, const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
     void (*final_pose)(const BodyBuffers& B, const FrameParams* fp, cudaStream_t s);
-    // Persistent cooperative kernel: runs a whole stage program with a grid barrier between ops. Returns a cudaError_t.
-    // barrier_counter must be zero at launch. blocks_per_sm <= 0 selects the default.
-    int (*persistent)(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
-                      unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
-    // Dataflow mode: one WarmStart / Solve pass over all device batches in one cooperative launch, per-body version dependencies (DataflowTables)
-    // instead of a kernel boundary per (batch, stage). pass_offset / ws_pass_offset: index of this pass / of its substep's WarmStart pass within the
-    // solve. error_flag is set to 4 if a dependency never arrives. contacts_only selects the instantiation whose type switch holds the contact types only.
-    int (*dataflow_pass)(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
-                         uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s);
     // Peer-sharded WarmStartFirst / WarmStart / Solve stage: like constraint_stage, and every written body record also goes to the ranks named by the
     // per-(lane, slot) destination masks at refs + peer_delta (launch_fill_peer_masks).
     void (*constraint_stage_sharded)(int stage, const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers,

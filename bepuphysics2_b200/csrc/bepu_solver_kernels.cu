@@ -1,14 +1,8 @@
 // Compiled per numerics flavour (-DBEPU_NS=bepu_fast with FMA contraction / -DBEPU_NS=bepu_strict -fmad=false) and per unit (-DBEPU_UNIT=n),
 // so that the big per-type switch of each kernel gets its own translation unit and the build parallelises:
 //   0 WarmStartFirst stage   1 WarmStart stage   2 Solve stage   3 Incremental stage + kinematic + final pose + launcher table
-//   4 persistent kernel      5 dataflow pass kernels
 #include <atomic>
 #include "bepu_solver_kernels.cuh"
-#if BEPU_UNIT == 4
-#include "bepu_persistent.cuh"
-#elif BEPU_UNIT == 5
-#include "bepu_dataflow.cuh"
-#endif
 #include "bepu_layout_kernels.h"
 
 namespace BEPU_NS {
@@ -19,12 +13,7 @@ void launch_stage_solve(const WorkRecord* records, const int32_t* ref_rows, int 
 void launch_stage_warm_start_first_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
 void launch_stage_warm_start_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
 void launch_stage_solve_sharded(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, const ShardPeers& peers, long long peer_delta, const ShardStage& shard, cudaStream_t s);
-int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
-                           unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s);
-int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
-                         uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s);
 
-#if BEPU_UNIT <= 3
 #ifndef BEPU_DEEP_MINB
 #define BEPU_DEEP_MINB 12
 #endif
@@ -85,7 +74,6 @@ static void launch_stage_t(const WorkRecord* records, const int32_t* ref_rows, i
     if (STAGE != kStageIncremental && work_count >= kDeepBatchBundles) launch_stage_variant<STAGE, BEPU_DEEP_MINB>(records, ref_rows, work_count, B, fp, launch_flags, s);
     else launch_stage_variant<STAGE, 1>(records, ref_rows, work_count, B, fp, launch_flags, s);
 }
-#endif
 
 #if BEPU_UNIT == 0
 void launch_stage_warm_start_first(const WorkRecord* records, const int32_t* ref_rows, int work_count, const BodyBuffers& B, const FrameParams* fp, int launch_flags, cudaStream_t s) {
@@ -139,19 +127,9 @@ static void launch_final_pose(const BodyBuffers& B, const FrameParams* fp, cudaS
     if (B.count <= 0) return;
     final_pose_kernel<<<(unsigned)((B.count + 255) / 256), 256, 0, s>>>(B, fp);
 }
-static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_persistent_unit, &launch_dataflow_unit, &launch_constraint_stage_sharded};
-#elif BEPU_UNIT == 4
-int launch_persistent_unit(const StageOp* program, int op_count, const WorkRecord* records, const int32_t* kinematics, const BodyBuffers& B, const FrameParams* fp,
-                           unsigned int* barrier_counter, int blocks_per_sm, cudaStream_t s) {
-    return launch_persistent(program, op_count, records, kinematics, B, fp, barrier_counter, blocks_per_sm, s);
-}
-#elif BEPU_UNIT == 5
-int launch_dataflow_unit(int stage, const WorkRecord* records, int work_count, const DataflowTables& df, const BodyBuffers& B, const FrameParams* fp, uint32_t pass_offset,
-                         uint32_t ws_pass_offset, int pose_stamped, int32_t* error_flag, int blocks_per_sm, int contacts_only, cudaStream_t s) {
-    return launch_dataflow_pass(stage, records, work_count, df, B, fp, pass_offset, ws_pass_offset, pose_stamped, error_flag, blocks_per_sm, contacts_only, s);
-}
+static const bepucuda::SolverLaunchers kLaunchers = {&launch_constraint_stage, &launch_kinematic_stage, &launch_final_pose, &launch_constraint_stage_sharded};
 #else
-#error "BEPU_UNIT must be 0..5"
+#error "BEPU_UNIT must be 0..3"
 #endif
 
 }  // namespace BEPU_NS

@@ -18,16 +18,10 @@ using namespace bepucuda;
 
 // ---- body records: one 32-byte record = one DRAM sector = ONE 256-bit load/store (LDG.E.256 / STG.E.256, new on sm_100) ----------------
 struct F8 { float a, b, c, d, e, f, g, h; };
-// Body records: one 256-bit access per 32-B record. In the per-stage kernels the records are marked evict-last in L2 (and never allocate in
-// L1) so that the body arrays stay L2-resident while the constraint rows stream past them (those are fetched evict-first, see the bulk copies);
-// the persistent / dataflow kernels, which rely on L2 as the coherence point across grid barriers inside one launch, keep plain ld/st.cg.
-#if defined(BEPU_UNIT) && BEPU_UNIT <= 3
+// Body records: one 256-bit access per 32-B record, marked evict-last in L2 (and never allocated in L1: other warps of the launch sequence write
+// them) so that the body arrays stay L2-resident while the constraint rows stream past them (those are fetched evict-first, see the bulk copies).
 #define BEPU_BODY_LD "ld.global.L1::no_allocate.L2::evict_last.v8.f32"
 #define BEPU_BODY_ST "st.global.L1::no_allocate.L2::evict_last.v8.f32"
-#else
-#define BEPU_BODY_LD "ld.global.cg.v8.f32"
-#define BEPU_BODY_ST "st.global.cg.v8.f32"
-#endif
 BEPU_DI F8 ld256(const float4* p) {
     F8 r;
     asm volatile(BEPU_BODY_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -263,7 +257,7 @@ template <int STAGE, class PR, class AR>
 BEPU_DI void run_bundle_rows(const WorkRecord& rec, int lane, PR p, AR a, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
     run_bundle_rows<STAGE, false>(rec, lane, p, a, enc0, enc1, B, fp);
 }
-// Rows straight from HBM (persistent / dataflow kernels, and the incremental stage everywhere).
+// Rows straight from HBM (the incremental stage).
 template <int STAGE>
 BEPU_DI void run_bundle(const WorkRecord& rec, int lane, uint32_t enc0, uint32_t enc1, const BodyBuffers& B, const FrameParams& fp) {
     run_bundle_rows<STAGE>(rec, lane, GlobalRows{rec.prestep + lane}, GlobalAcc{rec.impulses + lane}, enc0, enc1, B, fp);

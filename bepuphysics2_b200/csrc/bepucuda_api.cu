@@ -165,7 +165,7 @@ struct bepucuda_ctx {
     bool constraints_open = false, constraints_ready = false, data_dirty = false, descs_dirty = false;
     std::vector<SourceTypeBatch> sources;
     ChunkArena raw_arena, pinned_arena;
-    DeviceBuffer chain32, succ32, next_bundle, dep_counts, df_counters, body_counter, record_table, ref_rows, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, barrier_dev, error_dev;
+    DeviceBuffer record_table, ref_rows, source_bundle_flags, refs32, prestep32, impulses32, tb_table, tdesc_table, work_table, map_table, bodies_per_type, kinematics_dev, program_dev, frame_params_dev, error_dev;
     std::vector<DeviceTypeBatch> tbs;
     std::vector<TransposeDesc> tdescs;
     std::vector<WorkItem> work;                 // grouped by device batch, then the incremental list
@@ -201,7 +201,6 @@ struct bepucuda_ctx {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_valid = false;
-    bool dataflow_without_graph = false;  // the driver refused to capture cooperative launches: passes are issued directly
 
     bepucuda_timings timings{};
     int64_t h2d_accum = 0;
@@ -212,8 +211,6 @@ struct bepucuda_ctx {
     struct ChunkStage { void* host = nullptr; size_t capacity = 0; cudaEvent_t done = nullptr; };
     ChunkStage chunk_stage[4];             // pinned ring for chunk tables (a table must outlive its H2D copy)
     int chunk_stage_next = 0;
-    uint32_t pass_counter = 0;      // dataflow mode: WarmStart/Solve passes since the body versions were reset
-    bool versions_dirty = true;     // velocity-record padding words do not hold valid versions
     cudaEvent_t user_events[16] = {};
     DeviceBuffer color_refs, color_priorities, color_body_min, color_body_mask, color_out, color_lists, color_counts;  // bepucuda_color_constraints
     std::vector<cudaEvent_t> profile_events;
@@ -320,33 +317,9 @@ void issue_stage_sequence(bepucuda_ctx* ctx, cudaStream_t s, int64_t* launches) 
     // Row prefetch in the PDL prologue (see constraint_stage_kernel): allowed when the kernel launched immediately before neither rewrites this
     // batch's prestep rows (the incremental contact update does) nor its impulses (a stage of the same batch does: single-batch scenes).
     const StageOp* previous = nullptr;  // last launched op
-    uint32_t pass_offset = 0, ws_pass_offset = 0, exchange_index = 0;
-    bool first_substep = true;
+    uint32_t exchange_index = 0;
     const bool fused_pushes = ctx->peer_mode && !ctx->body_masks.empty();
-    DataflowTables df{};
-    int contacts_only = 1;
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && ctx->all_work_count > 0) {
-        df.chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
-        df.succ_delta = ctx->succ32.as<int32_t>() - ctx->refs32.as<int32_t>();
-        df.dep_counts = ctx->dep_counts.as<int2>();
-        df.counters = ctx->df_counters.as<unsigned int>();
-        for (const SourceTypeBatch& src : ctx->sources) contacts_only &= src.type_id <= 17;
-        launch_reset_counters(df.dep_counts, df.counters, ctx->all_work_count, s);
-        cudaMemsetAsync(ctx->error_dev.ptr, 0, 32, s);  // stall report of this solve (see report_stall)
-        ++n;
-    }
     for (const StageOp& op : ctx->program) {
-        if (op.pad == 1 && op.stage <= kStageSolve) {
-            // dataflow pass (BEPUCUDA_EXEC_DATAFLOW)
-            if (op.stage != kStageSolve) { ws_pass_offset = pass_offset; first_substep = op.stage == kStageWarmStartFirst; }
-            const int rc = ctx->launchers->dataflow_pass(op.stage, records, op.work_count, df, ctx->B, fp, pass_offset, ws_pass_offset, first_substep ? 0 : 1, ctx->error_dev.as<int32_t>(),
-                                                         ctx->cfg.reserved[0], contacts_only, s);
-            if (rc != 0) ctx->exchange_failed = true;  // reported by the caller
-            ++pass_offset;
-            previous = &op;
-            ++n;
-            continue;
-        }
         if (ctx->peer_mode && op.pad == -1) {
             // all ranks meet (nothing to push): before the first stage of a solve; around the incremental contact update, which reads the velocities
             // of shared bodies -- after every peer's last Solve stage has completed, before any peer's WarmStart stage stores into this rank's
@@ -437,14 +410,6 @@ void build_program(bepucuda_ctx* ctx) {
             ctx->program.push_back({kStageKinematicFirst, 0, kin, 0});
         }
         if (ctx->peer_mode) ctx->program.push_back({kStageKinematic, 0, 0, -1});  // rank barrier (see issue_stage_sequence)
-        if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
-            // one op per PASS over all device batches (pad = 1): the order inside a pass is kept by per-body versions, not by kernel boundaries
-            if (ctx->all_work_count > 0) {
-                ctx->program.push_back({s == 0 ? kStageWarmStartFirst : kStageWarmStart, 0, ctx->all_work_count, 1});
-                for (int it = 0; it < ctx->iterations[s]; ++it) ctx->program.push_back({kStageSolve, 0, ctx->all_work_count, 1});
-            }
-            continue;
-        }
         // pad carries the device batch index + 2 in peer mode (every rank runs the exchange of every batch, also of one it has no constraint in)
         for (size_t b = 0; b < ctx->batch_work.size(); ++b) {
             auto& bw = ctx->batch_work[b];
@@ -572,9 +537,9 @@ int32_t bepucuda_create(const bepucuda_config* cfg, bepucuda_ctx** out) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return BEPUCUDA_ERR_NO_DEVICE;  // no CPU fallback, by design
     if (cfg->device_ordinal < 0 || cfg->device_ordinal >= count) return BEPUCUDA_ERR_INVALID_ARGUMENT;
+    if (cfg->execution_mode != BEPUCUDA_EXEC_GRAPH && cfg->execution_mode != BEPUCUDA_EXEC_STREAM) return BEPUCUDA_ERR_INVALID_ARGUMENT;  // 1 and 3 are retired modes
     bepucuda_ctx* ctx = new bepucuda_ctx();
     ctx->cfg = *cfg;
-    if (getenv("BEPUCUDA_DATAFLOW_NOGRAPH")) ctx->dataflow_without_graph = true;  // development knob
     if (const char* tune = getenv("BEPUCUDA_TUNE")) sscanf(tune, "%d,%d,%d,%d", &ctx->tune[0], &ctx->tune[1], &ctx->tune[2], &ctx->tune[3]);
     ctx->device = cfg->device_ordinal;
     ctx->launchers = cfg->strict_fp ? get_launchers_bepu_strict() : get_launchers_bepu_fast();
@@ -587,8 +552,6 @@ int32_t bepucuda_create(const bepucuda_config* cfg, bepucuda_ctx** out) {
         if (e == cudaSuccess) e = cudaEventCreate(ev);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->frame_params_host, sizeof(FrameParams));
     if (e == cudaSuccess) e = ctx->frame_params_dev.reserve(sizeof(FrameParams));
-    if (e == cudaSuccess) e = ctx->barrier_dev.reserve(2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(ctx->barrier_dev.ptr, 0, 2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = ctx->error_dev.reserve(8 * sizeof(int32_t));
     if (e != cudaSuccess) {
         bepucuda_destroy(ctx);
@@ -609,8 +572,8 @@ int32_t bepucuda_destroy(bepucuda_ctx* ctx) {
     invalidate_graph(ctx);
     for (void* p : ctx->opened_ipc) cudaIpcCloseMemHandle(p);
     DeviceBuffer* bufs[] = {&ctx->shard_flags, &ctx->pushes_dev, &ctx->peer32, &ctx->body_masks_dev, &ctx->boundary_flags_dev, &ctx->raw_bodies, &ctx->pose, &ctx->velocity, &ctx->inertia_local, &ctx->inertia_world, &ctx->constrained, &ctx->first_batch, &ctx->sync_refcount,
-                            &ctx->sync_mask, &ctx->chunk_table, &ctx->chain32, &ctx->succ32, &ctx->next_bundle, &ctx->dep_counts, &ctx->df_counters, &ctx->body_counter, &ctx->record_table, &ctx->ref_rows, &ctx->color_refs, &ctx->color_priorities, &ctx->color_body_min, &ctx->color_body_mask, &ctx->color_out, &ctx->color_lists, &ctx->color_counts, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
-                            &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->barrier_dev, &ctx->error_dev, &ctx->exchange_staging};
+                            &ctx->sync_mask, &ctx->chunk_table, &ctx->record_table, &ctx->ref_rows, &ctx->color_refs, &ctx->color_priorities, &ctx->color_body_min, &ctx->color_body_mask, &ctx->color_out, &ctx->color_lists, &ctx->color_counts, &ctx->source_bundle_flags, &ctx->refs32, &ctx->prestep32, &ctx->impulses32, &ctx->tb_table, &ctx->tdesc_table, &ctx->work_table, &ctx->map_table,
+                            &ctx->bodies_per_type, &ctx->kinematics_dev, &ctx->program_dev, &ctx->frame_params_dev, &ctx->error_dev, &ctx->exchange_staging};
     for (auto b : bufs) b->release();
     ctx->raw_arena.release();
     ctx->pinned_arena.release();
@@ -716,8 +679,6 @@ int32_t bepucuda_upload_bodies(bepucuda_ctx* ctx, const void* body_dynamics, int
         CK(cudaMemcpyAsync(ctx->raw_bodies.ptr, body_dynamics, n * 128, cudaMemcpyHostToDevice, ctx->stream));
         ctx->h2d_accum += (int64_t)n * 128;
         launch_split_bodies(ctx->raw_bodies.ptr, body_count, ctx->B, ctx->stream);
-        ctx->pass_counter = 0;       // split_bodies zeroes the padding words = version 0 everywhere
-        ctx->versions_dirty = false;
         CK(cudaGetLastError());
     }
     return BEPUCUDA_OK;
@@ -948,9 +909,7 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
         impulse_floats += (size_t)ctx->tbs[i].bundle_count * t->impulse_rows * 32;
     }
     CK(ctx->refs32.reserve(refs_floats * 4 + 1024));  // slack: solver warps always read two body-reference rows
-    CK(ctx->chain32.reserve(refs_floats * 4 + 1024));
     ctx->refs_words = refs_floats;
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) CK(ctx->succ32.reserve(refs_floats * 4 + 1024));
     CK(ctx->prestep32.reserve(prestep_floats * 4 + 4));
     CK(ctx->impulses32.reserve(impulse_floats * 4 + 4));
     CK(ctx->map_table.reserve(maps.size() * 4 + 4));
@@ -1070,29 +1029,6 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
             return fail(ctx, BEPUCUDA_ERR_CUDA, "end_constraints: the exchange callback failed (constrained mask)");
         launch_narrow_i32(ctx->exchange_staging.as<int32_t>(), ctx->constrained.as<uint8_t>(), (size_t)ctx->body_count, ctx->stream);
     }
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) {
-        // rank of each constraint among its bodies' constraints: one small launch per device batch, in order
-        CK(ctx->body_counter.reserve(nb * 4));
-        CK(cudaMemsetAsync(ctx->body_counter.ptr, 0, nb * 4, ctx->stream));
-        const long long chain_delta = ctx->chain32.as<int32_t>() - ctx->refs32.as<int32_t>();
-        for (auto& bw : ctx->batch_work)
-            launch_chain_rank(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>() + bw.first, bw.second, ctx->bodies_per_type.as<int32_t>(), chain_delta,
-                              ctx->body_counter.as<int32_t>(), ctx->stream);
-        launch_chain_degree(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), chain_delta,
-                            ctx->body_counter.as<int32_t>(), ctx->error_dev.as<int32_t>(), ctx->stream);
-        // successor bundles (device batches visited last to first) and per-bundle dependency counts
-        const long long succ_delta = ctx->succ32.as<int32_t>() - ctx->refs32.as<int32_t>();
-        CK(ctx->next_bundle.reserve(nb * 4));
-        CK(ctx->dep_counts.reserve((size_t)std::max(ctx->all_work_count, 1) * sizeof(int2)));
-        CK(ctx->df_counters.reserve((size_t)std::max(ctx->all_work_count, 1) * 4));
-        launch_fill_i32(ctx->next_bundle.as<int32_t>(), nb, -1, ctx->stream);
-        for (auto bw = ctx->batch_work.rbegin(); bw != ctx->batch_work.rend(); ++bw)
-            launch_chain_succ(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>() + bw->first, bw->second, bw->first, ctx->bodies_per_type.as<int32_t>(), succ_delta,
-                              ctx->next_bundle.as<int32_t>(), ctx->stream);
-        launch_chain_finish(ctx->tb_table.as<DeviceTypeBatch>(), ctx->work_table.as<WorkItem>(), ctx->all_work_count, ctx->bodies_per_type.as<int32_t>(), chain_delta, succ_delta,
-                            ctx->next_bundle.as<int32_t>(), ctx->dep_counts.as<int2>(), ctx->stream);
-        ctx->versions_dirty = true;
-    }
     if (ctx->peer_mode && !ctx->body_masks.empty()) {
         // fused pushes: per body reference, the other ranks that need what this rank's constraint writes
         if ((int)ctx->body_masks.size() != ctx->body_count) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "end_constraints: bepucuda_shard_set_body_masks was called for another body count");
@@ -1135,7 +1071,6 @@ int32_t bepucuda_end_constraints(bepucuda_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));  // also guarantees the std::vector sources of the copies above were consumed
     if (err == 1) return fail(ctx, BEPUCUDA_ERR_BATCH_INVARIANT, "end_constraints: a synchronized batch references the same dynamic body more than once");
     if (err == 2) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "end_constraints: body reference out of range");
-    if (err == 3) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "end_constraints: a body has more than 65535 constraints (dataflow mode limit)");
 
     ctx->timings.constraint_count = constraint_count;
     ctx->timings.device_batch_count = (int)batch_tbs.size();
@@ -1244,8 +1179,6 @@ int32_t bepucuda_upload_body_motion(bepucuda_ctx* ctx, const void* body_dynamics
     }
     CK(cudaGetLastError());
     ctx->h2d_accum += (int64_t)n * 64;
-    ctx->pass_counter = 0;  // the velocity padding words (dataflow versions) were zeroed
-    ctx->versions_dirty = false;
     return BEPUCUDA_OK;
 }
 
@@ -1290,12 +1223,6 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     // frame parameters (previous frame's copy has completed by stream order only after its graph; wait for it before reusing the pinned struct)
     CK(cudaEventSynchronize(ctx->ev_solve_end));
     compute_frame_params(ctx, dt, ctx->frame_params_host);
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && ctx->versions_dirty) {
-        launch_reset_versions(ctx->velocity.as<float4>(), ctx->body_count, ctx->stream);
-        ctx->pass_counter = 0;
-        ctx->versions_dirty = false;
-    }
-    ctx->frame_params_host->pass_base = ctx->pass_counter;
     ctx->frame_params_host->exchange_base = ctx->exchange_counter;
     ctx->frame_params_host->shard_solve_index = ctx->shard_solve_index;
     CK(cudaMemcpyAsync(ctx->frame_params_dev.ptr, ctx->frame_params_host, sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
@@ -1309,13 +1236,7 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
     }
     CK(cudaEventRecord(ctx->ev_solve_begin, ctx->stream));
     int64_t launches = 0;
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_PERSISTENT) {
-        CK(cudaMemsetAsync(ctx->barrier_dev.ptr, 0, sizeof(unsigned int), ctx->stream));
-        int rc = ctx->launchers->persistent(ctx->program_dev.as<StageOp>(), (int)ctx->program.size(), ctx->record_table.as<WorkRecord>(), ctx->kinematics_dev.as<int32_t>(), ctx->B,
-                                            ctx->frame_params_dev.as<FrameParams>(), ctx->barrier_dev.as<unsigned int>(), ctx->cfg.reserved[0], ctx->stream);
-        if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "persistent kernel launch");
-        launches = 1;
-    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_GRAPH || (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && !ctx->dataflow_without_graph)) {
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_GRAPH) {
         if (!ctx->graph_valid) {
             ctx->exchange_failed = false;
             CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -1324,35 +1245,21 @@ int32_t bepucuda_solve(bepucuda_ctx* ctx, float dt) {
             cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->graph);
             if (e == cudaSuccess && ctx->exchange_failed) e = cudaErrorUnknown;
             if (e == cudaSuccess) e = cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0);
-            if (e != cudaSuccess) {
-                if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_DATAFLOW) return cuda_fail(ctx, e, "graph capture");
-                // cooperative launches could not be captured / instantiated on this driver: issue the passes directly from now on
-                cudaGetLastError();
-                invalidate_graph(ctx);
-                ctx->dataflow_without_graph = true;
-            } else {
-                ctx->graph_valid = true;
-                ctx->timings.kernel_launches = n;
-            }
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "graph capture");
+            ctx->graph_valid = true;
+            ctx->timings.kernel_launches = n;
         }
         if (ctx->graph_valid) {
             CK(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
             launches = ctx->timings.kernel_launches;
         }
     }
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW && ctx->dataflow_without_graph) {
-        ctx->exchange_failed = false;
-        issue_stage_sequence(ctx, ctx->stream, &launches);
-        CK(cudaGetLastError());
-        if (ctx->exchange_failed) return fail(ctx, BEPUCUDA_ERR_CUDA, "solve: a dataflow pass could not be launched");
-    } else if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_STREAM) {
+    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_STREAM) {
         issue_stage_sequence(ctx, ctx->stream, &launches);
         CK(cudaGetLastError());
         if (ctx->exchange_failed) return fail(ctx, BEPUCUDA_ERR_CUDA, "solve: the exchange callback failed");
     }
     CK(cudaEventRecord(ctx->ev_solve_end, ctx->stream));
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW)
-        for (int it : ctx->iterations) ctx->pass_counter += (uint32_t)it + 1u;  // body versions keep counting across solves
     if (ctx->peer_mode) { ctx->exchange_counter += ctx->exchanges_per_solve; ++ctx->shard_solve_index; }  // the flag barrier and the arrival counters keep counting across solves
     ctx->have_solve = true;
     ctx->timings.kernel_launches = launches;
@@ -1386,17 +1293,6 @@ static int check_device_error_flag(bepucuda_ctx* ctx) {
         CK(cudaMemcpyAsync(&e, ctx->error_dev.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (e == 5) return fail(ctx, BEPUCUDA_ERR_CUDA, "sharded solve: a peer rank never reached an exchange point (flag barrier timed out); results are invalid");
-    }
-    if (ctx->cfg.execution_mode != BEPUCUDA_EXEC_DATAFLOW) return BEPUCUDA_OK;
-    int32_t err[8] = {};
-    CK(cudaMemcpyAsync(err, ctx->error_dev.ptr, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (err[0] == 4) {
-        static const char* what[] = {"?", "bundle notification counter", "body velocity version", "world inertia stamp", "pose stamp"};
-        char msg[256];
-        snprintf(msg, sizeof(msg), "dataflow solve: a dependency never arrived (spin limit hit; %s: expected %u, observed %u, at %u; raw %d %d %d %d %d %d); results are invalid",
-                 what[err[1] >= 0 && err[1] <= 4 ? err[1] : 0], (unsigned)err[2], (unsigned)err[3], (unsigned)err[4], err[0], err[1], err[2], err[3], err[4], err[5]);
-        return fail(ctx, BEPUCUDA_ERR_CUDA, msg);
     }
     return BEPUCUDA_OK;
 }
@@ -1489,7 +1385,6 @@ int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_prof
     if (ctx && ctx->exchange) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages: not available with sharded batches");
     if (!ctx || !out || !(dt > 0)) return fail(ctx, BEPUCUDA_ERR_INVALID_ARGUMENT, "profile_stages: bad arguments");
     if (!ctx->constraints_ready) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages before end_constraints");
-    if (ctx->cfg.execution_mode == BEPUCUDA_EXEC_DATAFLOW) return fail(ctx, BEPUCUDA_ERR_BAD_STATE, "profile_stages: not available in dataflow mode (no per-stage launches)");
     CK(cudaSetDevice(ctx->device));
     std::memset(out, 0, sizeof(*out));
     { int rc = refresh_device_rows(ctx); if (rc != BEPUCUDA_OK) return rc; }

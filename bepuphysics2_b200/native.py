@@ -86,7 +86,7 @@ class StageProfile(C.Structure):
         return {n: {"ms": self.ms[i], "launches": self.launches[i], "algorithmic_bytes": self.algorithmic_bytes[i]} for i, n in enumerate(self.STAGE_NAMES) if self.launches[i]}
 
 
-EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW = 0, 1, 2, 3
+EXEC_GRAPH, EXEC_STREAM = 0, 2  # 1 and 3 (persistent / dataflow kernels) were removed: slower than the graph on every configuration
 
 # Every symbol include/bepucuda.h declares (checked by the CPU test-suite).
 C_ABI_SYMBOLS = [
@@ -330,12 +330,11 @@ class Simulation:
 class CudaTimestepper:
     """The Solve slot of DefaultTimestepper.Timestep (DefaultTimestepper.cs:L28-43) on the GPU, through the C ABI only."""
 
-    def __init__(self, simulation, device=0, strict_fp=False, execution_mode=EXEC_GRAPH, persistent_blocks_per_sm=0, disable_pdl=False):
+    def __init__(self, simulation, device=0, strict_fp=False, execution_mode=EXEC_GRAPH, disable_pdl=False):
         self._cuda, self._host = load_libraries()
         self.sim = simulation
         cfg = Config()
         cfg.device_ordinal, cfg.strict_fp, cfg.execution_mode = device, int(bool(strict_fp)), execution_mode
-        cfg.reserved[0] = persistent_blocks_per_sm or int(os.environ.get("BEPUCUDA_BLOCKS_PER_SM", "0"))  # development knob
         cfg.reserved[1] = int(bool(disable_pdl))
         ctx = C.c_void_p()
         rc = self._cuda.bepucuda_create(C.byref(cfg), C.byref(ctx))

@@ -43,10 +43,10 @@ typedef struct bepucuda_ctx bepucuda_ctx;
 /* How the (substep, stage, batch) sequence of Solver.Solve (Solver_Solve.cs:L1419-1479) is sequenced
  * on the device. */
 enum bepucuda_execution_mode {
-    BEPUCUDA_EXEC_GRAPH = 0,      /* one kernel per (batch, stage), whole frame captured in a CUDA graph */
-    BEPUCUDA_EXEC_PERSISTENT = 1, /* one cooperative kernel per frame, grid barrier per (batch, stage) */
-    BEPUCUDA_EXEC_STREAM = 2,     /* plain stream launches, no graph (debug / profiling with ncu) */
-    BEPUCUDA_EXEC_DATAFLOW = 3    /* one cooperative kernel per frame; per-body version dependencies instead of a barrier per (batch, stage) */
+    BEPUCUDA_EXEC_GRAPH = 0,      /* one kernel per (batch, stage) chained by programmatic dependent launch, whole frame captured in a CUDA graph */
+    BEPUCUDA_EXEC_STREAM = 2      /* the same launches issued directly on the stream, no graph (profiling with ncu; the exchange-callback sharding) */
+    /* 1 and 3 were a persistent cooperative kernel (grid barrier per stage) and a dataflow kernel (per-body version dependencies); both measured
+     * slower than the graph on every benchmark configuration (profiles/r02_summary.md) and were removed: bepucuda_create rejects them. */
 };
 
 typedef struct bepucuda_config {
@@ -55,7 +55,7 @@ typedef struct bepucuda_config {
      * (RyuJIT does not contract Vector<float> expressions). 0 = FMA contraction on (fast). */
     int32_t strict_fp;
     int32_t execution_mode;   /* enum bepucuda_execution_mode */
-    int32_t reserved[5];      /* reserved[0]: persistent mode CTAs per SM (0 = default 1); reserved[1]: 1 disables programmatic dependent launch between stage kernels */
+    int32_t reserved[5];      /* reserved[0]: unused; reserved[1]: 1 disables programmatic dependent launch between stage kernels */
 } bepucuda_config;
 
 /* Declarative stand-in for the user's IPoseIntegratorCallbacks struct (BepuPhysics/PoseIntegrator.cs:L42-94).

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from bepuphysics2_b200 import scenes
-from bepuphysics2_b200.native import EXEC_DATAFLOW, EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
+from bepuphysics2_b200.native import EXEC_GRAPH, EXEC_STREAM
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -28,7 +28,7 @@ def test_box_stack_config1_bit_exact(libs):
     assert got["timings"]["device_batch_count"] == 2
 
 
-@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_STREAM])
 def test_box_stack_substepped_all_execution_modes(libs, mode):
     _parity(scenes.box_stacks(8, 12), mode=mode, substeps=4, velocity_iterations=2, frames=3)
 
@@ -43,8 +43,8 @@ def test_shape_pile_nonconvex_types_bit_exact(libs):
     _parity(scenes.shape_pile(2000, seed=7, nonconvex_fraction=0.5), substeps=3, velocity_iterations=[1, 2, 3])
 
 
-def test_shape_pile_persistent_mode_bit_exact(libs):
-    _parity(scenes.shape_pile(5000, seed=11), mode=EXEC_PERSISTENT, substeps=4, velocity_iterations=2, frames=2)
+def test_shape_pile_stream_mode_bit_exact(libs):
+    _parity(scenes.shape_pile(5000, seed=11), mode=EXEC_STREAM, substeps=4, velocity_iterations=2, frames=2)
 
 
 def test_bundle_width_4_and_16_sources(libs):
@@ -94,49 +94,16 @@ def test_ragdolls_all_joint_types_bit_exact(libs):
     assert got["timings"]["constraint_count"] > 60 * 58
 
 
-def test_ragdolls_substepped_servo_variant_bit_exact(libs):
-    """AngularServo variant (RagdollDemo.cs:L199) with 8 substeps x 2 iterations."""
-    _parity(scenes.ragdolls(40, seed=6, motor="servo"), substeps=8, velocity_iterations=2, frames=2)
-
-
-def test_ragdolls_persistent_fast_within_tolerance(libs):
-    """Fast build on joints: relative RMS error <= 1e-3, max abs error <= 2e-2 after one frame (measured ~3e-5 / 1e-3; the twist/servo angle
-    measurements go through acos near 1, which amplifies rounding: see tests/tools/fast_error_stats.py)."""
-    _parity(scenes.ragdolls(60, seed=5), exact=False, mode=EXEC_PERSISTENT, rel_rms=1e-3, max_abs=2e-2, substeps=1, velocity_iterations=4)
-
-
-@pytest.mark.parametrize("scene_name", ["pile", "nonconvex", "ragdolls", "fallback", "mixed_bodies"])
-def test_dataflow_mode_bit_exact(libs, scene_name):
-    """Per-body version dependencies instead of a barrier per (batch, stage): same Gauss-Seidel order per body, so bit-identical results."""
-    if scene_name == "pile":
-        _parity(scenes.shape_pile(5000, seed=11), mode=EXEC_DATAFLOW, substeps=4, velocity_iterations=2, frames=3)
-    elif scene_name == "nonconvex":
-        _parity(scenes.shape_pile(2000, seed=7, nonconvex_fraction=0.5), mode=EXEC_DATAFLOW, substeps=3, velocity_iterations=[1, 2, 3], frames=2)
-    elif scene_name == "ragdolls":
-        _parity(scenes.ragdolls(60, seed=5), mode=EXEC_DATAFLOW, substeps=2, velocity_iterations=3, frames=3)
-    elif scene_name == "fallback":
-        _parity(scenes.fallback_stress(600, hubs=3, seed=5), mode=EXEC_DATAFLOW, fallback_batch_threshold=8, substeps=2, velocity_iterations=2, frames=2)
-    else:
-        scene = scenes.box_stacks(4, 4)
-        extra = scenes.make_bodies(np.array([[100, 5, 0], [120, 5, 0]], dtype=np.float32), linear=np.array([[1, 2, 3], [0, 0, 0]], dtype=np.float32),
-                                   angular=np.array([[0.5, 0.1, -0.3], [0, 1, 0]], dtype=np.float32), inverse_mass=np.array([1, 0], dtype=np.float32),
-                                   inverse_inertia=np.array([[2, 0, 2, 0, 0, 2], [0, 0, 0, 0, 0, 0]], dtype=np.float32))
-        scene["bodies"] = np.concatenate([scene["bodies"], extra])
-        scene["bodies"][0, 8:11] = (0.2, 0.0, 0.1)
-        integ = util.bp.IntegratorDesc.default()
-        integ.angular_integration_mode = 1
-        _parity(scene, mode=EXEC_DATAFLOW, substeps=3, velocity_iterations=2, integrator=integ, frames=2)
-
-
-def test_dataflow_device_resident_frames_keep_versions(libs):
-    """Several solves without re-uploading bodies: the version counters keep running across frames."""
+def test_device_resident_frames_without_reupload(libs):
+    """Several solves without re-uploading anything (the bench's device-resident loop): the captured graph is replayed on the state the previous
+    solve left on the device."""
     import bepuphysics2_b200 as bp
 
     scene = scenes.shape_pile(2000, seed=13)
     a = util.make_sim(scene, substeps=2, velocity_iterations=2)
     b = util.make_sim(scene, substeps=2, velocity_iterations=2)
     ref = util.run_oracle(a, DT, frames=4)
-    ts = bp.CudaTimestepper(b, strict_fp=True, execution_mode=EXEC_DATAFLOW)
+    ts = bp.CudaTimestepper(b, strict_fp=True, execution_mode=EXEC_GRAPH)
     ts.describe()
     for _ in range(3):
         ts.solve_device_only(DT)
@@ -144,6 +111,17 @@ def test_dataflow_device_resident_frames_keep_versions(libs):
     ts.download_prestep()
     ts.close()
     util.compare(ref, util.snapshot(b), exact=True)
+
+
+def test_ragdolls_substepped_servo_variant_bit_exact(libs):
+    """AngularServo variant (RagdollDemo.cs:L199) with 8 substeps x 2 iterations."""
+    _parity(scenes.ragdolls(40, seed=6, motor="servo"), substeps=8, velocity_iterations=2, frames=2)
+
+
+def test_ragdolls_stream_mode_fast_within_tolerance(libs):
+    """Fast build on joints: relative RMS error <= 1e-3, max abs error <= 2e-2 after one frame (measured ~3e-5 / 1e-3; the twist/servo angle
+    measurements go through acos near 1, which amplifies rounding: see tests/tools/fast_error_stats.py)."""
+    _parity(scenes.ragdolls(60, seed=5), exact=False, mode=EXEC_STREAM, rel_rms=1e-3, max_abs=2e-2, substeps=1, velocity_iterations=4)
 
 
 def test_registered_host_buffers_refresh_flow_bit_exact(libs):
@@ -177,7 +155,7 @@ def test_each_remaining_joint_type_bit_exact(libs, type_id):
     assert got["timings"]["constraint_count"] == 150
 
 
-@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_STREAM])
 def test_joint_zoo_all_types_together_all_execution_modes(libs, mode):
     """All 22 remaining types in one scene (many batches, kinematic partners, 3- and 4-body constraints) in every execution mode."""
     _parity(scenes.joint_zoo(1500, 120, seed=6), mode=mode, substeps=2, velocity_iterations=2, frames=2)
@@ -197,7 +175,7 @@ def test_joint_zoo_fast_build_within_tolerance(libs):
     _parity(scenes.joint_zoo(1500, 120, seed=6), exact=False, rel_rms=1e-3, max_abs=5e-2, substeps=2, velocity_iterations=2)
 
 
-@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_STREAM])
 def test_edge_cases_no_constraints_single_body_and_per_substep_iteration_schedule(libs, mode):
     """Degenerate inputs through the whole C-ABI sequence: bodies without any constraint (only IntegrateAfterSubstepping runs), a single constrained
     body, a one-constraint scene, and a per-substep velocity-iteration schedule that contains a zero."""
@@ -227,7 +205,7 @@ def test_randomised_mixed_scenes_bit_exact(libs, seed):
     integ = util.bp.IntegratorDesc.default()
     integ.angular_integration_mode = int(rng.integers(0, 3))
     integ.allow_substeps_for_unconstrained = int(rng.integers(0, 2))
-    _parity(scene, mode=int(rng.choice([EXEC_GRAPH, EXEC_STREAM, EXEC_PERSISTENT, EXEC_DATAFLOW])), bundle_width=int(rng.choice([4, 8, 16])),
+    _parity(scene, mode=int(rng.choice([EXEC_GRAPH, EXEC_STREAM])), bundle_width=int(rng.choice([4, 8, 16])),
             fallback_batch_threshold=int(rng.choice([6, 64])), substeps=substeps, velocity_iterations=iterations, integrator=integ, frames=2)
 
 
@@ -322,7 +300,7 @@ def test_sharded_batches_two_ranks_with_exchange_bit_exact(libs):
         assert (np.sum(masks, axis=0) <= 1).all()
 
 
-@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT])
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_STREAM])
 def test_fast_build_is_run_to_run_deterministic(libs, mode):
     """The reference's own determinism harness (Demos/SpecializedTests/DeterminismTest.cs) repeats a simulation and demands bitwise identical
     results. The strict build is bit-identical to the oracle, hence deterministic; this holds the default FMA build to the same standard: no
@@ -333,7 +311,7 @@ def test_fast_build_is_run_to_run_deterministic(libs, mode):
         util.compare(runs[0], other, exact=True)
 
 
-@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM, EXEC_DATAFLOW])
+@pytest.mark.parametrize("mode", [EXEC_GRAPH, EXEC_STREAM])
 def test_kinematic_velocity_integration_all_execution_modes(libs, mode):
     """IntegrateVelocityForKinematics = true (PoseIntegrator.cs:L451-487 first substep, L493-535 later substeps): the callback's gravity and damping
     are applied to constrained kinematic bodies by the prepass, so a moving kinematic ground accelerates under the stacks resting on it, and an

@@ -10,7 +10,7 @@ import torch
 
 import bepuphysics2_b200 as bp
 from bepuphysics2_b200 import scenes
-from bepuphysics2_b200.native import EXEC_DATAFLOW, EXEC_GRAPH, EXEC_PERSISTENT, EXEC_STREAM
+from bepuphysics2_b200.native import EXEC_GRAPH, EXEC_STREAM
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--bodies", type=int, default=100_000)
@@ -32,12 +32,12 @@ print(scene["description"], flush=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
-def run(mode, bps=0, do_flush=True, strict=False, pdl=True):
+def run(mode, do_flush=True, strict=False, pdl=True):
     sim = bp.Simulation(substeps=args.substeps, velocity_iterations=args.iterations)
     t0 = time.time()
     scenes.build(scene, sim)
     build_s = time.time() - t0
-    ts = bp.CudaTimestepper(sim, strict_fp=strict, execution_mode=mode, persistent_blocks_per_sm=bps, disable_pdl=not pdl)
+    ts = bp.CudaTimestepper(sim, strict_fp=strict, execution_mode=mode, disable_pdl=not pdl)
     t0 = time.time()
     ts.describe()
     ts.synchronize()
@@ -52,19 +52,13 @@ def run(mode, bps=0, do_flush=True, strict=False, pdl=True):
         if i >= 3:
             ms.append(t.solve_ms)
     ci = t.constraint_iterations
-    name = {EXEC_GRAPH: "graph", EXEC_PERSISTENT: "persistent", EXEC_STREAM: "stream", EXEC_DATAFLOW: "dataflow"}[mode]
-    print("%-10s bps=%d flush=%d strict=%d pdl=%d : %.3f ms/step (min %.3f)  %.2f G CI/s  batches=%d stages=%d alg=%.1f GB/s  [build %.1fs describe %.2fs]" % (
-        name, bps, do_flush, strict, pdl, np.mean(ms), np.min(ms), ci / np.mean(ms) / 1e6, t.device_batch_count, t.stage_count, t.algorithmic_bytes / np.mean(ms) / 1e6, build_s, describe_s), flush=True)
+    name = {EXEC_GRAPH: "graph", EXEC_STREAM: "stream"}[mode]
+    print("%-10s flush=%d strict=%d pdl=%d : %.3f ms/step (min %.3f)  %.2f G CI/s  batches=%d stages=%d alg=%.1f GB/s  [build %.1fs describe %.2fs]" % (
+        name, do_flush, strict, pdl, np.mean(ms), np.min(ms), ci / np.mean(ms) / 1e6, t.device_batch_count, t.stage_count, t.algorithmic_bytes / np.mean(ms) / 1e6, build_s, describe_s), flush=True)
     ts.close()
 
 
-if os.environ.get("SWEEP", "full") == "dataflow":
-    run(EXEC_GRAPH)
-    for bps in (1, 2):
-        run(EXEC_DATAFLOW, bps)
-    run(EXEC_DATAFLOW, 1, do_flush=False)
-    run(EXEC_DATAFLOW, 1, strict=True)
-elif os.environ.get("SWEEP", "full") == "graph":
+if os.environ.get("SWEEP", "full") == "graph":
     run(EXEC_GRAPH)
     run(EXEC_GRAPH, pdl=False)
 else:
@@ -72,7 +66,6 @@ else:
     run(EXEC_GRAPH, pdl=False)
     run(EXEC_STREAM)
     run(EXEC_STREAM, pdl=False)
-    run(EXEC_PERSISTENT, 1)
     run(EXEC_GRAPH, strict=True)
 
 if args.cpu:

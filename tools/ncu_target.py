@@ -6,7 +6,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bepuphysics2_b200 as bp
 from bepuphysics2_b200 import scenes
-from bepuphysics2_b200.native import EXEC_PERSISTENT, EXEC_STREAM
+from bepuphysics2_b200.native import EXEC_STREAM
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--bodies", type=int, default=100_000)
@@ -14,12 +14,11 @@ ap.add_argument("--scene", default="shape_pile")
 ap.add_argument("--frames", type=int, default=2)
 ap.add_argument("--substeps", type=int, default=8)
 ap.add_argument("--iterations", type=int, default=2)
-ap.add_argument("--persistent", action="store_true")
 args = ap.parse_args()
 scene = scenes.shape_pile(args.bodies, seed=5) if args.scene == "shape_pile" else scenes.ragdolls(args.bodies // 16, seed=5)
 sim = bp.Simulation(substeps=args.substeps, velocity_iterations=args.iterations)
 scenes.build(scene, sim)
-ts = bp.CudaTimestepper(sim, execution_mode=EXEC_PERSISTENT if args.persistent else EXEC_STREAM, disable_pdl=True)
+ts = bp.CudaTimestepper(sim, execution_mode=EXEC_STREAM, disable_pdl=True)
 ts.describe()
 for _ in range(args.frames):
     ts.solve_device_only(1 / 60)

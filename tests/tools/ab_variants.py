@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PKG = os.path.join(ROOT, "bepuphysics2_b200")
 VARIANTS = {
-    "deep16": ["-DBEPU_DEEP_MINB=16"],
+    # name: extra -D flags. Measured and rejected so far (profiles/r02_summary.md): deep16 = -DBEPU_DEEP_MINB=16 (64 registers for deep batches: slower).
 }
 PARITY = "box_stack or shape_pile or fallback or randomised or unconstrained or registered_host or deterministic"
 

@@ -97,9 +97,16 @@ C_ABI_SYMBOLS = [
     "bepucuda_event_record", "bepucuda_event_elapsed_ms", "bepucuda_profile_stages",
     "bepucuda_set_contact_features", "bepucuda_update_contacts", "bepucuda_upload_body_motion", "bepucuda_download_body_motion",
     "bepucuda_shard_export", "bepucuda_shard_import", "bepucuda_shard_set_global", "bepucuda_shard_set_pushes", "bepucuda_shard_set_body_masks", "bepucuda_shard_import_contexts",
-    "bepucuda_color_constraints", "bepucuda_color_hash",
+    "bepucuda_color_constraints", "bepucuda_color_hash", "bepucuda_set_body_shapes", "bepucuda_predict_bounding_boxes",
 ]
 
+
+# bepucuda_body_shape / bepucuda_body_activity (include/bepucuda.h) as numpy record types
+BODY_SHAPE_DTYPE = np.dtype([("type", "<i4"), ("a", "<f4"), ("b", "<f4"), ("c", "<f4"), ("minimum_speculative_margin", "<f4"), ("maximum_speculative_margin", "<f4"),
+                             ("allow_expansion_beyond_speculative_margin", "<i4"), ("reserved", "<i4")])
+BODY_ACTIVITY_DTYPE = np.dtype([("sleep_threshold", "<f4"), ("minimum_timesteps_under_threshold", "u1"), ("timesteps_under_threshold_count", "u1"), ("sleep_candidate", "u1"),
+                                ("reserved", "u1")])
+SHAPE_SPHERE, SHAPE_CAPSULE, SHAPE_BOX, SHAPE_CYLINDER = 0, 1, 2, 4  # Sphere.Id, Capsule.Id, Box.Id, Cylinder.Id of the reference
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
 
@@ -149,6 +156,8 @@ def load_libraries():
     cuda.bepucuda_host_unregister.argtypes = [vp, vp]
     cuda.bepucuda_color_constraints.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     cuda.bepucuda_color_hash.argtypes = [C.c_uint32]
+    cuda.bepucuda_set_body_shapes.argtypes = [vp, vp, i32]
+    cuda.bepucuda_predict_bounding_boxes.argtypes = [vp, f32, vp, vp]
     cuda.bepucuda_color_hash.restype = C.c_uint32
 
     host.bepuhost_create.restype = vp
@@ -373,6 +382,19 @@ class CudaTimestepper:
         self._check(self._cuda.bepucuda_color_constraints(self._ctx, n, slots, refs.ctypes.data, body_count, fallback_batch_threshold, order, None if pr is None else pr.ctypes.data,
                                                           out.ctypes.data, C.byref(count), C.byref(rounds)))
         return out[:n], count.value, rounds.value
+
+    def set_body_shapes(self, shapes):
+        """bepucuda_set_body_shapes: one BODY_SHAPE_DTYPE record per body (static between frames unless a shape changes)."""
+        shapes = np.ascontiguousarray(shapes, dtype=BODY_SHAPE_DTYPE)
+        self._check(self._cuda.bepucuda_set_body_shapes(self._ctx, shapes.ctypes.data, shapes.shape[0]))
+
+    def predict_bounding_boxes(self, dt, activities):
+        """bepucuda_predict_bounding_boxes on the body state resident on the device. `activities` (BODY_ACTIVITY_DTYPE) is updated in place.
+        Returns bounds[n, 8] = {min.xyz, speculative margin, max.xyz, valid}."""
+        assert activities.dtype == BODY_ACTIVITY_DTYPE and activities.flags["C_CONTIGUOUS"]
+        bounds = np.zeros((max(activities.shape[0], 1), 8), dtype=np.float32)
+        self._check(self._cuda.bepucuda_predict_bounding_boxes(self._ctx, dt, activities.ctypes.data, bounds.ctypes.data))
+        return bounds[:activities.shape[0]]
 
     def register_host_buffers(self):
         """Page-locks the simulation's buffers (a C# host would register its BufferPool blocks once)."""

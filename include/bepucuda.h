@@ -192,6 +192,38 @@ typedef struct bepucuda_stage_profile {
 } bepucuda_stage_profile;
 int32_t bepucuda_profile_stages(bepucuda_ctx* ctx, float dt, bepucuda_stage_profile* out);
 
+/* PredictBoundingBoxes on the device: the stage DefaultTimestepper runs right before collision detection
+ * (PoseIntegrator.PredictBoundingBoxes, PoseIntegrator.cs:L307-370, L424-444), over the body state the solver keeps resident. Per active body:
+ * the sleep-candidacy update (UpdateSleepCandidacy, L286-304: |v|^2 + |w|^2 of the CURRENT velocity against BodyActivity.SleepThreshold), the
+ * velocity callback with PrepareForIntegration(dt) applied to a copy of the velocity (the integrated velocity is used for the prediction only and
+ * is not stored, L339; kinematics only when IntegrateVelocityForKinematics), and for the convex primitive shapes the bounding box and speculative
+ * margin BoundingBoxBatcher.ExecuteConvexBatch computes (Collidables/BoundingBoxBatcher.cs:L142-222; IConvexShape.GetBounds of Sphere.cs:L149-160,
+ * Capsule.cs:L226-239, Box.cs:L211-222, Cylinder.cs:L222-235; BoundingBoxHelpers.cs:L12-58).
+ *   bepucuda_body_shape.type: the reference's shape type id -- 0 sphere (a = radius), 1 capsule (a = radius, b = half length), 2 box (a, b, c = half
+ *   width, height, length), 4 cylinder (a = radius, b = half length). Any other value (no shape; triangle, hull, compound, mesh: their bounds stay
+ *   on the host) yields valid = 0 for that body; its activity is still updated.
+ *   bepucuda_body_activity = BodyActivity (BodyProperties.cs:L386-416), updated in place.
+ *   bounds_out: 8 floats per body {min.x, min.y, min.z, speculative margin, max.x, max.y, max.z, valid (1 or 0)}.
+ * Uses the body arrays as they are on the device (after bepucuda_upload_bodies / bepucuda_solve) and the integrator set by bepucuda_set_integrator.
+ * Results are bit-identical to a non-contracting fp32 evaluation of the reference's expressions. Blocks until the outputs are written. */
+typedef struct bepucuda_body_shape {
+    int32_t type;
+    float a, b, c;
+    float minimum_speculative_margin;   /* Collidable.MinimumSpeculativeMargin */
+    float maximum_speculative_margin;   /* Collidable.MaximumSpeculativeMargin */
+    int32_t allow_expansion_beyond_speculative_margin;  /* Collidable.Continuity.AllowExpansionBeyondSpeculativeMargin */
+    int32_t reserved;
+} bepucuda_body_shape;
+typedef struct bepucuda_body_activity {
+    float sleep_threshold;
+    uint8_t minimum_timesteps_under_threshold;
+    uint8_t timesteps_under_threshold_count;
+    uint8_t sleep_candidate;
+    uint8_t reserved;
+} bepucuda_body_activity;
+int32_t bepucuda_set_body_shapes(bepucuda_ctx* ctx, const bepucuda_body_shape* shapes, int32_t body_count);
+int32_t bepucuda_predict_bounding_boxes(bepucuda_ctx* ctx, float dt, bepucuda_body_activity* activities, float* bounds_out);
+
 /* Device-side batch colouring. Replaces, for a whole constraint set at once, the batch search Solver.Add runs per constraint
  * (Solver.cs:L1182-1199: the first batch whose referenced-handle set holds none of the constraint's dynamic bodies; kinematic references never
  * block, GetBlockingBodyHandles L1058-1078; index == fallback_batch_threshold is the fallback batch and accepts everything, TryAllocateInBatch

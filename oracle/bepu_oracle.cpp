@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -915,6 +916,97 @@ extern "C" int32_t oracle_first_fit_batches(int32_t constraint_count, int32_t bo
         }
     }
     return (int32_t)batchReferencedHandles.size();
+}
+
+// ---- PredictBoundingBoxes, one body at a time in scalar fp32 (this file is compiled -ffp-contract=off) --------------------------------
+// PoseIntegrator.PredictBoundingBoxes (PoseIntegrator.cs:L307-370), UpdateSleepCandidacy (L286-304), BoundingBoxBatcher.ExecuteConvexBatch
+// (Collidables/BoundingBoxBatcher.cs:L176-197), IConvexShape.GetBounds of Sphere.cs:L149-160, Capsule.cs:L226-239, Box.cs:L211-222,
+// Cylinder.cs:L222-235, BoundingBoxHelpers.GetAngularBoundsExpansion / GetBoundsExpansion (BoundingBoxHelpers.cs:L12-58).
+struct oracle_body_shape { int32_t type; float a, b, c, minimum_speculative_margin, maximum_speculative_margin; int32_t allow_expansion_beyond_speculative_margin, reserved; };
+struct oracle_body_activity { float sleep_threshold; uint8_t minimum_timesteps_under_threshold, timesteps_under_threshold_count, sleep_candidate, reserved; };
+extern "C" int32_t oracle_predict_bounding_boxes(int32_t body_count, const float* bodies, const oracle_body_shape* shapes, oracle_body_activity* activities, float dt,
+                                                 const float* gravity, float linear_damping, float angular_damping, int32_t integrate_velocity_for_kinematics, float* bounds_out) {
+    auto clamp01 = [](float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); };
+    // Callbacks.PrepareForIntegration(dt), Demos/DemoCallbacks.cs:L79-86
+    const float linearDampingDt = powf(clamp01(1 - linear_damping), dt), angularDampingDt = powf(clamp01(1 - angular_damping), dt);
+    const V3<float> gravityDt = {gravity[0] * dt, gravity[1] * dt, gravity[2] * dt};
+    for (int i = 0; i < body_count; ++i) {
+        const float* b = bodies + (size_t)i * 32;
+        const Q4<float> orientation = {b[0], b[1], b[2], b[3]};
+        const V3<float> position = {b[4], b[5], b[6]};
+        V3<float> linear = {b[8], b[9], b[10]}, angular = {b[12], b[13], b[14]};
+        bool kinematic = true;  // Bodies.IsKinematic, Bodies.cs:L326-331
+        for (int k = 16; k < 23; ++k) { uint32_t bits; std::memcpy(&bits, b + k, 4); kinematic = kinematic && bits == 0u; }
+        const bool integrate = integrate_velocity_for_kinematics != 0 || !kinematic;
+        const float sleepEnergy = length_squared(linear) + length_squared(angular);
+        if (integrate) {  // DemoPoseIntegratorCallbacks.IntegrateVelocity, Demos/DemoCallbacks.cs:L99-104; the result is not stored (PoseIntegrator.cs:L339)
+            linear = scale(add(linear, gravityDt), linearDampingDt);
+            angular = scale(angular, angularDampingDt);
+        }
+        oracle_body_activity& activity = activities[i];
+        if (sleepEnergy > activity.sleep_threshold) {
+            activity.timesteps_under_threshold_count = 0;
+            activity.sleep_candidate = 0;
+        } else if (activity.timesteps_under_threshold_count < 255) {
+            ++activity.timesteps_under_threshold_count;
+            if (activity.timesteps_under_threshold_count >= activity.minimum_timesteps_under_threshold) activity.sleep_candidate = 1;
+        }
+        float* out = bounds_out + (size_t)i * 8;
+        const oracle_body_shape& s = shapes[i];
+        V3<float> max;
+        float maximumRadius, maximumAngularExpansion;
+        if (s.type == 0) {
+            max = {s.a, s.a, s.a};
+            maximumRadius = 0.0f;
+            maximumAngularExpansion = 0.0f;
+        } else if (s.type == 1) {
+            const float radius = s.a, halfLength = s.b;
+            V3<float> segmentOffset = scale(transform_unit_y(orientation), halfLength);
+            segmentOffset = {vabs(segmentOffset.x), vabs(segmentOffset.y), vabs(segmentOffset.z)};
+            max = {segmentOffset.x + radius, segmentOffset.y + radius, segmentOffset.z + radius};
+            maximumRadius = halfLength + radius;
+            maximumAngularExpansion = halfLength;
+        } else if (s.type == 2) {
+            const float HalfWidth = s.a, HalfHeight = s.b, HalfLength = s.c;
+            const M33<float> basis = matrix_from_quaternion(orientation);
+            max.x = vabs(HalfWidth * basis.x.x) + vabs(HalfHeight * basis.y.x) + vabs(HalfLength * basis.z.x);
+            max.y = vabs(HalfWidth * basis.x.y) + vabs(HalfHeight * basis.y.y) + vabs(HalfLength * basis.z.y);
+            max.z = vabs(HalfWidth * basis.x.z) + vabs(HalfHeight * basis.y.z) + vabs(HalfLength * basis.z.z);
+            maximumRadius = vsqrt(HalfWidth * HalfWidth + HalfHeight * HalfHeight + HalfLength * HalfLength);
+            maximumAngularExpansion = maximumRadius - vmin(HalfLength, vmin(HalfHeight, HalfLength));  // Box.cs:L221 as written
+        } else if (s.type == 4) {
+            const float Radius = s.a, HalfLength = s.b;
+            const V3<float> y = transform_unit_y(orientation);
+            const V3<float> squared = {1.0f - y.x * y.x, 1.0f - y.y * y.y, 1.0f - y.z * y.z};
+            max.x = vabs(HalfLength * y.x) + vsqrt(vmax(0.0f, squared.x)) * Radius;
+            max.y = vabs(HalfLength * y.y) + vsqrt(vmax(0.0f, squared.y)) * Radius;
+            max.z = vabs(HalfLength * y.z) + vsqrt(vmax(0.0f, squared.z)) * Radius;
+            maximumRadius = vsqrt(HalfLength * HalfLength + Radius * Radius);
+            maximumAngularExpansion = maximumRadius - vmin(HalfLength, Radius);
+        } else {
+            for (int k = 0; k < 8; ++k) out[k] = 0.0f;
+            continue;
+        }
+        // GetAngularBoundsExpansion
+        const float a = vmin(length(angular) * dt, 3.14159274f / 3.0f);
+        const float a2 = a * a, a4 = a2 * a2, a6 = a4 * a2;
+        const float cosAngleMinusOne = a2 * (-1.0f / 2.0f) + a4 * (1.0f / 24.0f) - a6 * (1.0f / 720.0f);
+        const float angularBoundsExpansion = vmin(maximumAngularExpansion, vsqrt(-2.0f * maximumRadius * maximumRadius * cosAngleMinusOne));
+        float speculativeMargin = length(linear) * dt + angularBoundsExpansion;
+        speculativeMargin = vmax(s.minimum_speculative_margin, vmin(s.maximum_speculative_margin, speculativeMargin));
+        const float maximumBoundsExpansion = s.allow_expansion_beyond_speculative_margin ? 3.40282347e+38f : speculativeMargin;
+        // GetBoundsExpansion
+        const V3<float> linearDisplacement = scale(linear, dt);
+        V3<float> minExpansion = {vmin(0.0f, linearDisplacement.x) - angularBoundsExpansion, vmin(0.0f, linearDisplacement.y) - angularBoundsExpansion, vmin(0.0f, linearDisplacement.z) - angularBoundsExpansion};
+        V3<float> maxExpansion = {vmax(0.0f, linearDisplacement.x) + angularBoundsExpansion, vmax(0.0f, linearDisplacement.y) + angularBoundsExpansion, vmax(0.0f, linearDisplacement.z) + angularBoundsExpansion};
+        minExpansion = {vmax(-maximumBoundsExpansion, minExpansion.x), vmax(-maximumBoundsExpansion, minExpansion.y), vmax(-maximumBoundsExpansion, minExpansion.z)};
+        maxExpansion = {vmin(maximumBoundsExpansion, maxExpansion.x), vmin(maximumBoundsExpansion, maxExpansion.y), vmin(maximumBoundsExpansion, maxExpansion.z)};
+        const V3<float> bundleMin = add(position, add(neg(max), minExpansion));
+        const V3<float> bundleMax = add(position, add(max, maxExpansion));
+        out[0] = bundleMin.x; out[1] = bundleMin.y; out[2] = bundleMin.z; out[3] = speculativeMargin;
+        out[4] = bundleMax.x; out[5] = bundleMax.y; out[6] = bundleMax.z; out[7] = 1.0f;
+    }
+    return 0;
 }
 
 extern "C" int32_t oracle_max_threads(void) {

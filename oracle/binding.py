@@ -135,3 +135,20 @@ def first_fit_batches(refs, body_count, fallback_threshold=64, order=0, prioriti
     if count < 0:
         raise ValueError("oracle_first_fit_batches failed: %d" % count)
     return out, count
+
+
+def predict_bounding_boxes(bodies, shapes, activities, dt, integrator):
+    """PoseIntegrator.PredictBoundingBoxes restated (PoseIntegrator.cs:L307-370): bodies[n, 32], shapes / activities as the record arrays of
+    bepuphysics2_b200.native (activities updated in place). Returns bounds[n, 8] = {min.xyz, speculative margin, max.xyz, valid}."""
+    lib = load()
+    bodies = np.ascontiguousarray(bodies, dtype=np.float32).reshape(-1, 32)
+    n = bodies.shape[0]
+    assert shapes.shape[0] == n and activities.shape[0] == n and shapes.dtype.itemsize == 32 and activities.dtype.itemsize == 8
+    shapes = np.ascontiguousarray(shapes)
+    bounds = np.zeros((max(n, 1), 8), dtype=np.float32)
+    gravity = (C.c_float * 3)(*integrator.gravity)
+    lib.oracle_predict_bounding_boxes.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_void_p]
+    rc = lib.oracle_predict_bounding_boxes(n, bodies.ctypes.data, shapes.ctypes.data, activities.ctypes.data, dt, gravity, integrator.linear_damping, integrator.angular_damping,
+                                           int(integrator.integrate_velocity_for_kinematics), bounds.ctypes.data)
+    assert rc == 0
+    return bounds[:n]

@@ -42,7 +42,13 @@ JOINT_FILES = ["BallSocketShared", "BallSocket", "AngularHinge", "AngularSwivelH
                "LinearAxisMotor", "LinearAxisLimit", "AngularAxisMotor", "OneBodyAngularServo", "OneBodyAngularMotor", "OneBodyLinearServo", "OneBodyLinearMotor",
                "SwivelHinge", "Hinge", "BallSocketMotor", "BallSocketServo", "AngularAxisGearMotor", "CenterDistanceLimit"]
 SOURCES += [(CON + f + ".cs", None) for f in JOINT_FILES]
+# PredictBoundingBoxes: the wide GetBounds of the convex primitives and the expansion helpers
+SOURCES += [("BepuPhysics/BoundingBoxHelpers.cs", ["BoundingBoxHelpers"]), ("BepuPhysics/Collidables/Capsule.cs", ["CapsuleWide"]),
+            ("BepuPhysics/Collidables/Box.cs", ["BoxWide"]), ("BepuPhysics/Collidables/Cylinder.cs", ["CylinderWide"])]
 
+# Types of which only the named methods are taken (the rest of the type needs shapes, rays, narrow types ... outside this path).
+ONLY_METHODS = {"CapsuleWide": {"GetBounds"}, "BoxWide": {"GetBounds"}, "CylinderWide": {"GetBounds"},
+                "BoundingBoxHelpers": {"GetAngularBoundsExpansion", "GetBoundsExpansion"}}
 # Types never emitted: descriptions (narrow <-> wide scatter code), type processors, interfaces.
 SKIP_TYPE = re.compile(r"TypeProcessor$|^I[A-Z]\w*$|^NonconvexConstraintHelpers$|^ConvexConstraintHelpers$")
 # A member is skipped (not an error) when its text needs something outside the hot-path arithmetic.
@@ -243,6 +249,8 @@ def parse_type(kind, name, generic, body):
                 if mm.group(4):
                     meth.generic = [g.strip() for g in mm.group(4).strip("<>").split(",")]
             else:
+                continue
+            if name in ONLY_METHODS and meth.name not in ONLY_METHODS[name]:
                 continue
             meth.params = parse_params(ptext)
             if meth.params is None or brace is None:
@@ -697,6 +705,30 @@ def harness(tr, layouts):
             "    return -1;", "}",
             "// MathHelper.Sin / Cos / Acos (BepuUtilities/MathHelper.cs:L274-362): the custom approximations every orientation integration goes through.",
             'extern "C" float ref_math(int fn, float x) { Vector<float> v(x); return fn == 0 ? MathHelper::Sin(v).v : fn == 1 ? MathHelper::Cos(v).v : MathHelper::Acos(v).v; }',
+            "// Convex-primitive bounds of PredictBoundingBoxes: transpiled CapsuleWide / BoxWide / CylinderWide.GetBounds and BoundingBoxHelpers.GetAngularBoundsExpansion /",
+            "// GetBoundsExpansion, glued exactly like BoundingBoxBatcher.ExecuteConvexBatch (Collidables/BoundingBoxBatcher.cs:L176-197) glues them. SphereWide.GetBounds",
+            "// (Sphere.cs:L149-160: max = radius, min = -radius, no angular expansion) is three assignments and is written out here (its `new Vector3Wide(ref x)` overload pair has no C++ counterpart).",
+            "// in: type, dims[3], margins {min, max}, allow, orientation[4], position[3], linear[3], angular[3] (velocity AFTER the callback), dt; out: min.xyz, margin, max.xyz.",
+            'extern "C" int ref_convex_bounds(int type, const float* dims, const float* margins, int allow, const float* q, const float* pos, const float* lin, const float* ang, float dt, float* out) {',
+            "    QuaternionWide orientations = quat(q); Vector3Wide positions = vec3(pos); BodyVelocityWide velocities; velocities.Linear = vec3(lin); velocities.Angular = vec3(ang);",
+            "    Vector<float> maximumRadius, maximumAngularExpansion; Vector3Wide bundleMin, bundleMax; Vector<float> dtWide(dt);",
+            "    if (type == 0) { maximumRadius = Vector<float>(0.0f); maximumAngularExpansion = Vector<float>(0.0f); Vector<float> Radius(dims[0]); Vector<float> negatedRadius = -Radius;",
+            "        bundleMax.X = Radius; bundleMax.Y = Radius; bundleMax.Z = Radius; bundleMin.X = negatedRadius; bundleMin.Y = negatedRadius; bundleMin.Z = negatedRadius; }",
+            "    else if (type == 1) { CapsuleWide s; s.Radius = dims[0]; s.HalfLength = dims[1]; s.GetBounds(orientations, 1, maximumRadius, maximumAngularExpansion, bundleMin, bundleMax); }",
+            "    else if (type == 2) { BoxWide s; s.HalfWidth = dims[0]; s.HalfHeight = dims[1]; s.HalfLength = dims[2]; s.GetBounds(orientations, 1, maximumRadius, maximumAngularExpansion, bundleMin, bundleMax); }",
+            "    else if (type == 4) { CylinderWide s; s.Radius = dims[0]; s.HalfLength = dims[1]; s.GetBounds(orientations, 1, maximumRadius, maximumAngularExpansion, bundleMin, bundleMax); }",
+            "    else return -1;",
+            "    Vector<float> angularSpeed; Vector3Wide::Length(velocities.Angular, angularSpeed); Vector<float> linearSpeed; Vector3Wide::Length(velocities.Linear, linearSpeed);",
+            "    auto angularBoundsExpansion = BoundingBoxHelpers::GetAngularBoundsExpansion(angularSpeed, dtWide, maximumRadius, maximumAngularExpansion);",
+            "    auto speculativeMargin = linearSpeed * dtWide + angularBoundsExpansion;",
+            "    speculativeMargin = VectorOps::Max(Vector<float>(margins[0]), VectorOps::Min(Vector<float>(margins[1]), speculativeMargin));",
+            "    auto maximumBoundsExpansion = VectorOps::ConditionalSelect(Vector<int>(allow ? -1 : 0), Vector<float>(3.40282347e+38f), speculativeMargin);",
+            "    Vector3Wide minExpansion, maxExpansion; BoundingBoxHelpers::GetBoundsExpansion(velocities.Linear, dtWide, angularBoundsExpansion, minExpansion, maxExpansion);",
+            "    Vector3Wide negated; negated.X = -maximumBoundsExpansion; negated.Y = -maximumBoundsExpansion; negated.Z = -maximumBoundsExpansion;",
+            "    minExpansion.X = VectorOps::Max(negated.X, minExpansion.X); minExpansion.Y = VectorOps::Max(negated.Y, minExpansion.Y); minExpansion.Z = VectorOps::Max(negated.Z, minExpansion.Z);",
+            "    maxExpansion.X = VectorOps::Min(maximumBoundsExpansion, maxExpansion.X); maxExpansion.Y = VectorOps::Min(maximumBoundsExpansion, maxExpansion.Y); maxExpansion.Z = VectorOps::Min(maximumBoundsExpansion, maxExpansion.Z);",
+            "    bundleMin = positions + (bundleMin + minExpansion); bundleMax = positions + (bundleMax + maxExpansion);",
+            "    out[0] = bundleMin.X.v; out[1] = bundleMin.Y.v; out[2] = bundleMin.Z.v; out[3] = speculativeMargin.v; out[4] = bundleMax.X.v; out[5] = bundleMax.Y.v; out[6] = bundleMax.Z.v; return 0; }",
             'extern "C" int ref_covered_types(int* ids, int capacity) { static const int k[] = {%s}; int n = (int)(sizeof(k) / sizeof(k[0])); for (int i = 0; i < n && i < capacity; ++i) ids[i] = k[i]; return n; }' % ", ".join(map(str, covered))]
     return "\n".join(out) + "\n"
 

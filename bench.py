@@ -500,6 +500,31 @@ def main():
         colouring["host_solver_add_what"] = "Bodies.Add + Solver.Add of every constraint in the C++ host mirror, one thread (batch search AND writing the type batches)"
         del host_sim
 
+    # ---- PredictBoundingBoxes on the resident body state: wall clock of the C-ABI call, i.e. activities up (8 B / body), the kernel,
+    # ---- bounds + margins + activities down (40 B / body)
+    predict = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        from bepuphysics2_b200 import native as native_mod
+
+        rng = np.random.default_rng(3)
+        nb = sim.body_count
+        shapes = np.zeros(nb, dtype=native_mod.BODY_SHAPE_DTYPE)
+        shapes["type"] = rng.choice([0, 1, 2, 4], size=nb)
+        shapes["a"], shapes["b"], shapes["c"] = rng.uniform(0.3, 1.5, size=(3, nb)).astype(np.float32)
+        shapes["maximum_speculative_margin"] = 3.40282347e+38
+        shapes["allow_expansion_beyond_speculative_margin"] = 1
+        activities = np.zeros(nb, dtype=native_mod.BODY_ACTIVITY_DTYPE)
+        activities["sleep_threshold"], activities["minimum_timesteps_under_threshold"] = 0.01, 32
+        ts.set_body_shapes(shapes)
+        for _ in range(2):
+            ts.predict_bounding_boxes(DT, activities)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            bounds = ts.predict_bounding_boxes(DT, activities)
+        p_ms = (time.perf_counter() - t0) * 1e3 / 10
+        predict = {"bodies": int(nb), "ms_per_call": p_ms, "bodies_per_s": nb / (p_ms * 1e-3), "valid_bounds": int((bounds[:, 7] == 1).sum()),
+                   "what": "bepucuda_predict_bounding_boxes through the C ABI, pageable host buffers: 8 B / body up, 40 B / body down, one kernel (168 B / body of HBM traffic)"}
+
     configs = None
     if rank == 0 and world == 1 and not args.no_configs and args.scene == "shape_pile":
         ts.close()
@@ -583,6 +608,8 @@ def main():
             line["e2e_resident_impulses"] = resident
         if colouring is not None:
             line["device_colouring"] = colouring
+        if predict is not None:
+            line["predict_bounding_boxes"] = predict
         if configs is not None:
             line["configs"] = configs
         if sharded is not None:

@@ -43,11 +43,39 @@ def _digest(sources, flag_sets):
 
 
 def _stamp_matches(stamp, digest):
+    """Line 1 of the stamp: digest of the sources the library was built from (line 2: sha256 of the library itself, see binary_matches_stamp)."""
     try:
         with open(stamp) as f:
-            return f.read().strip() == digest
+            return f.read().split("\n")[0].strip() == digest
     except OSError:
         return False
+
+
+def _sha256(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for block in iter(lambda: f.read(1 << 20), b""):
+            h.update(block)
+    return h.hexdigest()
+
+
+def _write_stamp(stamp, digest, lib):
+    with open(stamp, "w") as f:
+        f.write(digest + "\n" + _sha256(lib) + "\n")
+
+
+def binary_matches_stamp(lib=None):
+    """True / False when the stamp next to the library records the library's own hash and it does / does not match the file (a stale or foreign
+    binary next to a fresh stamp); None when there is no such record (stamp missing or written by an older build script)."""
+    lib = lib or LIB_CUDA
+    try:
+        with open(lib + ".stamp") as f:
+            lines = f.read().split("\n")
+    except OSError:
+        return None
+    if len(lines) < 2 or len(lines[1].strip()) != 64:
+        return None
+    return lines[1].strip() == _sha256(lib)
 
 
 def _run(cmd):
@@ -79,8 +107,7 @@ def build(force=False, verbose=False, variant=None, defines=()):
     if not force and not defines and fresh:
         units = []
         if not os.path.exists(stamp):
-            with open(stamp, "w") as f:
-                f.write(digest + "\n")
+            _write_stamp(stamp, digest, LIB_CUDA)
     jobs = []
     for obj, src, extra in units:
         o = os.path.join(BUILD, obj)
@@ -99,8 +126,7 @@ def build(force=False, verbose=False, variant=None, defines=()):
     if units and (force or _newer(LIB_CUDA, objs) or not _stamp_matches(stamp, digest)):
         _run([NVCC] + NVCC_FLAGS + ["-shared", "-o", LIB_CUDA] + objs)
     if units and not os.environ.get("BEPUCUDA_FREEZE_UNITS"):
-        with open(stamp, "w") as f:
-            f.write(digest + "\n")
+        _write_stamp(stamp, digest, LIB_CUDA)
     if variant:
         return LIB_CUDA, LIB_HOST
     host_src = os.path.join(CSRC, "host", "bepu_host.cpp")

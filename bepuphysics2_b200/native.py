@@ -122,6 +122,11 @@ def load_libraries():
     for p in (cuda_path, host_path):
         if not os.path.exists(p):
             raise ImportError("%s is missing: run `python -m bepuphysics2_b200._build` (or __graft_entry__.build()); there is no CPU fallback" % p)
+    if not variant:
+        from . import _build
+
+        if _build.binary_matches_stamp(cuda_path) is False:
+            raise ImportError("%s does not match the hash recorded in its stamp (a stale or foreign binary): rebuild with `python -m bepuphysics2_b200._build --force`" % cuda_path)
     cuda = C.CDLL(cuda_path, mode=C.RTLD_GLOBAL)
     host = C.CDLL(host_path)
     vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float

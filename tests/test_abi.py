@@ -126,3 +126,24 @@ def test_csharp_timestepper_follows_the_reference_scheduler_rule_and_checks_the_
     sim = bp.Simulation(substeps=4, velocity_iterations=3)
     sim.set_solve_description(4, 3, velocity_iteration_scheduler=lambda i: [2, 0, -1, 5][i])
     assert sim.velocity_iterations == [2, 3, 3, 5]
+
+
+def test_library_binary_matches_its_stamp(libs):
+    """The stamp next to libbepucuda.so records a digest of the sources AND the sha256 of the binary built from them; the loader refuses a binary
+    that does not match (a stale or foreign .so next to a fresh stamp)."""
+    import shutil
+    import tempfile
+
+    from bepuphysics2_b200 import _build
+
+    assert _build.binary_matches_stamp() is True
+    with tempfile.TemporaryDirectory() as d:
+        lib = os.path.join(d, "libbepucuda.so")
+        shutil.copy(_build.LIB_CUDA, lib)
+        shutil.copy(_build.LIB_CUDA + ".stamp", lib + ".stamp")
+        assert _build.binary_matches_stamp(lib) is True
+        with open(lib, "ab") as f:
+            f.write(b"\0")
+        assert _build.binary_matches_stamp(lib) is False
+        os.remove(lib + ".stamp")
+        assert _build.binary_matches_stamp(lib) is None

@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round 2, GPU call 17: full GPU test-suite (incl. PredictBoundingBoxes and colouring), smoke, bench both arms on the current build.
+# Round 2, GPU call 20: full GPU test-suite (incl. PredictBoundingBoxes and colouring), smoke, bench both arms on the current build.
 mkdir -p gpurun_out
-P=gpurun_out/r2c17
+P=gpurun_out/r2c20
 (time timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -8) > ${P}_tests.log 2>&1
 (time timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')") > ${P}_smoke.log 2>&1
 (time timeout 900 python bench.py > ${P}_bench.json 2> ${P}_bench.err) 2> ${P}_bench_time.log

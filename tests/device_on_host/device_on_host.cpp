@@ -123,3 +123,17 @@ extern "C" int32_t device_on_host_eval_integration(int32_t op, const float* in, 
     }
     return 0;
 }
+
+// PredictBoundingBoxes arithmetic of csrc/bepu_bounds_math.cuh (same operand layout as ref_convex_bounds of the transpiled reference's harness).
+#include "bepu_bounds_math.cuh"
+extern "C" int32_t device_on_host_convex_bounds(int32_t type, const float* dims, const float* margins, int32_t allow, const float* q, const float* pos, const float* lin, const float* ang,
+                                                float dt, float* out) {
+    using namespace BEPU_NS;
+    if (!(type == 0 || type == 1 || type == 2 || type == 4)) return -1;
+    const ConvexShape shape = {type, dims[0], dims[1], dims[2], margins[0], margins[1], allow};
+    V3 mn, mx;
+    float margin;
+    convex_bounds(shape, Q4{q[0], q[1], q[2], q[3]}, V3{pos[0], pos[1], pos[2]}, Velocity{{lin[0], lin[1], lin[2]}, {ang[0], ang[1], ang[2]}}, dt, mn, mx, margin);
+    out[0] = mn.x; out[1] = mn.y; out[2] = mn.z; out[3] = margin; out[4] = mx.x; out[5] = mx.y; out[6] = mx.z;
+    return 0;
+}

@@ -27,7 +27,7 @@ DT = 1.0 / 240.0  # a substep of the 8 x 2 configuration at 1/30 s
 def device_on_host():
     lib = os.path.join(HERE, "libdevice_on_host.so")
     defines = []
-    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh", "bepu_integration.cuh")]
+    srcs = [os.path.join(HERE, "device_on_host.cpp"), os.path.join(HERE, "stubs", "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("bepu_device_math.cuh", "bepu_contacts.cuh", "bepu_joints.cuh", "bepu_joints_more.cuh", "bepu_integration.cuh", "bepu_bounds_math.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-pthread"] + defines +
                               ["-I", os.path.join(HERE, "stubs"), "-I", HERE, "-I", CSRC, "-shared", "-fPIC", "-o", lib, srcs[0]])
@@ -144,3 +144,22 @@ def test_device_integration_source_matches_the_oracle_bit_for_bit(libs, device_o
             assert orc.oracle_eval_integration(op, _ptr(operands), _ptr(b)) == 0
             assert np.isfinite(b).all()
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "integration op %d, trial %d: %s vs %s" % (op, trial, a, b)
+
+
+def test_bounds_source_reproduces_the_reference_vectors_bit_for_bit(device_on_host):
+    """csrc/bepu_bounds_math.cuh (the arithmetic of bepucuda_predict_bounding_boxes) compiled for the host against the known-answer vectors generated
+    from the reference's own C# text (tests/golden/reference_bounds_vectors.npz): the CUDA source of f4 is pinned to the reference without a GPU."""
+    dev, _ = device_on_host
+    fp = C.POINTER(C.c_float)
+    dev.device_on_host_convex_bounds.argtypes = [C.c_int32, fp, fp, C.c_int32, fp, fp, fp, fp, C.c_float, fp]
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "reference_bounds_vectors.npz"))
+    checked = 0
+    for k in (0, 1):
+        types, dims, margins, allow, q, pos, lin, ang = (np.ascontiguousarray(golden["set%d_%s" % (k, n)]) for n in ("types", "dims", "margins", "allow", "q", "pos", "lin", "ang"))
+        dt, want = float(golden["set%d_dt" % k]), golden["set%d_out" % k]
+        for i in range(types.shape[0]):
+            out = np.zeros(7, dtype=np.float32)
+            assert dev.device_on_host_convex_bounds(int(types[i]), _ptr(dims[i]), _ptr(margins[i]), int(allow[i]), _ptr(q[i]), _ptr(pos[i]), _ptr(lin[i]), _ptr(ang[i]), dt, _ptr(out)) == 0
+            assert np.array_equal(out.view(np.uint32), want[i].view(np.uint32)), "set %d sample %d (shape type %d)" % (k, i, types[i])
+            checked += 1
+    assert checked == 96

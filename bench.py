@@ -479,8 +479,14 @@ def main():
 
     # ---- device-side batch colouring of this workload's constraint list: bepucuda_color_constraints vs the host mirror's
     # ---- sequential Solver.Add batch search (C++, one thread), wall clock including the reference upload and the batch-index download
-    colouring = None
-    if rank == 0 and world == 1 and not args.no_configs:
+    def side_block(fn):
+        """A side block never takes the headline line down with it: on failure its entry carries the error text instead."""
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            return {"error": "%s: %s" % (type(e).__name__, e)}
+
+    def measure_colouring():
         from bepuphysics2_b200 import coloring
 
         scene_for_refs = make_scene(args, 5)
@@ -499,11 +505,13 @@ def main():
         colouring["host_solver_add_ms"] = (time.perf_counter() - t0) * 1e3
         colouring["host_solver_add_what"] = "Bodies.Add + Solver.Add of every constraint in the C++ host mirror, one thread (batch search AND writing the type batches)"
         del host_sim
+        return colouring
+
+    colouring = side_block(measure_colouring) if rank == 0 and world == 1 and not args.no_configs else None
 
     # ---- PredictBoundingBoxes on the resident body state: wall clock of the C-ABI call, i.e. activities up (8 B / body), the kernel,
     # ---- bounds + margins + activities down (40 B / body)
-    predict = None
-    if rank == 0 and world == 1 and not args.no_configs:
+    def measure_predict():
         from bepuphysics2_b200 import native as native_mod
 
         rng = np.random.default_rng(3)
@@ -524,6 +532,9 @@ def main():
         p_ms = (time.perf_counter() - t0) * 1e3 / 10
         predict = {"bodies": int(nb), "ms_per_call": p_ms, "bodies_per_s": nb / (p_ms * 1e-3), "valid_bounds": int((bounds[:, 7] == 1).sum()),
                    "what": "bepucuda_predict_bounding_boxes through the C ABI, pageable host buffers: 8 B / body up, 40 B / body down, one kernel (168 B / body of HBM traffic)"}
+        return predict
+
+    predict = side_block(measure_predict) if rank == 0 and world == 1 and not args.no_configs else None
 
     configs = None
     if rank == 0 and world == 1 and not args.no_configs and args.scene == "shape_pile":
@@ -532,7 +543,7 @@ def main():
         peak_for_configs, _ = load_peaks()
         configs = {}
         for key, overrides in side_configs(args):
-            configs[key] = measure_config(args, overrides, torch, bp, modes, flush, peak_for_configs, args.config_steps, with_cpu=not args.no_cpu_baseline)
+            configs[key] = side_block(lambda: measure_config(args, overrides, torch, bp, modes, flush, peak_for_configs, args.config_steps, with_cpu=not args.no_cpu_baseline))
 
     # ---- N > 1: ONE constraint graph over the N GPUs, next to the N independent islands above: the 1M-body pile of configs[4],
     # ---- constraints split by body slab, shared body records pushed over NVLink by the stage kernels (bepucuda_shard_*); strong scaling
